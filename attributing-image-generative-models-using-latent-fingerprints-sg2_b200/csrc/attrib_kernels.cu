@@ -1,0 +1,154 @@
+// Fingerprint embed (w0 = U^T alpha + mu, wx = w0 + sd V^T diag(sigma) sigmoid(key)) and the MSE
+// loss glue of the attribution loop, batched over trajectories (C-ABI group 4).
+// Reference: src/main.py:60-61, src/generator.py:148-161, src/utils.py:46-47.
+#include "common.cuh"
+
+namespace lfp {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// one thread per (b, j): coalesced over j in U[i][j] and V[k][j]
+__global__ void __launch_bounds__(128) embed_fwd_kernel(const float* __restrict__ alpha,
+                                                        const float* __restrict__ key,
+                                                        const float* __restrict__ U,
+                                                        const float* __restrict__ V,
+                                                        const float* __restrict__ sigma,
+                                                        const float* __restrict__ mu, float sd,
+                                                        int n_main, int key_len, int dim,
+                                                        float* __restrict__ w0, float* __restrict__ wx) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int b = blockIdx.y;
+  if (j >= dim) return;
+  float acc = 0.f;
+  for (int i = 0; i < n_main; ++i) acc = fmaf(__ldg(U + (int64_t)i * dim + j), __ldg(alpha + (int64_t)b * n_main + i), acc);
+  const float base = acc + __ldg(mu + j);
+  float e = 0.f;
+  for (int k = 0; k < key_len; ++k)
+    e = fmaf(__ldg(V + (int64_t)k * dim + j) * __ldg(sigma + k), sigmoidf_(__ldg(key + (int64_t)b * key_len + k)), e);
+  w0[(int64_t)b * dim + j] = base;
+  wx[(int64_t)b * dim + j] = base + sd * e;
+}
+
+// one warp per output element: dot over dim
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ d_wx,
+                                                        const float* __restrict__ key,
+                                                        const float* __restrict__ U,
+                                                        const float* __restrict__ V,
+                                                        const float* __restrict__ sigma, float sd,
+                                                        int n_main, int key_len, int dim,
+                                                        float* __restrict__ d_alpha,
+                                                        float* __restrict__ d_key) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n_main + key_len) return;
+  const float* m = row < n_main ? U + (int64_t)row * dim : V + (int64_t)(row - n_main) * dim;
+  float acc = 0.f;
+  for (int j = lane; j < dim; j += 32) acc = fmaf(__ldg(m + j), __ldg(d_wx + (int64_t)b * dim + j), acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane != 0) return;
+  if (row < n_main) {
+    d_alpha[(int64_t)b * n_main + row] = acc;
+  } else {
+    const int k = row - n_main;
+    const float sg = sigmoidf_(__ldg(key + (int64_t)b * key_len + k));
+    d_key[(int64_t)b * key_len + k] = sd * __ldg(sigma + k) * acc * sg * (1.f - sg);
+  }
+}
+
+// MSE: pass 1 writes d_est and per-CTA partial sums of squared error; pass 2 reduces in order
+__global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ est,
+                                                          const float* __restrict__ target,
+                                                          int64_t target_bstride, int64_t numel_per,
+                                                          float* __restrict__ d_est,
+                                                          float* __restrict__ partial, int chunks) {
+  __shared__ float sm[256];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t per = ceil_div(ceil_div(numel_per, 4), chunks) * 4;
+  const int64_t lo = per * chunk, hi = lo + per < numel_per ? lo + per : numel_per;
+  const float scale = 2.f / (float)numel_per;
+  const float* e = est + (int64_t)b * numel_per;
+  const float* t = target + (int64_t)b * target_bstride;
+  float* g = d_est ? d_est + (int64_t)b * numel_per : nullptr;
+  float acc = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const float d = e[i] - t[i];
+    acc = fmaf(d, d, acc);
+    if (g) g[i] = d * scale;
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(int64_t)b * chunks + chunk] = sm[0];
+}
+__global__ void mse_final_kernel(const float* __restrict__ partial, float* __restrict__ loss, int batch,
+                                 int chunks, float inv_n) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  float acc = 0.f;
+  for (int k = 0; k < chunks; ++k) acc += partial[(int64_t)b * chunks + k];
+  loss[b] = acc * inv_n;
+}
+
+static int mse_chunks(int batch, int64_t numel_per) {
+  int64_t c = ceil_div((int64_t)num_sms() * 8, batch);
+  const int64_t maxc = ceil_div(numel_per, 4096);
+  if (c > maxc) c = maxc;
+  if (c < 1) c = 1;
+  if (c > 2048) c = 2048;
+  return (int)c;
+}
+
+}  // namespace lfp
+
+using namespace lfp;
+
+extern "C" int lfp_embed_forward(const float* alpha, const float* key_logits, const float* U,
+                                 const float* V, const float* sigma_key, const float* mu, float sd,
+                                 int batch, int n_main, int key_len, int dim, float* w0, float* wx,
+                                 void* stream) {
+  LFP_CHECK_ARG(alpha && key_logits && U && V && sigma_key && mu && w0 && wx, "embed_forward: null argument");
+  LFP_CHECK_ARG(batch >= 1 && batch <= 65535 && n_main >= 0 && key_len >= 0 && dim >= 1, "embed_forward: bad extent");
+  dim3 grid((unsigned)ceil_div(dim, 128), (unsigned)batch);
+  embed_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(alpha, key_logits, U, V, sigma_key, mu, sd, n_main, key_len, dim, w0, wx);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lfp_embed_backward(const float* d_wx, const float* key_logits, const float* U,
+                                  const float* V, const float* sigma_key, float sd, int batch,
+                                  int n_main, int key_len, int dim, float* d_alpha, float* d_key,
+                                  void* stream) {
+  LFP_CHECK_ARG(d_wx && key_logits && U && V && sigma_key && d_alpha && d_key, "embed_backward: null argument");
+  LFP_CHECK_ARG(batch >= 1 && batch <= 65535, "embed_backward: bad batch");
+  dim3 grid((unsigned)ceil_div(n_main + key_len, 8), (unsigned)batch);
+  embed_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_wx, key_logits, U, V, sigma_key, sd, n_main, key_len, dim, d_alpha, d_key);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t lfp_mse_scratch_bytes(int batch, int64_t numel_per) {
+  if (batch <= 0 || numel_per <= 0) return 0;
+  return (size_t)batch * mse_chunks(batch, numel_per) * sizeof(float);
+}
+
+extern "C" int lfp_mse_loss_grad(const float* est, const float* target, int target_batch, int batch,
+                                 int64_t numel_per, float* loss, float* d_est, void* scratch,
+                                 size_t scratch_bytes, void* stream) {
+  LFP_CHECK_ARG(est && target && loss && scratch, "mse: null argument");
+  LFP_CHECK_ARG(batch >= 1 && batch <= 65535 && numel_per >= 1, "mse: bad extent");
+  LFP_CHECK_ARG(target_batch == 1 || target_batch == batch, "mse: target batch must be 1 or %d", batch);
+  const int chunks = mse_chunks(batch, numel_per);
+  if (scratch_bytes < (size_t)batch * chunks * sizeof(float)) { set_error("mse: scratch too small"); return LFP_ENOMEM; }
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid((unsigned)chunks, (unsigned)batch);
+  mse_partial_kernel<<<grid, 256, 0, s>>>(est, target, target_batch == 1 ? 0 : numel_per, numel_per, d_est, (float*)scratch, chunks);
+  LFP_LAUNCH_CHECK();
+  mse_final_kernel<<<(unsigned)ceil_div(batch, 128), 128, 0, s>>>((const float*)scratch, loss, batch, chunks, 1.f / (float)numel_per);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}

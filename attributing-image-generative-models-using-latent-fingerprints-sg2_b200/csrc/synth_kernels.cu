@@ -1,0 +1,709 @@
+// Kernels of the fused synthesis path: fp32 CUDA-core gather convolution with fused epilogues,
+// NHWC FIR, ToRGB, activation backward and the small style / demodulation kernels.
+// Algebra: the reference's activation-modulated ("unfused") form, src/model.py:229-256, which
+// keeps the weights shared across the batch and makes the style gradient two reductions
+// (SURVEY.md 7.3 "Style gradient without wgrad").  Reductions use fixed-order partials, so a
+// trajectory's result does not depend on which other trajectories share its batch or GPU.
+#include "synth_kernels.cuh"
+
+namespace lfp {
+
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 c) { return make_float4(fmaf(s, a.x, c.x), fmaf(s, a.y, c.y), fmaf(s, a.z, c.z), fmaf(s, a.w, c.w)); }
+__device__ __forceinline__ float4 f4_fma4(float4 a, float4 b, float4 c) { return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w)); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ float lrelu_fwd(float v) { return (v > 0.f ? v : v * kLreluSlope) * kLreluGain; }
+
+// =============================================================================================
+// Gather convolution, CUDA cores (fp32 path)
+// =============================================================================================
+struct ConvKArgs {
+  const float* in; const float* mod; const float* wtab; float* out;
+  ConvGeom g; ConvEpiArgs e; int seglen;
+};
+
+template <int TN, int EPI, bool MOD>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvKArgs a) {
+  constexpr int KC = 16, TM = 128, LDA = TM + 4;
+  constexpr int NT = TN / 4;    // threads along n
+  constexpr int NG = 256 / NT;  // row groups
+  constexpr int TMR = TM / NG;  // rows per thread (8 for TN=64, 4 for TN=32)
+  __shared__ __align__(16) float As[2][KC][LDA];
+  __shared__ __align__(16) float Bs[2][KC][TN];
+
+  const ConvGeom& g = a.g;
+  const int tid = threadIdx.x;
+  const int pix_per = g.gh * g.gw;
+  const int64_t total_pix = (int64_t)g.batch * pix_per;
+  const int64_t tile0 = (int64_t)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  const int K = g.K, N = g.N;
+
+  // ---- loader roles ----
+  const int a_row = tid >> 2;
+  const int a_kq = (tid & 3) * 4;
+  int lb[2], lgy[2], lgx[2];
+  bool lvalid[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int64_t p = tile0 + a_row + 64 * i;
+    lvalid[i] = p < total_pix;
+    const int64_t pp = lvalid[i] ? p : 0;
+    lb[i] = (int)(pp / pix_per);
+    const int rem = (int)(pp - (int64_t)lb[i] * pix_per);
+    lgy[i] = rem / g.gw;
+    lgx[i] = rem - lgy[i] * g.gw;
+  }
+  const int b_row = tid / NT;
+  const int b_c4 = tid % NT;
+  const bool b_active = b_row < KC && (n0 + b_c4 * 4) < N;
+
+  const int kchunks = K / KC;
+  const int nit = g.ntaps * kchunks;
+
+  float4 ar[2], br;
+  auto load = [&](int it) {
+    const int tap = it / kchunks;
+    const int k0 = (it - tap * kchunks) * KC;
+    const int dy = g.dy[tap], dx = g.dx[tap], wi = g.widx[tap];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int iy = lgy[i] * g.in_stride + dy, ix = lgx[i] * g.in_stride + dx;
+      const bool ok = lvalid[i] && iy >= 0 && iy < g.in_h && ix >= 0 && ix < g.in_w;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) {
+        v = __ldg(reinterpret_cast<const float4*>(a.in + (int64_t)lb[i] * g.in_bstride +
+                                                  ((int64_t)iy * g.in_w + ix) * K + k0 + a_kq));
+        if (MOD) v = f4_mul(v, __ldg(reinterpret_cast<const float4*>(a.mod + (int64_t)lb[i] * K + k0 + a_kq)));
+      }
+      ar[i] = v;
+    }
+    br = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b_active)
+      br = __ldg(reinterpret_cast<const float4*>(a.wtab + ((int64_t)wi * K + k0 + b_row) * N + n0 + b_c4 * 4));
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      As[buf][a_kq + 0][a_row + 64 * i] = ar[i].x;
+      As[buf][a_kq + 1][a_row + 64 * i] = ar[i].y;
+      As[buf][a_kq + 2][a_row + 64 * i] = ar[i].z;
+      As[buf][a_kq + 3][a_row + 64 * i] = ar[i].w;
+    }
+    if (b_row < KC) *reinterpret_cast<float4*>(&Bs[buf][b_row][b_c4 * 4]) = br;
+  };
+
+  const int tm = tid / NT, tn = tid % NT;
+  float acc[TMR][4];
+#pragma unroll
+  for (int r = 0; r < TMR; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  load(0);
+  store(0);
+  __syncthreads();
+  for (int it = 0; it < nit; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < nit) load(it + 1);
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      float av[TMR];
+#pragma unroll
+      for (int q = 0; q < TMR / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[buf][kk][tm * TMR + q * 4]);
+        av[q * 4 + 0] = t.x; av[q * 4 + 1] = t.y; av[q * 4 + 2] = t.z; av[q * 4 + 3] = t.w;
+      }
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tn * 4]);
+#pragma unroll
+      for (int r = 0; r < TMR; ++r) {
+        acc[r][0] = fmaf(av[r], bv.x, acc[r][0]);
+        acc[r][1] = fmaf(av[r], bv.y, acc[r][1]);
+        acc[r][2] = fmaf(av[r], bv.z, acc[r][2]);
+        acc[r][3] = fmaf(av[r], bv.w, acc[r][3]);
+      }
+    }
+    if (it + 1 < nit) store(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const int n = n0 + tn * 4;
+  const bool n_ok = n < N;
+  float4 red = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float nw = 0.f;
+  if (EPI == EPI_ACT && n_ok) {
+    bias4 = __ldg(reinterpret_cast<const float4*>(a.e.bias + n));
+    nw = __ldg(a.e.noise_w);
+  }
+#pragma unroll
+  for (int r = 0; r < TMR; ++r) {
+    const int64_t p = tile0 + tm * TMR + r;
+    if (p >= total_pix || !n_ok) continue;
+    const int b = (int)(p / pix_per);
+    const int rem = (int)(p - (int64_t)b * pix_per);
+    const int gy = rem / g.gw, gx = rem - gy * g.gw;
+    float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    if (EPI == EPI_ACT) {
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.e.demod + (int64_t)b * N + n));
+      const float nz = nw * __ldg(a.e.noise + (int64_t)b * a.e.noise_bstride + rem);
+      v.x = lrelu_fwd(fmaf(v.x, d4.x, nz) + bias4.x);
+      v.y = lrelu_fwd(fmaf(v.y, d4.y, nz) + bias4.y);
+      v.z = lrelu_fwd(fmaf(v.z, d4.z, nz) + bias4.z);
+      v.w = lrelu_fwd(fmaf(v.w, d4.w, nz) + bias4.w);
+    } else if (EPI == EPI_DGRAD) {
+      const float4 xs = __ldg(reinterpret_cast<const float4*>(a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)rem * N + n));
+      red = f4_fma4(xs, v, red);
+      v = f4_mul(v, __ldg(reinterpret_cast<const float4*>(a.e.mod_out + (int64_t)b * N + n)));
+    }
+    if (a.out != nullptr) {
+      const int oy = gy * g.out_stride + g.out_oy, ox = gx * g.out_stride + g.out_ox;
+      *reinterpret_cast<float4*>(a.out + (((int64_t)b * g.out_h + oy) * g.out_w + ox) * N + n) = v;
+    }
+  }
+  if (EPI == EPI_DGRAD) {
+    // fixed-order reduction over the rows of each segment (seglen pixels of one sample)
+    float* redbuf = &As[0][0][0];  // NG x TN floats
+    *reinterpret_cast<float4*>(&redbuf[tm * TN + tn * 4]) = red;
+    __syncthreads();
+    const int gps = a.seglen / TMR;        // row groups per segment
+    const int nseg = TM / a.seglen;        // segments per tile
+    for (int t = tid; t < nseg * TN; t += 256) {
+      const int seg = t / TN, nn = t - seg * TN;
+      const int64_t p0 = tile0 + (int64_t)seg * a.seglen;
+      if (p0 >= total_pix || n0 + nn >= N) continue;
+      float sacc = 0.f;
+      for (int q = 0; q < gps; ++q) sacc += redbuf[(seg * gps + q) * TN + nn];
+      a.e.partial[(p0 / a.seglen) * N + n0 + nn] = sacc;
+    }
+  }
+}
+
+int conv_dgrad_seglen(const ConvGeom& g) {
+  const int hw = g.gh * g.gw;
+  return hw < 128 ? hw : 128;
+}
+
+template <int TN, int EPI>
+static int conv_simt_launch2(const ConvKArgs& ka, bool mod, dim3 grid, cudaStream_t s) {
+  if (mod) conv_simt_kernel<TN, EPI, true><<<grid, 256, 0, s>>>(ka);
+  else conv_simt_kernel<TN, EPI, false><<<grid, 256, 0, s>>>(ka);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_conv_simt(const float* in, const float* mod, const float* wtab, float* out,
+                     const ConvGeom& g, int epi, const ConvEpiArgs& e, cudaStream_t s) {
+  LFP_CHECK_ARG(g.K % 16 == 0 && g.N % 4 == 0, "conv: K=%d must be a multiple of 16, N=%d of 4", g.K, g.N);
+  LFP_CHECK_ARG(g.ntaps >= 1 && g.ntaps <= 9, "conv: bad tap count");
+  ConvKArgs ka{in, mod, wtab, out, g, e, 0};
+  const int64_t total_pix = (int64_t)g.batch * g.gh * g.gw;
+  if (total_pix == 0) return 0;
+  if (epi == EPI_DGRAD) {
+    const int hw = g.gh * g.gw;
+    LFP_CHECK_ARG((hw & (hw - 1)) == 0 && hw >= 8, "dgrad: grid %dx%d must be a power of two >= 8 pixels", g.gh, g.gw);
+    ka.seglen = conv_dgrad_seglen(g);
+  }
+  const int TN = g.N >= 64 ? 64 : 32;
+  dim3 grid((unsigned)ceil_div(total_pix, 128), (unsigned)ceil_div(g.N, TN));
+  const bool m = mod != nullptr;
+  if (TN == 64) {
+    if (epi == EPI_STORE) return conv_simt_launch2<64, EPI_STORE>(ka, m, grid, s);
+    if (epi == EPI_ACT) return conv_simt_launch2<64, EPI_ACT>(ka, m, grid, s);
+    return conv_simt_launch2<64, EPI_DGRAD>(ka, m, grid, s);
+  }
+  if (epi == EPI_STORE) return conv_simt_launch2<32, EPI_STORE>(ka, m, grid, s);
+  if (epi == EPI_ACT) return conv_simt_launch2<32, EPI_ACT>(ka, m, grid, s);
+  return conv_simt_launch2<32, EPI_DGRAD>(ka, m, grid, s);
+}
+
+// =============================================================================================
+// 4x4 FIR on NHWC with a register sliding window (blur after the transposed conv, and its adjoint)
+// =============================================================================================
+template <bool ACT>
+__global__ void __launch_bounds__(256) fir4x4_nhwc_kernel(const float* __restrict__ in,
+                                                          float* __restrict__ out, const FirArgs a,
+                                                          int C4, int PX, int RY) {
+  const int c4 = threadIdx.x % C4;
+  const int px = threadIdx.x / C4;
+  const int ox = blockIdx.x * PX + px;
+  const int oy0 = blockIdx.y * RY;
+  const int b = blockIdx.z;
+  if (px >= PX || ox >= a.out_w) return;
+  float coef[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) coef[i] = __ldg(a.coef + i);
+  const int C = a.C;
+  const float* src = in + (int64_t)b * a.in_h * a.in_w * C + c4 * 4;
+  float4 win[4][4];
+  auto load_row = [&](int iy, float4(&row)[4]) {
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) {
+      const int ix = ox + tx - a.pad;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < a.in_h && ix >= 0 && ix < a.in_w)
+        v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)iy * a.in_w + ix) * C));
+      row[tx] = v;
+    }
+  };
+  load_row(oy0 - a.pad + 0, win[0]);
+  load_row(oy0 - a.pad + 1, win[1]);
+  load_row(oy0 - a.pad + 2, win[2]);
+  float4 d4 = make_float4(1.f, 1.f, 1.f, 1.f), bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float nw = 0.f;
+  if (ACT) {
+    d4 = __ldg(reinterpret_cast<const float4*>(a.demod + (int64_t)b * C + c4 * 4));
+    bias4 = __ldg(reinterpret_cast<const float4*>(a.bias + c4 * 4));
+    nw = __ldg(a.noise_w);
+  }
+  for (int o = 0; o < RY; o += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int oy = oy0 + o + u;
+      if (oy >= a.out_h) return;
+      load_row(oy + 3 - a.pad, win[(u + 3) & 3]);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) acc = f4_fma(coef[r * 4 + tx], win[(u + r) & 3][tx], acc);
+      if (ACT) {
+        const float nz = nw * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox);
+        acc.x = lrelu_fwd(fmaf(acc.x, d4.x, nz) + bias4.x);
+        acc.y = lrelu_fwd(fmaf(acc.y, d4.y, nz) + bias4.y);
+        acc.z = lrelu_fwd(fmaf(acc.z, d4.z, nz) + bias4.z);
+        acc.w = lrelu_fwd(fmaf(acc.w, d4.w, nz) + bias4.w);
+      }
+      *reinterpret_cast<float4*>(out + (((int64_t)b * a.out_h + oy) * a.out_w + ox) * C + c4 * 4) = acc;
+    }
+  }
+}
+
+int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream_t s) {
+  LFP_CHECK_ARG(a.C % 4 == 0 && a.C <= 1024, "fir: C=%d must be a multiple of 4 and <= 1024", a.C);
+  const int C4 = a.C / 4;
+  const int PX = 256 / C4 > 0 ? 256 / C4 : 1;
+  const int RY = 8;
+  dim3 grid((unsigned)ceil_div(a.out_w, PX), (unsigned)ceil_div(a.out_h, RY), (unsigned)a.batch);
+  if (a.act) fir4x4_nhwc_kernel<true><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+  else fir4x4_nhwc_kernel<false><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// ToRGB forward (+ bias + FIR-upsampled skip)
+// =============================================================================================
+__device__ __forceinline__ float up2_sample(const float* __restrict__ sp, int h2, int w2,
+                                            const float* __restrict__ kup, int oy, int ox) {
+  // Upsample: upfirdn2d(up=2, pad=(2,1)) (src/model.py:33-51); flipped tap (ty,tx) = kup[3-ty][3-tx]
+  float acc = 0.f;
+#pragma unroll
+  for (int ty = 0; ty < 4; ++ty) {
+    const int sy = oy + ty - 2;
+    if (sy < 0 || (sy & 1)) continue;
+    const int iy = sy >> 1;
+    if (iy >= h2) continue;
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) {
+      const int sx = ox + tx - 2;
+      if (sx < 0 || (sx & 1)) continue;
+      const int ix = sx >> 1;
+      if (ix >= w2) continue;
+      acc = fmaf(__ldg(sp + (int64_t)iy * w2 + ix), __ldg(kup + (3 - ty) * 4 + (3 - tx)), acc);
+    }
+  }
+  return acc;
+}
+
+template <int LPP, int NCH>
+__global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict__ act,
+                                                        const float* __restrict__ s,
+                                                        const float* __restrict__ wrgb,
+                                                        const float* __restrict__ bias,
+                                                        const float* __restrict__ skip,
+                                                        const float* __restrict__ kup,
+                                                        float* __restrict__ rgb, int h, int w, int C) {
+  constexpr int PPW = 32 / LPP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int hw = h * w;
+  const int pix0 = (blockIdx.x * 8 + warp) * 32;
+  if (pix0 >= hw) return;
+  const int sub = lane / LPP, li = lane % LPP;
+  float4 m[3][NCH];
+#pragma unroll
+  for (int q = 0; q < NCH; ++q) {
+    const int c = (q * LPP + li) * 4;
+    const float4 sv = __ldg(reinterpret_cast<const float4*>(s + (int64_t)b * C + c));
+#pragma unroll
+    for (int o = 0; o < 3; ++o) m[o][q] = f4_mul(sv, __ldg(reinterpret_cast<const float4*>(wrgb + o * C + c)));
+  }
+  float mine[3] = {0.f, 0.f, 0.f};
+  const float* base = act + (int64_t)b * hw * C;
+#pragma unroll 1
+  for (int it = 0; it < LPP; ++it) {
+    const int pix = pix0 + it * PPW + sub;
+    float r[3] = {0.f, 0.f, 0.f};
+    if (pix < hw) {
+#pragma unroll
+      for (int q = 0; q < NCH; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)pix * C + (q * LPP + li) * 4));
+#pragma unroll
+        for (int o = 0; o < 3; ++o) r[o] += f4_dot(v, m[o][q]);
+      }
+    }
+#pragma unroll
+    for (int off = LPP / 2; off > 0; off >>= 1)
+#pragma unroll
+      for (int o = 0; o < 3; ++o) r[o] += __shfl_xor_sync(0xffffffffu, r[o], off);
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const float v = __shfl_sync(0xffffffffu, r[o], (lane % PPW) * LPP);
+      if (lane / PPW == it) mine[o] = v;
+    }
+  }
+  const int pix = pix0 + lane;
+  if (pix < hw) {
+    const int y = pix / w, x = pix - y * w;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      float v = mine[o] + __ldg(bias + o);
+      if (skip != nullptr) v += up2_sample(skip + ((int64_t)b * 3 + o) * (h / 2) * (w / 2), h / 2, w / 2, kup, y, x);
+      rgb[((int64_t)b * 3 + o) * hw + pix] = v;
+    }
+  }
+}
+
+int launch_torgb_fwd(const float* act, const float* s, const float* wrgb, const float* bias,
+                     const float* skip, const float* kup, float* rgb, int batch, int h, int w,
+                     int C, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div((int64_t)h * w, 256), (unsigned)batch);
+#define LFP_TORGB(LPP, NCH) torgb_fwd_kernel<LPP, NCH><<<grid, 256, 0, st>>>(act, s, wrgb, bias, skip, kup, rgb, h, w, C)
+  switch (C) {
+    case 16: LFP_TORGB(4, 1); break;
+    case 32: LFP_TORGB(8, 1); break;
+    case 64: LFP_TORGB(16, 1); break;
+    case 128: LFP_TORGB(32, 1); break;
+    case 256: LFP_TORGB(32, 2); break;
+    case 512: LFP_TORGB(32, 4); break;
+    default: set_error("torgb: unsupported channel count %d", C); return LFP_EUNSUPPORTED;
+  }
+#undef LFP_TORGB
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// Backward through noise / bias / lrelu (+ ToRGB branch), with the two style-gradient reductions
+// =============================================================================================
+__global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdArgs a, int C4, int PX, int seglen) {
+  __shared__ float redT[1024];
+  __shared__ float redR[1024];
+  const int tid = threadIdx.x;
+  const int c4 = tid % C4, py = tid / C4;
+  const bool active = py < PX;
+  const int segs_per = a.hw / seglen;
+  const int seg = blockIdx.x;
+  const int b = seg / segs_per;
+  const int pix0 = (seg - b * segs_per) * seglen;
+  const int C = a.C;
+  const bool has_rgb = a.drgb != nullptr;
+  float4 T4 = make_float4(0.f, 0.f, 0.f, 0.f), R4 = T4;
+  if (active) {
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.demod + (int64_t)b * C + c4 * 4));
+    const float4 bias4 = __ldg(reinterpret_cast<const float4*>(a.bias + c4 * 4));
+    const float nw = __ldg(a.noise_w);
+    float4 s4 = T4, w0 = T4, w1 = T4, w2 = T4;
+    if (has_rgb) {
+      s4 = __ldg(reinterpret_cast<const float4*>(a.s_rgb + (int64_t)b * C + c4 * 4));
+      w0 = __ldg(reinterpret_cast<const float4*>(a.wrgb + 0 * C + c4 * 4));
+      w1 = __ldg(reinterpret_cast<const float4*>(a.wrgb + 1 * C + c4 * 4));
+      w2 = __ldg(reinterpret_cast<const float4*>(a.wrgb + 2 * C + c4 * 4));
+    }
+    const float inv_pos = 1.f / kLreluGain, inv_neg = 1.f / (kLreluGain * kLreluSlope);
+    for (int i = py; i < seglen; i += PX) {
+      const int pix = pix0 + i;
+      const int64_t idx = ((int64_t)b * a.hw + pix) * C + c4 * 4;
+      const float4 act4 = __ldg(reinterpret_cast<const float4*>(a.act + idx));
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.g_has_input) g4 = *reinterpret_cast<const float4*>(a.g + idx);
+      if (has_rgb) {
+        const float r0 = __ldg(a.drgb + ((int64_t)b * 3 + 0) * a.hw + pix);
+        const float r1 = __ldg(a.drgb + ((int64_t)b * 3 + 1) * a.hw + pix);
+        const float r2 = __ldg(a.drgb + ((int64_t)b * 3 + 2) * a.hw + pix);
+        float4 q4 = make_float4(r0 * w0.x, r0 * w0.y, r0 * w0.z, r0 * w0.w);
+        q4 = f4_fma(r1, w1, q4);
+        q4 = f4_fma(r2, w2, q4);
+        g4 = f4_fma4(q4, s4, g4);
+        R4 = f4_fma4(act4, q4, R4);
+      }
+      const float nz = nw * __ldg(a.noise + (int64_t)b * a.noise_bstride + pix);
+      float4 o4;
+#define LFP_ACTB(comp)                                                          \
+  {                                                                             \
+    const bool pos = act4.comp > 0.f;                                           \
+    const float gpre = g4.comp * (pos ? kLreluGain : kLreluGain * kLreluSlope); \
+    const float pre = act4.comp * (pos ? inv_pos : inv_neg);                    \
+    T4.comp = fmaf(gpre, pre - nz - bias4.comp, T4.comp);                       \
+    o4.comp = gpre * d4.comp;                                                   \
+  }
+      LFP_ACTB(x) LFP_ACTB(y) LFP_ACTB(z) LFP_ACTB(w)
+#undef LFP_ACTB
+      *reinterpret_cast<float4*>(a.g + idx) = o4;
+    }
+    *reinterpret_cast<float4*>(&redT[py * C + c4 * 4]) = T4;
+    *reinterpret_cast<float4*>(&redR[py * C + c4 * 4]) = R4;
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    float t = 0.f, r = 0.f;
+    for (int q = 0; q < PX; ++q) { t += redT[q * C + c]; r += redR[q * C + c]; }
+    a.pT[(int64_t)seg * C + c] = t;
+    if (has_rgb) a.pR[(int64_t)seg * C + c] = r;
+  }
+}
+
+int actbwd_seglen(int hw, int C) {
+  const int PX = 1024 / C;  // pixels per CTA pass
+  int seg = PX * 8;
+  if (seg < 256) seg = 256;
+  if (seg > hw) seg = hw;
+  return seg;
+}
+
+int launch_act_bwd(const ActBwdArgs& a, cudaStream_t s) {
+  LFP_CHECK_ARG(a.C % 4 == 0 && a.C <= 1024 && 1024 % a.C == 0, "act_bwd: unsupported C=%d", a.C);
+  const int C4 = a.C / 4, PX = 256 / C4;
+  const int seglen = actbwd_seglen(a.hw, a.C);
+  LFP_CHECK_ARG(a.hw % seglen == 0, "act_bwd: hw=%d not divisible by segment %d", a.hw, seglen);
+  const int64_t nseg = (int64_t)a.batch * (a.hw / seglen);
+  act_bwd_kernel<<<(unsigned)nseg, 256, 0, s>>>(a, C4, PX, seglen);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[b, c] = sum_q partial[b*Q + q, c], fixed order (8 contiguous q-ranges, then 8 sums)
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial,
+                                                             float* __restrict__ out, int Q, int C,
+                                                             int64_t out_bstride) {
+  __shared__ float sm[8][32];
+  const int cx = threadIdx.x & 31, qy = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int b = blockIdx.y;
+  const int per = (Q + 7) / 8;
+  const int q0 = qy * per, q1 = min(Q, q0 + per);
+  float acc = 0.f;
+  if (c < C)
+    for (int q = q0; q < q1; ++q) acc += __ldg(partial + ((int64_t)b * Q + q) * C + c);
+  sm[qy][cx] = acc;
+  __syncthreads();
+  if (qy == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    out[(int64_t)b * out_bstride + c] = t;
+  }
+}
+
+int launch_partial_reduce(const float* partial, float* out, int batch, int Q, int C, int64_t out_bstride,
+                          cudaStream_t s) {
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)batch);
+  partial_reduce_kernel<<<grid, 256, 0, s>>>(partial, out, Q, C, out_bstride);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// Style affine (all modulation linears of one forward in one launch), demodulation, style grads
+// =============================================================================================
+__global__ void __launch_bounds__(256) style_affine_kernel(const float* __restrict__ latent,
+                                                           const float* __restrict__ A,
+                                                           const float* __restrict__ bias,
+                                                           const int* __restrict__ row_slot,
+                                                           const int* __restrict__ row_base,
+                                                           const int* __restrict__ row_cin,
+                                                           float* __restrict__ s, int batch, int rows,
+                                                           int n_latent, int dim) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int slot = row_slot[r];
+  const float* arow = A + (int64_t)r * dim;
+  const float bv = __ldg(bias + r);
+  const int base = row_base[r], cin = row_cin[r];
+  for (int b = 0; b < batch; ++b) {
+    const float* lrow = latent + ((int64_t)b * n_latent + slot) * dim;
+    float acc = 0.f;
+    for (int j = lane * 4; j < dim; j += 128)
+      acc += f4_dot(__ldg(reinterpret_cast<const float4*>(arow + j)), __ldg(reinterpret_cast<const float4*>(lrow + j)));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s[(int64_t)batch * base + (int64_t)b * cin + (r - base)] = acc + bv;
+  }
+}
+
+int launch_style_affine(const float* latent, const float* A, const float* bias, const int* row_slot,
+                        const int* row_base, const int* row_cin, float* s, int batch, int rows,
+                        int n_latent, int dim, cudaStream_t st) {
+  LFP_CHECK_ARG(dim % 4 == 0, "style_affine: dim must be a multiple of 4");
+  style_affine_kernel<<<(unsigned)ceil_div(rows, 8), 256, 0, st>>>(latent, A, bias, row_slot, row_base, row_cin, s, batch, rows, n_latent, dim);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(128) style_affine_bwd_kernel(const float* __restrict__ ds,
+                                                               const float* __restrict__ A,
+                                                               const int* __restrict__ row_begin,
+                                                               const int* __restrict__ row_end,
+                                                               const int* __restrict__ row_base,
+                                                               const int* __restrict__ row_cin,
+                                                               float* __restrict__ d_latent, int batch,
+                                                               int n_latent, int dim) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int slot = blockIdx.y, b = blockIdx.z;
+  if (j >= dim) return;
+  const int r0 = row_begin[slot], r1 = row_end[slot];
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const int base = row_base[r];
+    acc = fmaf(__ldg(ds + (int64_t)batch * base + (int64_t)b * row_cin[r] + (r - base)), __ldg(A + (int64_t)r * dim + j), acc);
+  }
+  d_latent[((int64_t)b * n_latent + slot) * dim + j] = acc;
+}
+
+int launch_style_affine_bwd(const float* ds, const float* A, const int* slot_row_begin,
+                            const int* slot_row_end, const int* row_base, const int* row_cin,
+                            float* d_latent, int batch, int rows, int n_latent, int dim,
+                            cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(dim, 128), (unsigned)n_latent, (unsigned)batch);
+  style_affine_bwd_kernel<<<grid, 128, 0, st>>>(ds, A, slot_row_begin, slot_row_end, row_base, row_cin, d_latent, batch, n_latent, dim);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ s, int64_t s_bstride,
+                                                    const float* __restrict__ wsq,
+                                                    float* __restrict__ d, int64_t d_bstride,
+                                                    int cin, int cout) {
+  const int lane = threadIdx.x & 31;
+  const int co = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (co >= cout) return;
+  float acc = 0.f;
+  for (int ci = lane; ci < cin; ci += 32) {
+    const float sv = __ldg(s + (int64_t)b * s_bstride + ci);
+    acc = fmaf(sv * sv, __ldg(wsq + (int64_t)co * cin + ci), acc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) d[(int64_t)b * d_bstride + co] = rsqrtf(acc + 1e-8f);
+}
+
+int launch_demod(const float* s, int64_t s_bstride, const float* wsq, float* d, int64_t d_bstride,
+                 int batch, int cin, int cout, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(cout, 8), (unsigned)batch);
+  demod_kernel<<<grid, 256, 0, st>>>(s, s_bstride, wsq, d, d_bstride, cin, cout);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(128) style_grad_kernel(const float* __restrict__ r1,
+                                                         const float* __restrict__ s, int64_t s_bstride,
+                                                         const float* __restrict__ T,
+                                                         const float* __restrict__ d, int64_t d_bstride,
+                                                         const float* __restrict__ wsq,
+                                                         float* __restrict__ ds, int cin, int cout) {
+  const int ci = blockIdx.x * 128 + threadIdx.x;
+  const int b = blockIdx.y;
+  if (ci >= cin) return;
+  float acc = 0.f;
+  for (int co = 0; co < cout; ++co) {
+    const float dv = __ldg(d + (int64_t)b * d_bstride + co);
+    acc = fmaf(__ldg(T + (int64_t)b * d_bstride + co) * dv * dv, __ldg(wsq + (int64_t)co * cin + ci), acc);
+  }
+  const int64_t i = (int64_t)b * s_bstride + ci;
+  ds[i] = r1[i] - __ldg(s + i) * acc;
+}
+
+int launch_style_grad(const float* r1, const float* s, int64_t s_bstride, const float* T,
+                      const float* d, int64_t d_bstride, const float* wsq, float* ds, int batch,
+                      int cin, int cout, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(cin, 128), (unsigned)batch);
+  style_grad_kernel<<<grid, 128, 0, st>>>(r1, s, s_bstride, T, d, d_bstride, wsq, ds, cin, cout);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// One-off weight preparation and layout helpers
+// =============================================================================================
+__global__ void prep_conv3x3_kernel(const float* __restrict__ W, float scale, float* __restrict__ wf,
+                                    float* __restrict__ wg, float* __restrict__ wsq, int cin, int cout) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)cin * cout) return;
+  const int co = (int)(i / cin), ci = (int)(i - (int64_t)co * cin);
+  float sq = 0.f;
+  for (int t = 0; t < 9; ++t) {
+    const float v = W[((int64_t)co * cin + ci) * 9 + t] * scale;
+    wf[((int64_t)t * cin + ci) * cout + co] = v;
+    wg[((int64_t)t * cout + co) * cin + ci] = v;
+    sq = fmaf(v, v, sq);
+  }
+  wsq[(int64_t)co * cin + ci] = sq;
+}
+
+int launch_prep_conv3x3(const float* W, float scale, float* wf, float* wg, float* wsq, int cin,
+                        int cout, cudaStream_t st) {
+  prep_conv3x3_kernel<<<(unsigned)ceil_div((int64_t)cin * cout, 256), 256, 0, st>>>(W, scale, wf, wg, wsq, cin, cout);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void scale_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, float scale, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] * scale;
+}
+int launch_scale_copy(const float* src, float* dst, float scale, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 4096) blocks = 4096;
+  scale_copy_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, scale, n);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+// tiled transpose of the [C, hw] <-> [hw, C] planes of each sample
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) layout_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int hw) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = in + (int64_t)b * C * hw;
+  float* dst = out + (int64_t)b * C * hw;
+  for (int k = ty; k < 32; k += 8) {
+    if (TO_NHWC) { const int c = c0 + k, p = p0 + tx; if (c < C && p < hw) t[k][tx] = src[(int64_t)c * hw + p]; }
+    else { const int p = p0 + k, c = c0 + tx; if (c < C && p < hw) t[k][tx] = src[(int64_t)p * C + c]; }
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    if (TO_NHWC) { const int p = p0 + k, c = c0 + tx; if (c < C && p < hw) dst[(int64_t)p * C + c] = t[tx][k]; }
+    else { const int c = c0 + k, p = p0 + tx; if (c < C && p < hw) dst[(int64_t)c * hw + p] = t[tx][k]; }
+  }
+}
+int launch_nchw_to_nhwc(const float* in, float* out, int batch, int C, int hw, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(hw, 32), (unsigned)ceil_div(C, 32), (unsigned)batch);
+  layout_kernel<true><<<grid, 256, 0, st>>>(in, out, C, hw);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+int launch_nhwc_to_nchw(const float* in, float* out, int batch, int C, int hw, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(hw, 32), (unsigned)ceil_div(C, 32), (unsigned)batch);
+  layout_kernel<false><<<grid, 256, 0, st>>>(in, out, C, hw);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace lfp

@@ -1,0 +1,519 @@
+// Whole-synthesis plan: owns the prepared generator weights and sequences the kernels of one
+// forward / backward pass (the additive C-ABI group 3 of include/lfp_sg2.h).
+//
+// Replaces the module chain of Generator.forward(input_is_latent=True), src/model.py:551-566.
+// Layer order, channel table and latent-slot indexing follow src/model.py:418-474, 551-564.
+#include <math.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "synth_kernels.cuh"
+
+namespace lfp {
+
+struct ConvLayer {
+  std::string name;
+  int cin = 0, cout = 0, res_in = 0, res_out = 0;
+  bool up = false;
+  int slot = 0, noise_idx = 0;
+  float *W = nullptr, *modw = nullptr, *modb = nullptr, *noise_w = nullptr, *act_bias = nullptr;
+  float *wf = nullptr, *wg = nullptr, *wsq = nullptr;
+  int row0 = 0;       // first row in the stacked modulation matrix
+  int demod_off = 0;  // offset into the demod table (units of cout, times batch at run time)
+  size_t act_off = 0; // workspace offset (floats) of the saved output activation
+};
+struct RgbLayer {
+  std::string name;
+  int cin = 0, res = 0, slot = 0;
+  float *W = nullptr, *modw = nullptr, *modb = nullptr, *bias = nullptr, *wrgb = nullptr;
+  int row0 = 0;
+  size_t skip_off = 0;
+};
+
+struct Layout {
+  size_t s_all, d_all, scratchT, bufA, bufB, dskipA, dskipB, pT, pR, pX, T_all, R1_all, ds_all, total;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace lfp
+
+using namespace lfp;
+
+struct lfp_synth {
+  int size = 0, log_size = 0, style_dim = 0, cm = 2, n_latent = 0, num_noise = 0;
+  std::vector<ConvLayer> convs;  // [0]=conv1, [1+2j]=convs.2j (up), [2+2j]=convs.2j+1
+  std::vector<RgbLayer> rgbs;    // [0]=to_rgb1, [1+j]=to_rgbs.j
+  float* const_nchw = nullptr;
+  float* const_nhwc = nullptr;
+  float *A_all = nullptr, *b_all = nullptr;
+  int *row_slot = nullptr, *row_base = nullptr, *row_cin = nullptr, *slot_begin = nullptr, *slot_end = nullptr;
+  int rows = 0, demod_total = 0;
+  float* fir = nullptr;  // 4 x 16 floats: blur fwd coef, blur bwd coef, upsample kernel, flipped upsample kernel
+  float blur1d[4] = {1, 3, 3, 1};
+  bool finalized = false;
+  int fwd_batch = -1;
+  std::vector<const float*> fwd_noise;
+  std::vector<int> fwd_noise_batch;
+  std::vector<void*> owned;
+
+  ~lfp_synth() {
+    for (void* p : owned) cudaFree(p);
+  }
+  int alloc(float** p, size_t n) {
+    LFP_CUDA(cudaMalloc((void**)p, n * sizeof(float)));
+    owned.push_back(*p);
+    return 0;
+  }
+  int alloc_i(int** p, size_t n) {
+    LFP_CUDA(cudaMalloc((void**)p, n * sizeof(int)));
+    owned.push_back(*p);
+    return 0;
+  }
+  int channels(int res) const {
+    // src/model.py:418-428
+    switch (res) {
+      case 4: case 8: case 16: case 32: return 512;
+      case 64: return 256 * cm;
+      case 128: return 128 * cm;
+      case 256: return 64 * cm;
+      case 512: return 32 * cm;
+      case 1024: return 16 * cm;
+    }
+    return 0;
+  }
+  Layout layout(int B) const;
+};
+
+Layout lfp_synth::layout(int B) const {
+  Layout L{};
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
+  L.s_all = take((size_t)B * rows);
+  L.d_all = take((size_t)B * demod_total);
+  size_t max_act = 0, max_T = 0, max_pT = 0, max_pX = 0;
+  for (const ConvLayer& c : convs) {
+    const size_t n = (size_t)B * c.res_out * c.res_out * c.cout;
+    const_cast<ConvLayer&>(c).act_off = take(n);
+    if (n > max_act) max_act = n;
+    const size_t nin = (size_t)B * c.res_in * c.res_in * c.cin;
+    if (nin > max_act) max_act = nin;
+    if (c.up) {
+      const size_t t = (size_t)B * (c.res_out + 1) * (c.res_out + 1) * c.cout;
+      if (t > max_T) max_T = t;
+    }
+    const int hw = c.res_out * c.res_out;
+    const size_t pt = (size_t)B * (hw / actbwd_seglen(hw, c.cout)) * c.cout;
+    if (pt > max_pT) max_pT = pt;
+    const int hwi = c.res_in * c.res_in;
+    const size_t px = (size_t)B * (hwi / (hwi < 128 ? hwi : 128)) * c.cin;
+    if (px > max_pX) max_pX = px;
+  }
+  for (size_t i = 0; i < rgbs.size(); ++i)
+    const_cast<RgbLayer&>(rgbs[i]).skip_off = take((size_t)B * 3 * rgbs[i].res * rgbs[i].res);
+  L.scratchT = take(max_T);
+  L.bufA = take(max_act);
+  L.bufB = take(max_act);
+  const size_t half = (size_t)B * 3 * (size / 2) * (size / 2);
+  L.dskipA = take(half);
+  L.dskipB = take(half);
+  L.pT = take(max_pT);
+  L.pR = take(max_pT);
+  L.pX = take(max_pX);
+  L.T_all = take((size_t)B * demod_total);
+  L.R1_all = take((size_t)B * rows);
+  L.ds_all = take((size_t)B * rows);
+  L.total = off;
+  return L;
+}
+
+extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int channel_multiplier,
+                                const float* blur_kernel_1d, int blur_taps) {
+  LFP_CHECK_ARG(out != nullptr, "synth_create: null out");
+  const int ls = (int)lround(log2((double)size));
+  LFP_CHECK_ARG(size >= 8 && size <= 1024 && (1 << ls) == size, "synth_create: size %d must be a power of two in [8,1024]", size);
+  LFP_CHECK_ARG(style_dim >= 4 && style_dim % 4 == 0, "synth_create: style_dim %d must be a multiple of 4", style_dim);
+  LFP_CHECK_ARG(channel_multiplier >= 1, "synth_create: bad channel multiplier");
+  if (blur_kernel_1d != nullptr && blur_taps != 4) {
+    set_error("synth_create: only 4-tap blur kernels are supported by the fused path (got %d)", blur_taps);
+    return LFP_EUNSUPPORTED;
+  }
+  lfp_synth* h = new lfp_synth();
+  h->size = size; h->log_size = ls; h->style_dim = style_dim; h->cm = channel_multiplier;
+  h->n_latent = ls * 2 - 2;
+  h->num_noise = (ls - 2) * 2 + 1;
+  if (blur_kernel_1d) memcpy(h->blur1d, blur_kernel_1d, 4 * sizeof(float));
+  for (int r = 4; r <= size; r *= 2) {
+    const int c = h->channels(r);
+    if (c % 16 != 0 || 1024 % c != 0) {
+      set_error("synth_create: %d channels at %d px not supported (need a power of two >= 16)", c, r);
+      delete h;
+      return LFP_EUNSUPPORTED;
+    }
+  }
+  ConvLayer c1;
+  c1.name = "conv1"; c1.cin = c1.cout = h->channels(4); c1.res_in = c1.res_out = 4; c1.slot = 0; c1.noise_idx = 0;
+  h->convs.push_back(c1);
+  RgbLayer r1;
+  r1.name = "to_rgb1"; r1.cin = h->channels(4); r1.res = 4; r1.slot = 1;
+  h->rgbs.push_back(r1);
+  int cin = h->channels(4);
+  for (int j = 0; j + 3 <= ls; ++j) {
+    const int res = 8 << j, cout = h->channels(res);
+    ConvLayer u;
+    u.name = "convs." + std::to_string(2 * j); u.cin = cin; u.cout = cout; u.res_in = res / 2; u.res_out = res;
+    u.up = true; u.slot = 1 + 2 * j; u.noise_idx = 1 + 2 * j;
+    ConvLayer p;
+    p.name = "convs." + std::to_string(2 * j + 1); p.cin = cout; p.cout = cout; p.res_in = p.res_out = res;
+    p.slot = 2 + 2 * j; p.noise_idx = 2 + 2 * j;
+    RgbLayer r;
+    r.name = "to_rgbs." + std::to_string(j); r.cin = cout; r.res = res; r.slot = 3 + 2 * j;
+    h->convs.push_back(u); h->convs.push_back(p); h->rgbs.push_back(r);
+    cin = cout;
+  }
+  // raw parameter storage
+  int rc = 0;
+  const int c4 = h->channels(4);
+  rc |= h->alloc(&h->const_nchw, (size_t)c4 * 16);
+  rc |= h->alloc(&h->const_nhwc, (size_t)c4 * 16);
+  for (ConvLayer& c : h->convs) {
+    rc |= h->alloc(&c.W, (size_t)c.cout * c.cin * 9);
+    rc |= h->alloc(&c.modw, (size_t)c.cin * style_dim);
+    rc |= h->alloc(&c.modb, c.cin);
+    rc |= h->alloc(&c.noise_w, 1);
+    rc |= h->alloc(&c.act_bias, c.cout);
+    rc |= h->alloc(&c.wf, (size_t)9 * c.cin * c.cout);
+    rc |= h->alloc(&c.wg, (size_t)9 * c.cin * c.cout);
+    rc |= h->alloc(&c.wsq, (size_t)c.cin * c.cout);
+  }
+  for (RgbLayer& r : h->rgbs) {
+    rc |= h->alloc(&r.W, (size_t)3 * r.cin);
+    rc |= h->alloc(&r.modw, (size_t)r.cin * style_dim);
+    rc |= h->alloc(&r.modb, r.cin);
+    rc |= h->alloc(&r.bias, 3);
+    rc |= h->alloc(&r.wrgb, (size_t)3 * r.cin);
+  }
+  // modulation rows, ordered by latent slot so every slot owns one contiguous row range
+  std::vector<int> row_slot, row_base, row_cin, sb(h->n_latent, 0), se(h->n_latent, 0);
+  int rows = 0, demod = 0;
+  for (int slot = 0; slot < h->n_latent; ++slot) {
+    sb[slot] = rows;
+    for (RgbLayer& r : h->rgbs)
+      if (r.slot == slot) { r.row0 = rows; for (int i = 0; i < r.cin; ++i) { row_slot.push_back(slot); row_base.push_back(r.row0); row_cin.push_back(r.cin); } rows += r.cin; }
+    for (ConvLayer& c : h->convs)
+      if (c.slot == slot) { c.row0 = rows; for (int i = 0; i < c.cin; ++i) { row_slot.push_back(slot); row_base.push_back(c.row0); row_cin.push_back(c.cin); } rows += c.cin; }
+    se[slot] = rows;
+  }
+  for (ConvLayer& c : h->convs) { c.demod_off = demod; demod += c.cout; }
+  h->rows = rows; h->demod_total = demod;
+  rc |= h->alloc(&h->A_all, (size_t)rows * style_dim);
+  rc |= h->alloc(&h->b_all, rows);
+  rc |= h->alloc_i(&h->row_slot, rows);
+  rc |= h->alloc_i(&h->row_base, rows);
+  rc |= h->alloc_i(&h->row_cin, rows);
+  rc |= h->alloc_i(&h->slot_begin, h->n_latent);
+  rc |= h->alloc_i(&h->slot_end, h->n_latent);
+  rc |= h->alloc(&h->fir, 64);
+  if (rc != 0) { delete h; return rc; }
+  auto up = [&](void* d, const void* s, size_t n) { return cudaMemcpy(d, s, n, cudaMemcpyHostToDevice); };
+  cudaError_t e = up(h->row_slot, row_slot.data(), rows * sizeof(int));
+  if (e == cudaSuccess) e = up(h->row_base, row_base.data(), rows * sizeof(int));
+  if (e == cudaSuccess) e = up(h->row_cin, row_cin.data(), rows * sizeof(int));
+  if (e == cudaSuccess) e = up(h->slot_begin, sb.data(), h->n_latent * sizeof(int));
+  if (e == cudaSuccess) e = up(h->slot_end, se.data(), h->n_latent * sizeof(int));
+  // FIR tables.  k2 = outer(k,k)/sum * 4 is both Blur(upsample_factor=2) (src/model.py:75-86) and
+  // Upsample (src/model.py:37-38).
+  float k2[16], tab[64];
+  float sum = 0.f;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { k2[i * 4 + j] = h->blur1d[i] * h->blur1d[j]; sum += k2[i * 4 + j]; }
+  for (int i = 0; i < 16; ++i) k2[i] = k2[i] / sum * 4.f;
+  for (int ty = 0; ty < 4; ++ty)
+    for (int tx = 0; tx < 4; ++tx) {
+      tab[0 + ty * 4 + tx] = k2[(3 - ty) * 4 + (3 - tx)];   // blur forward: flipped taps, pad 1
+      tab[16 + ty * 4 + tx] = k2[ty * 4 + tx];              // blur adjoint: un-flipped taps, pad 2
+      tab[32 + ty * 4 + tx] = k2[ty * 4 + tx];              // upsample kernel as stored by the module
+      tab[48 + ty * 4 + tx] = k2[(3 - ty) * 4 + (3 - tx)];  // flipped, for the skip-upsample adjoint
+    }
+  if (e == cudaSuccess) e = up(h->fir, tab, sizeof(tab));
+  if (e != cudaSuccess) { set_error("synth_create: %s", cudaGetErrorString(e)); delete h; return (int)e; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void lfp_synth_destroy(lfp_synth* h) { delete h; }
+extern "C" int lfp_synth_n_latent(const lfp_synth* h) { return h ? h->n_latent : 0; }
+extern "C" int lfp_synth_num_noise(const lfp_synth* h) { return h ? h->num_noise : 0; }
+
+extern "C" int lfp_synth_set_param(lfp_synth* h, const char* name, const float* data, int64_t numel, void* stream) {
+  LFP_CHECK_ARG(h && name && data, "synth_set_param: null argument");
+  const std::string n(name);
+  float* dst = nullptr;
+  int64_t want = -1;
+  auto match = [&](const std::string& prefix, const char* suffix, float* p, int64_t cnt) {
+    if (n == prefix + suffix) { dst = p; want = cnt; }
+  };
+  if (n == "input.input") { dst = h->const_nchw; want = (int64_t)h->channels(4) * 16; }
+  for (ConvLayer& c : h->convs) {
+    match(c.name, ".conv.weight", c.W, (int64_t)c.cout * c.cin * 9);
+    match(c.name, ".conv.modulation.weight", c.modw, (int64_t)c.cin * h->style_dim);
+    match(c.name, ".conv.modulation.bias", c.modb, c.cin);
+    match(c.name, ".noise.weight", c.noise_w, 1);
+    match(c.name, ".activate.bias", c.act_bias, c.cout);
+  }
+  for (RgbLayer& r : h->rgbs) {
+    match(r.name, ".conv.weight", r.W, (int64_t)3 * r.cin);
+    match(r.name, ".conv.modulation.weight", r.modw, (int64_t)r.cin * h->style_dim);
+    match(r.name, ".conv.modulation.bias", r.modb, r.cin);
+    match(r.name, ".bias", r.bias, 3);
+  }
+  LFP_CHECK_ARG(dst != nullptr, "synth_set_param: unknown parameter '%s'", name);
+  LFP_CHECK_ARG(want == numel, "synth_set_param: '%s' expects %lld elements, got %lld", name, (long long)want, (long long)numel);
+  LFP_CUDA(cudaMemcpyAsync(dst, data, numel * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  h->finalized = false;
+  return 0;
+}
+
+extern "C" int lfp_synth_finalize(lfp_synth* h, void* stream) {
+  LFP_CHECK_ARG(h != nullptr, "synth_finalize: null plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  const float mscale = 1.f / sqrtf((float)h->style_dim);  // EqualLinear scale, lr_mul = 1 (src/model.py:148)
+  for (ConvLayer& c : h->convs) {
+    const float wscale = 1.f / sqrtf((float)(c.cin * 9));  // src/model.py:208-209
+    LFP_TRY(launch_prep_conv3x3(c.W, wscale, c.wf, c.wg, c.wsq, c.cin, c.cout, s));
+    LFP_TRY(launch_scale_copy(c.modw, h->A_all + (size_t)c.row0 * h->style_dim, mscale, (int64_t)c.cin * h->style_dim, s));
+    LFP_TRY(launch_scale_copy(c.modb, h->b_all + c.row0, 1.f, c.cin, s));
+  }
+  for (RgbLayer& r : h->rgbs) {
+    LFP_TRY(launch_scale_copy(r.W, r.wrgb, 1.f / sqrtf((float)r.cin), (int64_t)3 * r.cin, s));
+    LFP_TRY(launch_scale_copy(r.modw, h->A_all + (size_t)r.row0 * h->style_dim, mscale, (int64_t)r.cin * h->style_dim, s));
+    LFP_TRY(launch_scale_copy(r.modb, h->b_all + r.row0, 1.f, r.cin, s));
+  }
+  LFP_TRY(launch_nchw_to_nhwc(h->const_nchw, h->const_nhwc, 1, h->channels(4), 16, s));
+  h->finalized = true;
+  return 0;
+}
+
+extern "C" size_t lfp_synth_workspace_bytes(const lfp_synth* h, int batch) {
+  if (!h || batch <= 0) return 0;
+  return h->layout(batch).total * sizeof(float);
+}
+
+static void plain_taps(ConvGeom& g) {  // out[y,x] += in[y+ky-1, x+kx-1] * W[ky,kx]
+  g.ntaps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) { const int t = ky * 3 + kx; g.dy[t] = (signed char)(ky - 1); g.dx[t] = (signed char)(kx - 1); g.widx[t] = (signed char)t; }
+}
+
+static int check_run(const lfp_synth* h, int batch, const void* ws, size_t ws_bytes, int precision) {
+  LFP_CHECK_ARG(h != nullptr && ws != nullptr, "synth: null plan or workspace");
+  LFP_CHECK_ARG(batch >= 1 && batch <= 65535, "synth: batch %d out of range", batch);
+  if (!h->finalized) { set_error("synth: lfp_synth_finalize has not been called since the last set_param"); return LFP_ESTATE; }
+  if (ws_bytes < h->layout(batch).total * sizeof(float)) { set_error("synth: workspace too small (%zu < %zu bytes)", ws_bytes, h->layout(batch).total * sizeof(float)); return LFP_ENOMEM; }
+  LFP_CHECK_ARG(((uintptr_t)ws & 255) == 0, "synth: workspace must be 256-byte aligned");
+  if (precision != LFP_PREC_FP32) { set_error("synth: precision mode %d not available in this build", precision); return LFP_EUNSUPPORTED; }
+  return 0;
+}
+
+extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, const float* const* noise,
+                                 const int* noise_batch, float* image, void* workspace, size_t workspace_bytes,
+                                 int precision, void* stream) {
+  LFP_TRY(check_run(h, batch, workspace, workspace_bytes, precision));
+  LFP_CHECK_ARG(latent && noise && noise_batch && image, "synth_forward: null argument");
+  for (int i = 0; i < h->num_noise; ++i)
+    LFP_CHECK_ARG(noise[i] != nullptr && (noise_batch[i] == 1 || noise_batch[i] == batch), "synth_forward: noise %d must have batch 1 or %d", i, batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  const Layout L = h->layout(batch);
+  float* ws = (float*)workspace;
+  float* s_all = ws + L.s_all;
+  float* d_all = ws + L.d_all;
+  const int B = batch;
+
+  LFP_TRY(launch_style_affine(latent, h->A_all, h->b_all, h->row_slot, h->row_base, h->row_cin, s_all, B, h->rows, h->n_latent, h->style_dim, s));
+  for (const ConvLayer& c : h->convs)
+    LFP_TRY(launch_demod(s_all + (size_t)B * c.row0, c.cin, c.wsq, d_all + (size_t)B * c.demod_off, c.cout, B, c.cin, c.cout, s));
+
+  const float* x = h->const_nhwc;
+  int64_t x_bstride = 0;
+  for (size_t li = 0; li < h->convs.size(); ++li) {
+    const ConvLayer& c = h->convs[li];
+    float* act = ws + c.act_off;
+    const float* smod = s_all + (size_t)B * c.row0;
+    const float* dmod = d_all + (size_t)B * c.demod_off;
+    const int nb = noise_batch[c.noise_idx];
+    const int64_t nstride = nb == 1 ? 0 : (int64_t)c.res_out * c.res_out;
+    if (!c.up) {
+      ConvGeom g{};
+      g.batch = B; g.gh = g.gw = c.res_out; g.in_h = g.in_w = c.res_in; g.in_bstride = x_bstride; g.in_stride = 1;
+      g.out_h = g.out_w = c.res_out; g.out_stride = 1; g.out_oy = g.out_ox = 0; g.K = c.cin; g.N = c.cout;
+      plain_taps(g);
+      ConvEpiArgs e;
+      e.demod = dmod; e.noise = noise[c.noise_idx]; e.noise_bstride = nstride; e.noise_w = c.noise_w; e.bias = c.act_bias;
+      LFP_TRY(launch_conv_simt(x, smod, c.wf, act, g, EPI_ACT, e, s));
+    } else {
+      // stride-2 transposed conv as four sub-pixel phases into [B, 2H+1, 2W+1, Cout], then blur+epilogue
+      float* T = ws + L.scratchT;
+      const int H = c.res_in;
+      for (int a = 0; a < 2; ++a)
+        for (int bb = 0; bb < 2; ++bb) {
+          ConvGeom g{};
+          g.batch = B; g.gh = a == 0 ? H + 1 : H; g.gw = bb == 0 ? H + 1 : H;
+          g.in_h = g.in_w = H; g.in_bstride = x_bstride; g.in_stride = 1;
+          g.out_h = g.out_w = 2 * H + 1; g.out_stride = 2; g.out_oy = a; g.out_ox = bb; g.K = c.cin; g.N = c.cout;
+          int t = 0;
+          for (int ky = a == 0 ? 0 : 1; ky < 3; ky += 2)
+            for (int kx = bb == 0 ? 0 : 1; kx < 3; kx += 2) {
+              g.dy[t] = (signed char)(ky == 2 ? -1 : 0); g.dx[t] = (signed char)(kx == 2 ? -1 : 0); g.widx[t] = (signed char)(ky * 3 + kx); ++t;
+            }
+          g.ntaps = t;
+          LFP_TRY(launch_conv_simt(x, smod, c.wf, T, g, EPI_STORE, ConvEpiArgs{}, s));
+        }
+      FirArgs f{};
+      f.batch = B; f.in_h = f.in_w = 2 * H + 1; f.out_h = f.out_w = 2 * H; f.C = c.cout; f.pad = 1; f.coef = h->fir + 0;
+      f.act = true; f.demod = dmod; f.noise = noise[c.noise_idx]; f.noise_bstride = nstride; f.noise_w = c.noise_w; f.bias = c.act_bias;
+      LFP_TRY(launch_fir4x4_nhwc(T, act, f, s));
+    }
+    x = act;
+    x_bstride = (int64_t)c.res_out * c.res_out * c.cout;
+    if (li == 0 || (li % 2) == 0) {  // conv1 and every second conv of a block feed a ToRGB
+      const size_t ri = li / 2;
+      const RgbLayer& r = h->rgbs[ri];
+      const bool last = ri + 1 == h->rgbs.size();
+      float* dst = last ? image : ws + r.skip_off;
+      const float* skip = ri == 0 ? nullptr : ws + h->rgbs[ri - 1].skip_off;
+      LFP_TRY(launch_torgb_fwd(act, s_all + (size_t)B * r.row0, r.wrgb, r.bias, skip, h->fir + 32, dst, B, r.res, r.res, r.cin, s));
+    }
+  }
+  h->fwd_batch = batch;
+  h->fwd_noise.assign(noise, noise + h->num_noise);
+  h->fwd_noise_batch.assign(noise_batch, noise_batch + h->num_noise);
+  return 0;
+}
+
+extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image, float* d_latent,
+                                  void* workspace, size_t workspace_bytes, int precision, void* stream) {
+  LFP_TRY(check_run(h, batch, workspace, workspace_bytes, precision));
+  LFP_CHECK_ARG(d_image && d_latent, "synth_backward: null argument");
+  if (h->fwd_batch != batch) { set_error("synth_backward: no matching forward (forward batch %d, backward batch %d)", h->fwd_batch, batch); return LFP_ESTATE; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const Layout L = h->layout(batch);
+  float* ws = (float*)workspace;
+  float* s_all = ws + L.s_all;
+  float* d_all = ws + L.d_all;
+  float* T_all = ws + L.T_all;
+  float* R1_all = ws + L.R1_all;
+  float* ds_all = ws + L.ds_all;
+  float* bufs[2] = {ws + L.bufA, ws + L.bufB};
+  float* dskips[2] = {ws + L.dskipA, ws + L.dskipB};
+  const int B = batch;
+
+  const float* dskip = d_image;       // gradient wrt the running skip image at the current level
+  float* g = nullptr;                 // gradient wrt the current layer's output activation (null: none yet)
+  int cur = 0, dcur = 0;
+  for (int li = (int)h->convs.size() - 1; li >= 0; --li) {
+    const ConvLayer& c = h->convs[li];
+    const int hw = c.res_out * c.res_out;
+    const bool feeds_rgb = li == 0 || (li % 2) == 0;
+    const RgbLayer* r = feeds_rgb ? &h->rgbs[li / 2] : nullptr;
+    float* gbuf = g != nullptr ? g : bufs[cur];
+    ActBwdArgs ab{};
+    ab.batch = B; ab.hw = hw; ab.C = c.cout; ab.act = ws + c.act_off; ab.g = gbuf; ab.g_has_input = g != nullptr;
+    ab.demod = d_all + (size_t)B * c.demod_off;
+    ab.noise = h->fwd_noise[c.noise_idx];
+    ab.noise_bstride = h->fwd_noise_batch[c.noise_idx] == 1 ? 0 : hw;
+    ab.noise_w = c.noise_w; ab.bias = c.act_bias;
+    if (r) { ab.drgb = dskip; ab.s_rgb = s_all + (size_t)B * r->row0; ab.wrgb = r->wrgb; }
+    ab.pT = ws + L.pT; ab.pR = ws + L.pR;
+    LFP_TRY(launch_act_bwd(ab, s));
+    const int Q = hw / actbwd_seglen(hw, c.cout);
+    LFP_TRY(launch_partial_reduce(ab.pT, T_all + (size_t)B * c.demod_off, B, Q, c.cout, c.cout, s));
+    if (r) LFP_TRY(launch_partial_reduce(ab.pR, ds_all + (size_t)B * r->row0, B, Q, c.cout, c.cout, s));
+    if (g == nullptr) { g = gbuf; }
+    // g now holds dRaw = d(loss)/d(conv output before demod) * demod, at the layer's output resolution
+    float* other = (g == bufs[0]) ? bufs[1] : bufs[0];
+    const float* xin = li == 0 ? h->const_nhwc : ws + h->convs[li - 1].act_off;
+    const int64_t xin_bstride = li == 0 ? 0 : (int64_t)c.res_in * c.res_in * c.cin;
+    ConvGeom gg{};
+    gg.batch = B; gg.gh = gg.gw = c.res_in; gg.in_bstride = 0; gg.K = c.cout; gg.N = c.cin;
+    gg.out_h = gg.out_w = c.res_in; gg.out_stride = 1; gg.out_oy = gg.out_ox = 0;
+    const float* gin = g;
+    if (!c.up) {
+      gg.in_h = gg.in_w = c.res_out; gg.in_stride = 1; gg.in_bstride = (int64_t)hw * c.cout;
+      gg.ntaps = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) { const int t = ky * 3 + kx; gg.dy[t] = (signed char)(1 - ky); gg.dx[t] = (signed char)(1 - kx); gg.widx[t] = (signed char)t; }
+    } else {
+      // adjoint of the blur: [2H,2H] -> [2H+1,2H+1], un-flipped taps, pad 2 (src/op/upfirdn2d.py:112-115)
+      float* T = ws + L.scratchT;
+      FirArgs f{};
+      f.batch = B; f.in_h = f.in_w = c.res_out; f.out_h = f.out_w = c.res_out + 1; f.C = c.cout; f.pad = 2; f.coef = h->fir + 16;
+      LFP_TRY(launch_fir4x4_nhwc(g, T, f, s));
+      gin = T;
+      gg.in_h = gg.in_w = c.res_out + 1; gg.in_stride = 2; gg.in_bstride = (int64_t)(c.res_out + 1) * (c.res_out + 1) * c.cout;
+      gg.ntaps = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) { const int t = ky * 3 + kx; gg.dy[t] = (signed char)ky; gg.dx[t] = (signed char)kx; gg.widx[t] = (signed char)t; }
+    }
+    ConvEpiArgs e;
+    e.mod_out = s_all + (size_t)B * c.row0; e.xsave = xin; e.xsave_bstride = xin_bstride; e.partial = ws + L.pX;
+    float* dx = li == 0 ? nullptr : other;
+    LFP_TRY(launch_conv_simt(gin, nullptr, c.wg, dx, gg, EPI_DGRAD, e, s));
+    const int hwi = c.res_in * c.res_in;
+    LFP_TRY(launch_partial_reduce(e.partial, R1_all + (size_t)B * c.row0, B, hwi / conv_dgrad_seglen(gg), c.cin, c.cin, s));
+    LFP_TRY(launch_style_grad(R1_all + (size_t)B * c.row0, s_all + (size_t)B * c.row0, c.cin, T_all + (size_t)B * c.demod_off,
+                              d_all + (size_t)B * c.demod_off, c.cout, c.wsq, ds_all + (size_t)B * c.row0, B, c.cin, c.cout, s));
+    g = dx;
+    // crossing a resolution boundary: the skip gradient goes through the Upsample adjoint
+    if (c.up) {
+      float* nd = dskips[dcur];
+      LFP_TRY(upfirdn2d_dispatch(dskip, h->fir + 48, nd, LFP_F32, (int64_t)B * 3, c.res_out, c.res_out, 1, 4, 4, 1, 1, 2, 2, 1, 1, 1, 1, s, true));
+      dskip = nd;
+      dcur ^= 1;
+    }
+  }
+  LFP_TRY(launch_style_affine_bwd(ds_all, h->A_all, h->slot_begin, h->slot_end, h->row_base, h->row_cin, d_latent, B, h->rows, h->n_latent, h->style_dim, s));
+  return 0;
+}
+
+extern "C" int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const float* latent,
+                                               const float* const* noise, const int* noise_batch,
+                                               float* image, const float* d_image, float* d_latent,
+                                               int precision) {
+  LFP_CHECK_ARG(h && latent && noise && noise_batch && image, "synth_host: null argument");
+  LFP_CHECK_ARG(batch >= 1, "synth_host: bad batch");
+  const size_t nlat = (size_t)batch * h->n_latent * h->style_dim;
+  const size_t nimg = (size_t)batch * 3 * h->size * h->size;
+  const size_t wsb = lfp_synth_workspace_bytes(h, batch);
+  std::vector<void*> tmp;
+  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
+  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+  float* dlat = (float*)dalloc(nlat * 4);
+  float* dimg = (float*)dalloc(nimg * 4);
+  void* ws = dalloc(wsb);
+  std::vector<const float*> dn(h->num_noise);
+  bool ok = dlat && dimg && ws;
+  for (int i = 0; ok && i < h->num_noise; ++i) {
+    const int res = i == 0 ? 4 : (8 << ((i - 1) / 2));
+    const size_t n = (size_t)noise_batch[i] * res * res;
+    float* p = (float*)dalloc(n * 4);
+    ok = p && cudaMemcpy(p, noise[i], n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    dn[i] = p;
+  }
+  if (!ok) { cleanup(); set_error("synth_host: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError())); return LFP_ENOMEM; }
+  int rc = 0;
+  if (cudaMemcpy(dlat, latent, nlat * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = LFP_EINVAL;
+  if (rc == 0) rc = lfp_synth_forward(h, batch, dlat, dn.data(), noise_batch, dimg, ws, wsb, precision, nullptr);
+  if (rc == 0 && cudaMemcpy(image, dimg, nimg * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = LFP_EINVAL;
+  if (rc == 0 && d_image != nullptr && d_latent != nullptr) {
+    float* dg = (float*)dalloc(nimg * 4);
+    float* dl = (float*)dalloc(nlat * 4);
+    if (!dg || !dl) rc = LFP_ENOMEM;
+    if (rc == 0 && cudaMemcpy(dg, d_image, nimg * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = LFP_EINVAL;
+    if (rc == 0) rc = lfp_synth_backward(h, batch, dg, dl, ws, wsb, precision, nullptr);
+    if (rc == 0 && cudaMemcpy(d_latent, dl, nlat * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = LFP_EINVAL;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc == 0 && e != cudaSuccess) { set_error("synth_host: %s", cudaGetErrorString(e)); rc = (int)e; }
+  cleanup();
+  return rc;
+}

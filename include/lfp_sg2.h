@@ -1,0 +1,172 @@
+/*
+ * lfp_sg2.h - C ABI of the B200-native latent-fingerprint (StyleGAN2 synthesis) hot path.
+ *
+ * One shared library, liblfp_sg2.so, built by nvcc for sm_100a with no torch / ATen
+ * dependency.  Every entry point takes plain pointers and sizes; device pointers are
+ * raw CUDA device addresses, `stream` is a cudaStream_t passed as void* (NULL = legacy
+ * default stream).  All functions return 0 on success, a positive cudaError_t value
+ * when a CUDA call failed, or a negative LFP_E* code for argument errors;
+ * lfp_last_error() returns a thread-local description of the last failure.
+ * Launches are asynchronous on `stream` unless the name ends in `_host`.
+ *
+ * The first two groups are exactly what the reference's FFI for this path binds
+ * (its two pybind11 modules); the third group is additive: the fused whole-synthesis
+ * forward / backward that replaces the Python module chain in src/model.py.
+ * Citations are relative to /root/reference/.
+ */
+#ifndef LFP_SG2_H_
+#define LFP_SG2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFP_OK 0
+#define LFP_EINVAL (-1)    /* bad argument (shape, dtype, null pointer)            */
+#define LFP_ESTATE (-2)    /* call sequence error (e.g. backward without forward) */
+#define LFP_ENOMEM (-3)    /* workspace too small                                 */
+#define LFP_EUNSUPPORTED (-4)
+
+/* element types accepted by the two legacy ops (the reference dispatches
+ * AT_DISPATCH_FLOATING_TYPES_AND_HALF, src/op/upfirdn2d_kernel.cu:310,
+ * src/op/fused_bias_act_kernel.cu:96) */
+#define LFP_F32 0
+#define LFP_F64 1
+#define LFP_F16 2
+
+const char* lfp_last_error(void);
+int lfp_version(void);
+/* number of kernels this library has launched since load (all entry points) */
+uint64_t lfp_launch_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * 1. upfirdn2d  -  replaces `upfirdn2d(input, kernel, up_x, up_y, down_x, down_y,
+ *    pad_x0, pad_x1, pad_y0, pad_y1)` of module "upfirdn2d"
+ *    (src/op/upfirdn2d.cpp:17-31 -> upfirdn2d_op, src/op/upfirdn2d_kernel.cu:209-369).
+ *    input  [major, in_h, in_w, minor] contiguous, kernel [kernel_h, kernel_w] same dtype,
+ *    out    [major, out_h, out_w, minor] with
+ *           out_h = (in_h*up_y + pad_y0 + pad_y1 - kernel_h + down_y) / down_y (likewise w).
+ *    The FIR is applied flipped (true convolution); negative pads crop.  64-bit indexing
+ *    throughout (the reference overflows int at 2^31 elements).
+ * --------------------------------------------------------------------------------- */
+int lfp_upfirdn2d_out_size(int in_h, int in_w, int kernel_h, int kernel_w, int up_x, int up_y,
+                           int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                           int* out_h, int* out_w);
+
+int lfp_upfirdn2d(const void* input, const void* kernel, void* out, int dtype, int64_t major,
+                  int in_h, int in_w, int64_t minor, int kernel_h, int kernel_w, int up_x, int up_y,
+                  int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                  void* stream);
+
+/* same op on HOST buffers: allocates device scratch, copies in, runs, copies out, syncs */
+int lfp_upfirdn2d_host(const void* input, const void* kernel, void* out, int dtype, int64_t major,
+                       int in_h, int in_w, int64_t minor, int kernel_h, int kernel_w, int up_x,
+                       int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                       int pad_y1);
+
+/* ---------------------------------------------------------------------------------
+ * 2. fused_bias_act  -  replaces `fused_bias_act(input, bias, refer, act, grad, alpha,
+ *    scale)` of module "fused" (src/op/fused_bias_act.cpp:18-32 -> fused_bias_act_op,
+ *    src/op/fused_bias_act_kernel.cu:67-104).
+ *    x[size_x] contiguous; bias[size_b] or NULL ("empty tensor"); ref[size_x] or NULL;
+ *    bias index of element i is (i / step_b) % size_b, step_b = prod(dims >= 2).
+ *    act*10+grad: 10,11 -> y=x; 30 -> x>0?x:x*alpha; 31 -> ref>0?x:x*alpha; 12,32 -> 0;
+ *    out = y*scale.
+ * --------------------------------------------------------------------------------- */
+int lfp_fused_bias_act(const void* x, const void* bias, const void* ref, void* out, int dtype,
+                       int64_t size_x, int64_t step_b, int64_t size_b, int act, int grad,
+                       float alpha, float scale, void* stream);
+
+int lfp_fused_bias_act_host(const void* x, const void* bias, const void* ref, void* out, int dtype,
+                            int64_t size_x, int64_t step_b, int64_t size_b, int act, int grad,
+                            float alpha, float scale);
+
+/* grad_bias = sum over all dims but 1 of grad_input (src/op/fused_act.py:34-40), fp32 only,
+ * deterministic (fixed summation order).  g [outer, size_b, step_b]; out [size_b]. */
+int lfp_bias_grad_reduce(const float* g, float* out, int64_t outer, int64_t size_b, int64_t step_b,
+                         void* scratch, size_t scratch_bytes, void* stream);
+size_t lfp_bias_grad_reduce_scratch(int64_t outer, int64_t size_b, int64_t step_b);
+
+/* ---------------------------------------------------------------------------------
+ * 3. Whole-synthesis plan (additive).  Replaces the module chain executed by
+ *    Generator.forward with input_is_latent=True (src/model.py:551-566): ConstantInput,
+ *    StyledConv (ModulatedConv2d :258-302 + NoiseInjection :311-316 + FusedLeakyReLU),
+ *    ToRGB (:379-388) incl. Blur / Upsample, and its autograd backward to the latent.
+ *    Generator parameters are frozen (the attribution loop discards their gradients,
+ *    src/main.py:58); only d(image)/d(latent) is produced.
+ *
+ *    Activations are kept NHWC fp32 inside the workspace; the public tensors keep the
+ *    reference layouts: latent [B, n_latent, style_dim], noise_i [nb, 1, h, h] with nb in
+ *    {1, B}, image / d_image [B, 3, size, size] (NCHW), d_latent [B, n_latent, style_dim].
+ * --------------------------------------------------------------------------------- */
+typedef struct lfp_synth lfp_synth;
+
+/* precision modes for the 3x3 convolutions */
+#define LFP_PREC_FP32 0 /* CUDA-core FFMA, fp32 operands and accumulation                  */
+#define LFP_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 storage, fp32 accumulation in TMEM      */
+
+int lfp_synth_create(lfp_synth** out, int size, int style_dim, int channel_multiplier,
+                     const float* blur_kernel_1d, int blur_taps);
+void lfp_synth_destroy(lfp_synth* h);
+
+int lfp_synth_n_latent(const lfp_synth* h);   /* 2*log2(size)-2  (src/model.py:474)       */
+int lfp_synth_num_noise(const lfp_synth* h);  /* 2*(log2(size)-2)+1 (src/model.py:437-438) */
+
+/* Upload one tensor by its reference state_dict name, e.g.
+ * "conv1.conv.weight", "convs.3.conv.modulation.bias", "to_rgbs.2.bias", "input.input".
+ * `data` is a DEVICE pointer to fp32, `numel` must match the expected shape.  Unknown
+ * names (mapping network, stored noises, FIR buffers) return LFP_EINVAL. */
+int lfp_synth_set_param(lfp_synth* h, const char* name, const float* data, int64_t numel,
+                        void* stream);
+/* Build derived tables (scaled / re-laid-out weights, sum-of-squares, stacked modulation
+ * matrix).  Must be called after the last set_param and before forward. */
+int lfp_synth_finalize(lfp_synth* h, void* stream);
+
+size_t lfp_synth_workspace_bytes(const lfp_synth* h, int batch);
+
+/* noise: host array of lfp_synth_num_noise() device pointers; noise_batch[i] in {1, batch}.
+ * The workspace must stay untouched between forward and the matching backward. */
+int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, const float* const* noise,
+                      const int* noise_batch, float* image, void* workspace,
+                      size_t workspace_bytes, int precision, void* stream);
+int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image, float* d_latent,
+                       void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* Host-buffer convenience (what a non-torch caller binds): latent / noise / image / d_image /
+ * d_latent are HOST pointers; copies are inside the call; synchronous.  d_image may be NULL
+ * (forward only). */
+int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const float* latent,
+                                    const float* const* noise, const int* noise_batch,
+                                    float* image, const float* d_image, float* d_latent,
+                                    int precision);
+
+/* ---------------------------------------------------------------------------------
+ * 4. Fingerprint embed + loss glue used by the attribution loop (additive).
+ *    w0 = U^T alpha + mu (src/main.py:60); wx = w0 + sd * V^T diag(sigma) sigmoid(key)
+ *    (src/generator.py:148-161, src/main.py:61), batched over B trajectories, row-major:
+ *    alpha [B, n_main], key_logits [B, key_len], U [n_main, dim], V [key_len, dim],
+ *    sigma_key [key_len], mu [dim]; outputs w0, wx [B, dim].
+ *    Backward: given d_wx [B, dim] -> d_alpha [B, n_main], d_key [B, key_len].
+ * --------------------------------------------------------------------------------- */
+int lfp_embed_forward(const float* alpha, const float* key_logits, const float* U, const float* V,
+                      const float* sigma_key, const float* mu, float sd, int batch, int n_main,
+                      int key_len, int dim, float* w0, float* wx, void* stream);
+int lfp_embed_backward(const float* d_wx, const float* key_logits, const float* U, const float* V,
+                       const float* sigma_key, float sd, int batch, int n_main, int key_len,
+                       int dim, float* d_alpha, float* d_key, void* stream);
+
+/* mean-squared-error per trajectory against a shared or per-trajectory target, and its
+ * gradient (src/utils.py:46-47): loss[b] = mean((est[b]-target[b or 0])^2),
+ * d_est = 2*(est-target)/numel_per.  Deterministic two-pass reduction. */
+int lfp_mse_loss_grad(const float* est, const float* target, int target_batch, int batch,
+                      int64_t numel_per, float* loss, float* d_est, void* scratch,
+                      size_t scratch_bytes, void* stream);
+size_t lfp_mse_scratch_bytes(int batch, int64_t numel_per);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFP_SG2_H_ */

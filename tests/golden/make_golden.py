@@ -210,6 +210,18 @@ def gen_generator(ref, out):
         out[f"gen/{name}/latent_shape"] = np.array(lat.shape)
 
 
+def gen_state_dict_keys(ref):
+    """Names and shapes of Generator.state_dict() for the checkpoint-compatibility test."""
+    import json
+    table = {}
+    for size, cm in ((32, 2), (256, 2), (1024, 2), (64, 1)):
+        g = ref["model"].Generator(size, 512, 8, channel_multiplier=cm)
+        table[f"{size}_cm{cm}"] = {k: list(v.shape) for k, v in g.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_keys.json"), "w") as f:
+        json.dump(table, f, indent=0, sort_keys=True)
+    print("state_dict_keys.json", {k: len(v) for k, v in table.items()})
+
+
 def gen_embed_and_loop(ref, out):
     size, seed = 32, 11
     g = ref_generator(ref, size, seed)
@@ -272,6 +284,7 @@ def gen_embed_and_loop(ref, out):
 def main():
     torch.set_num_threads(8)
     ref = import_reference()
+    gen_state_dict_keys(ref)
     for fname, fn in [("ops.npz", lambda o: (gen_upfirdn(ref, o), gen_lrelu(ref, o))),
                       ("modconv.npz", lambda o: gen_modconv(ref, o)),
                       ("generator.npz", lambda o: gen_generator(ref, o)),

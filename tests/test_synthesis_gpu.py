@@ -1,0 +1,164 @@
+"""GPU parity of the fused synthesis path (Generator.forward -> lfp_synth_forward/backward) against
+the reference-generated golden vectors and the CPU oracle.
+
+Tolerances (fp32 path): images are compared on their own scale - random-init images are not in
+[-1,1] - so the north-star bar "max-abs <= 1e-3 on [-1,1] pixels" is applied as
+max-abs <= 1e-3 * max(1, max|ref|); latent gradients to 1e-3 relative L2.  Measured differences are
+two orders of magnitude below both."""
+import numpy as np
+import pytest
+import torch
+
+import fixtures as fx
+import oracle
+from golden.make_golden import GEN_CASES
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build_generator(size, seed, cm=2):
+    from model import Generator
+    g = Generator(size, 512, 8, channel_multiplier=cm)
+    missing = g.load_state_dict(fx.make_params(size, seed, cm), strict=False)
+    assert not missing.unexpected_keys
+    return g.eval().to(DEV)
+
+
+def img_close(a, ref, tol=1e-3):
+    err = np.abs(a - ref).max()
+    assert err <= tol * max(1.0, np.abs(ref).max()), f"max-abs {err} vs scale {np.abs(ref).max()}"
+    return err
+
+
+@pytest.mark.parametrize("case", GEN_CASES, ids=[c[0] for c in GEN_CASES])
+def test_generator_golden(golden, case):
+    name, size, cm, B, seed = case
+    g = build_generator(size, seed, cm)
+    noise = [n.to(DEV) for n in fx.make_noise(size, seed + 1)]
+    w = fx.seeded((B, 512), seed + 2).to(DEV).requires_grad_(True)
+    img, none = g([w], input_is_latent=True, noise=noise)
+    assert none is None and img.shape == (B, 3, size, size)
+    ref = golden[f"gen/{name}/img"]
+    img_close(img.detach().cpu().numpy(), ref, 1e-4)
+    ct = fx.seeded(tuple(img.shape), seed + 3).to(DEV)
+    (gw,) = torch.autograd.grad((img * ct).sum(), w)
+    gref = golden[f"gen/{name}/gw"]
+    rel = np.linalg.norm(gw.cpu().numpy() - gref) / np.linalg.norm(gref)
+    assert rel <= 1e-4, rel
+    # mapping network + z input
+    z = fx.seeded((3, 512), seed + 4).to(DEV)
+    with torch.no_grad():
+        np.testing.assert_allclose(g.style(z).cpu().numpy(), golden[f"gen/{name}/mapping"], rtol=1e-3, atol=1e-4)
+        img_z, lat = g([z[:B]], noise=noise, return_latents=True)
+    img_close(img_z.cpu().numpy(), golden[f"gen/{name}/img_from_z"], 1e-3)
+    assert tuple(lat.shape) == tuple(golden[f"gen/{name}/latent_shape"])
+
+
+@pytest.mark.parametrize("size,B", [(8, 1), (16, 5), (128, 2), (256, 1)])
+def test_generator_vs_oracle(size, B):
+    seed = 20 + size
+    params = fx.make_params(size, seed)
+    g = build_generator(size, seed)
+    noise = fx.make_noise(size, seed + 1)
+    w = fx.seeded((B, 512), seed + 2)
+    wr = w.clone().requires_grad_(True)
+    ref = oracle.generator_forward(params, [wr], size, input_is_latent=True, noise=noise)
+    ct = fx.seeded(tuple(ref.shape), seed + 3)
+    (gref,) = torch.autograd.grad((ref * ct).sum(), wr)
+    wg = w.to(DEV).requires_grad_(True)
+    img, _ = g([wg], input_is_latent=True, noise=[n.to(DEV) for n in noise])
+    img_close(img.detach().cpu().numpy(), ref.detach().numpy(), 1e-4)
+    (gw,) = torch.autograd.grad((img * ct.to(DEV)).sum(), wg)
+    rel = np.linalg.norm(gw.cpu().numpy() - gref.numpy()) / np.linalg.norm(gref.numpy())
+    assert rel <= 2e-4, rel
+
+
+def test_per_sample_noise_style_mixing_and_per_slot_gradient():
+    size, seed, B = 32, 31, 3
+    params = fx.make_params(size, seed)
+    g = build_generator(size, seed)
+    noise = fx.make_noise(size, seed + 1, batch=B)           # per-sample noise maps [B,1,h,h]
+    lat = fx.seeded((B, oracle.n_latent(size), 512), seed + 2)   # a different latent per slot
+    lr = lat.clone().requires_grad_(True)
+    ref = oracle.synthesis(params, lr, noise)
+    ct = fx.seeded(tuple(ref.shape), seed + 3)
+    (gref,) = torch.autograd.grad((ref * ct).sum(), lr)
+    lg = lat.to(DEV).requires_grad_(True)
+    img, _ = g([lg], input_is_latent=True, noise=[n.to(DEV) for n in noise])
+    img_close(img.detach().cpu().numpy(), ref.detach().numpy(), 1e-4)
+    (gl,) = torch.autograd.grad((img * ct.to(DEV)).sum(), lg)
+    assert gl.shape == lat.shape
+    rel = np.linalg.norm(gl.cpu().numpy() - gref.numpy()) / np.linalg.norm(gref.numpy())
+    assert rel <= 2e-4, rel
+    # style mixing goes through the same latent assembly as the reference (src/model.py:536-548)
+    w1, w2 = fx.seeded((B, 512), 40), fx.seeded((B, 512), 41)
+    mixed = torch.cat([w1[:, None].repeat(1, 4, 1), w2[:, None].repeat(1, oracle.n_latent(size) - 4, 1)], 1)
+    with torch.no_grad():
+        img_mix, _ = g([w1.to(DEV), w2.to(DEV)], input_is_latent=True, noise=[n.to(DEV) for n in noise], inject_index=4)
+        ref_mix = oracle.synthesis(params, mixed, noise)
+    img_close(img_mix.cpu().numpy(), ref_mix.numpy(), 1e-4)
+
+
+def test_batch_independence_is_bitwise():
+    """A trajectory's image and gradient do not depend on what shares its batch (what makes the
+    sharded attribution run reproduce the unsharded one bit for bit)."""
+    size, seed = 64, 50
+    g = build_generator(size, seed)
+    noise = [n.to(DEV) for n in fx.make_noise(size, seed + 1)]
+    w = fx.seeded((4, 512), seed + 2).to(DEV)
+    ct = fx.seeded((4, 3, size, size), seed + 3).to(DEV)
+
+    def run(idx):
+        wi = w[idx].clone().requires_grad_(True)
+        img, _ = g([wi], input_is_latent=True, noise=noise)
+        (gw,) = torch.autograd.grad((img * ct[idx]).sum(), wi)
+        return img.detach(), gw
+
+    img_all, g_all = run(slice(0, 4))
+    for i in range(4):
+        img_i, g_i = run(slice(i, i + 1))
+        assert torch.equal(img_i[0], img_all[i])
+        assert torch.equal(g_i[0], g_all[i])
+
+
+def test_interleaved_forwards_keep_backward_correct():
+    size, seed = 16, 60
+    g = build_generator(size, seed)
+    noise = [n.to(DEV) for n in fx.make_noise(size, seed + 1)]
+    w1 = fx.seeded((2, 512), 61).to(DEV).requires_grad_(True)
+    w2 = fx.seeded((2, 512), 62).to(DEV).requires_grad_(True)
+    img1, _ = g([w1], input_is_latent=True, noise=noise)
+    img2, _ = g([w2], input_is_latent=True, noise=noise)   # second forward before the first backward
+    (g1,) = torch.autograd.grad(img1.square().sum(), w1)
+    (g2,) = torch.autograd.grad(img2.square().sum(), w2)
+    w1b = w1.detach().clone().requires_grad_(True)
+    img1b, _ = g([w1b], input_is_latent=True, noise=noise)
+    (g1b,) = torch.autograd.grad(img1b.square().sum(), w1b)
+    assert torch.equal(g1, g1b)
+    assert not torch.equal(g1, g2)
+
+
+def test_host_buffer_entry_point_matches():
+    """lfp_synth_forward_backward_host: HOST pointers in and out (INTEGRATION.md binding)."""
+    import ctypes as C
+    from lfp_native import capi
+    from lfp_native.synthesis import SynthesisPlan
+    size, seed, B = 16, 70, 2
+    params = fx.make_params(size, seed)
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(params)
+    noise = fx.make_noise(size, seed + 1)
+    lat = fx.seeded((B, plan.n_latent, 512), seed + 2).contiguous()
+    ct = fx.seeded((B, 3, size, size), seed + 3).contiguous()
+    img = torch.empty(B, 3, size, size)
+    dlat = torch.empty_like(lat)
+    nptr = (C.c_void_p * plan.num_noise)(*[n.data_ptr() for n in noise])
+    nb = (C.c_int * plan.num_noise)(*[1] * plan.num_noise)
+    capi.check(capi.lib().lfp_synth_forward_backward_host(plan._h, B, lat.data_ptr(), nptr, nb, img.data_ptr(),
+                                                          ct.data_ptr(), dlat.data_ptr(), capi.PREC_FP32))
+    lr = lat.clone().requires_grad_(True)
+    ref = oracle.synthesis(params, lr, noise)
+    (gref,) = torch.autograd.grad((ref * ct).sum(), lr)
+    img_close(img.numpy(), ref.detach().numpy(), 1e-4)
+    assert np.linalg.norm(dlat.numpy() - gref.numpy()) <= 2e-4 * np.linalg.norm(gref.numpy())
