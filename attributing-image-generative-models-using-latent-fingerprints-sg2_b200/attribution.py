@@ -1,0 +1,164 @@
+"""Batched latent-optimisation engine: the reference's hot loop (``optimization`` in
+src/main.py:45-89) for B trajectories at once on one GPU, every step through the native path.
+
+One trajectory = one (image, Latin-hypercube guess) pair.  Trajectories never interact: Adam
+state is per element, the lr schedule ``lr * exp(-0.001 (i+1))`` (src/main.py:42-43) is shared,
+the loss is per trajectory, and the native kernels reduce in a fixed order per sample, so a
+trajectory's result is independent of what else is in its batch or on which rank it runs.
+
+Per step (src/main.py:58-70):
+    w0 = U^T alpha + mu ; wx = w0 + sd V^T diag(sigma) sigmoid(key)      lfp_embed_forward
+    est = G(wx, noise)                                                   lfp_synth_forward
+    loss = MSE(target, est) + 0.1 * alpha_bound(alpha)                   lfp_mse_loss_grad (+ bound)
+    backward to (alpha, key)                                             lfp_synth_backward, lfp_embed_backward
+    Adam(lr_i)                                                           per-element update
+The perceptual (LPIPS-VGG16) loss of the reference is outside this path;
+``loss="mse"`` is the reference's own alternative (src/utils.py:46-47).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from lfp_native import capi
+from lfp_native.synthesis import SynthesisPlan
+from lfp_native.torch_glue import ptr, stream_ptr
+
+
+def get_lr(step: int, lr0: float = 0.2) -> float:
+    """src/main.py:42-43."""
+    return lr0 * math.exp(-0.001 * (step + 1))
+
+
+class AttributionEngine:
+    def __init__(self, plan: SynthesisPlan, noise: Sequence[torch.Tensor], pc: torch.Tensor,
+                 sigma_512: torch.Tensor, latent_mean: torch.Tensor, key_len: int = 64, shift: int = 448,
+                 sigma: float = 1.0, sd: float = 1.0, lr: float = 0.2, precision: int = capi.PREC_FP32):
+        self.plan, self.device = plan, plan.device
+        dev, f32 = self.device, torch.float32
+        dim = pc.shape[0]
+        self.dim, self.key_len, self.n_main = dim, key_len, dim - key_len
+        pc = pc.to(dev, f32)
+        s512 = sigma_512.to(dev, f32).reshape(-1)
+        # get_uv / get_alpha_bound (src/main.py:23-40)
+        self.V = pc[shift:shift + key_len].contiguous()
+        self.U = torch.cat([pc[:shift], pc[shift + key_len:dim]], 0).contiguous()
+        self.sigma_key = torch.full((key_len,), float(sigma), device=dev, dtype=f32)
+        self.sigma_main = torch.cat([s512[:shift], s512[shift + key_len:dim]], 0).contiguous()
+        self.max_alpha, self.min_alpha = 3 * self.sigma_main, -3 * self.sigma_main
+        self.mu = latent_mean.to(dev, f32).reshape(-1).contiguous()
+        self.sd, self.lr0, self.precision = float(sd), float(lr), precision
+        self.noise = [n.to(dev, f32).contiguous() for n in noise]
+        self._ws = None
+        self._mse_scratch = None
+
+    # ---- pieces -------------------------------------------------------------------------------
+    def embed(self, alpha: torch.Tensor, key: torch.Tensor):
+        """alpha [B, n_main], key logits [B, key_len] -> (w0, wx) [B, dim]."""
+        B = alpha.shape[0]
+        w0 = torch.empty(B, self.dim, device=self.device)
+        wx = torch.empty_like(w0)
+        capi.check(capi.lib().lfp_embed_forward(ptr(alpha), ptr(key), ptr(self.U), ptr(self.V), ptr(self.sigma_key),
+                                                ptr(self.mu), self.sd, B, self.n_main, self.key_len, self.dim,
+                                                ptr(w0), ptr(wx), stream_ptr(self.device)), "embed_forward")
+        return w0, wx
+
+    def embed_with_key(self, alpha: torch.Tensor, key_bits: torch.Tensor):
+        """generate_with_alpha's latent (src/generator.py:83-89): binary key instead of sigmoid(logits)."""
+        w0 = alpha @ self.U + self.mu
+        wx = w0 + self.sd * ((self.sigma_key * key_bits.to(w0.dtype)) @ self.V)
+        return w0, wx
+
+    def render(self, wx: torch.Tensor) -> torch.Tensor:
+        """generate_image (src/generator.py:170-174) for B latents, no gradient kept."""
+        B = wx.shape[0]
+        latent = wx[:, None, :].expand(B, self.plan.n_latent, self.dim).contiguous()
+        return self.plan.forward(latent, self.noise, self.plan.shared_workspace(B), self.precision)
+
+    def loss_and_grad(self, wx: torch.Tensor, target: torch.Tensor):
+        """MSE(target, G(wx)) per trajectory and its gradient w.r.t. wx.  target [1 or B, 3, S, S]."""
+        B = wx.shape[0]
+        L = capi.lib()
+        if self._ws is None or self._ws.numel() < self.plan.workspace_bytes(B) + 256:
+            self._ws = None
+            self._ws = self.plan.new_workspace(B)
+        latent = wx[:, None, :].expand(B, self.plan.n_latent, self.dim).contiguous()
+        img = self.plan.forward(latent, self.noise, self._ws, self.precision)
+        numel = img[0].numel()
+        nb = L.lfp_mse_scratch_bytes(B, numel)
+        if self._mse_scratch is None or self._mse_scratch.numel() < nb:
+            self._mse_scratch = torch.empty(max(nb, 4), dtype=torch.uint8, device=self.device)
+        loss = torch.empty(B, device=self.device)
+        d_img = torch.empty_like(img)
+        capi.check(L.lfp_mse_loss_grad(ptr(img), ptr(target), target.shape[0], B, numel, ptr(loss), ptr(d_img),
+                                       ptr(self._mse_scratch), self._mse_scratch.numel(), stream_ptr(self.device)),
+                   "mse_loss_grad")
+        d_latent = self.plan.backward(d_img, B, self._ws, self.precision)
+        return loss, d_latent.sum(1), img
+
+    def loss_and_grad_host(self, wx_host: torch.Tensor, target: torch.Tensor, loss_host: torch.Tensor,
+                           dwx_host: torch.Tensor) -> None:
+        """End-to-end call with HOST (pinned) buffers: H2D of the latents, synthesis forward +
+        backward, D2H of the per-trajectory loss and d(loss)/d(wx); synchronous."""
+        wx = wx_host.to(self.device, non_blocking=True)
+        loss, dwx, _ = self.loss_and_grad(wx, target)
+        loss_host.copy_(loss, non_blocking=True)
+        dwx_host.copy_(dwx, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # ---- the loop -----------------------------------------------------------------------------
+    def init_state(self, alpha0: torch.Tensor, optimise_alpha: bool = True):
+        """alpha0 [B, n_main]; key logits start at zero (src/utils.py:19-21)."""
+        alpha = alpha0.to(self.device, torch.float32).clone().contiguous()
+        key = torch.zeros(alpha.shape[0], self.key_len, device=self.device)
+        z = torch.zeros_like
+        return dict(alpha=alpha, key=key, m_a=z(alpha), v_a=z(alpha), m_k=z(key), v_k=z(key), step=0,
+                    optimise_alpha=optimise_alpha, loss=None)
+
+    def alpha0_from_lhs(self, u: torch.Tensor) -> torch.Tensor:
+        """LHS sample in (0,1) -> ``2 u sigma - sigma`` (src/main.py:52)."""
+        u = u.to(self.device, torch.float32)
+        return 2 * u * self.sigma_main - self.sigma_main
+
+    @staticmethod
+    def _adam(p, g, m, v, t, lr, b1=0.9, b2=0.999, eps=1e-8):
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (v.sqrt() / math.sqrt(1 - b2 ** t)).add_(eps)
+        p.addcdiv_(m, denom, value=-(lr / (1 - b1 ** t)))
+
+    def step(self, st: dict, target: torch.Tensor) -> None:
+        """One Adam step of every trajectory in ``st`` (no host synchronisation)."""
+        alpha, key = st["alpha"], st["key"]
+        B = alpha.shape[0]
+        w0, wx = self.embed(alpha, key)
+        mse, d_wx, _ = self.loss_and_grad(wx, target)
+        d_alpha = torch.empty_like(alpha)
+        d_key = torch.empty_like(key)
+        capi.check(capi.lib().lfp_embed_backward(ptr(d_wx), ptr(key), ptr(self.U), ptr(self.V), ptr(self.sigma_key),
+                                                 self.sd, B, self.n_main, self.key_len, self.dim, ptr(d_alpha),
+                                                 ptr(d_key), stream_ptr(self.device)), "embed_backward")
+        over, under = alpha - self.max_alpha, self.min_alpha - alpha
+        bound = torch.relu(over).sum(1) + torch.relu(under).sum(1)          # src/utils.py:53-58
+        d_alpha += 0.1 * ((over > 0).float() - (under > 0).float())
+        st["loss"] = mse + 0.1 * bound                                      # src/main.py:65
+        st["w0"] = w0
+        i = st["step"]
+        lr = get_lr(i, self.lr0)                                            # src/main.py:67
+        if st["optimise_alpha"]:
+            self._adam(alpha, d_alpha, st["m_a"], st["v_a"], i + 1, lr)
+        self._adam(key, d_key, st["m_k"], st["v_k"], i + 1, lr)
+        st["step"] = i + 1
+
+    def run(self, alpha0: torch.Tensor, target: torch.Tensor, steps: int, optimise_alpha: bool = True):
+        st = self.init_state(alpha0, optimise_alpha)
+        for _ in range(steps):
+            self.step(st, target)
+        return st
+
+    @staticmethod
+    def decode(key_logits: torch.Tensor) -> torch.Tensor:
+        """``round(sigmoid(key))`` (src/main.py:72)."""
+        return torch.round(torch.sigmoid(key_logits))

@@ -10,7 +10,22 @@
 
 #include "synth_kernels.cuh"
 
+#define LFP_PROF(h, kind, flops, bytes, s, call)            \
+  do {                                                      \
+    const bool _p = (h)->prof_begin(kind, flops, bytes, s); \
+    const int _r = (call);                                  \
+    (h)->prof_end(_p, s);                                   \
+    if (_r != 0) return _r;                                 \
+  } while (0)
+
 namespace lfp {
+
+static double conv_flops(const ConvGeom& g) { return 2.0 * g.batch * g.gh * g.gw * g.ntaps * (double)g.K * g.N; }
+static double conv_bytes(const ConvGeom& g) {
+  // algorithmic: the input window the grid touches once + the output once + the taps used
+  const double in_px = (double)g.batch * (g.in_bstride == 0 ? 1.0 / g.batch : 1.0) * g.in_h * g.in_w;
+  return 4.0 * (in_px * g.K + (double)g.batch * g.gh * g.gw * g.N + (double)g.ntaps * g.K * g.N);
+}
 
 struct ConvLayer {
   std::string name;
@@ -58,8 +73,35 @@ struct lfp_synth {
   std::vector<int> fwd_noise_batch;
   std::vector<void*> owned;
 
+  // optional per-kernel-class timing with CUDA events on the launching stream
+  bool prof_on = false;
+  int prof_mask = 0;
+  std::vector<cudaEvent_t> prof_ev;       // pairs
+  std::vector<int> prof_kind;
+  size_t prof_used = 0;
+  double prof_flops[LFP_KIND_COUNT] = {0}, prof_bytes[LFP_KIND_COUNT] = {0};
+  int64_t prof_launches[LFP_KIND_COUNT] = {0};
+
   ~lfp_synth() {
     for (void* p : owned) cudaFree(p);
+    for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
+  }
+  bool prof_begin(int kind, double flops, double bytes, cudaStream_t s) {
+    if (!prof_on || !((prof_mask >> kind) & 1)) return false;
+    prof_flops[kind] += flops; prof_bytes[kind] += bytes; prof_launches[kind] += 1;
+    if (prof_used + 2 > prof_ev.size()) {
+      if (prof_ev.size() >= 400000) return false;
+      for (int i = 0; i < 2; ++i) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return false; prof_ev.push_back(e); }
+    }
+    if (prof_kind.size() < prof_ev.size() / 2) prof_kind.resize(prof_ev.size() / 2);
+    prof_kind[prof_used / 2] = kind;
+    cudaEventRecord(prof_ev[prof_used], s);
+    return true;
+  }
+  void prof_end(bool started, cudaStream_t s) {
+    if (!started) return;
+    cudaEventRecord(prof_ev[prof_used + 1], s);
+    prof_used += 2;
   }
   int alloc(float** p, size_t n) {
     LFP_CUDA(cudaMalloc((void**)p, n * sizeof(float)));
@@ -349,7 +391,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
       plain_taps(g);
       ConvEpiArgs e;
       e.demod = dmod; e.noise = noise[c.noise_idx]; e.noise_bstride = nstride; e.noise_w = c.noise_w; e.bias = c.act_bias;
-      LFP_TRY(launch_conv_simt(x, smod, c.wf, act, g, EPI_ACT, e, s));
+      LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_simt(x, smod, c.wf, act, g, EPI_ACT, e, s));
     } else {
       // stride-2 transposed conv as four sub-pixel phases into [B, 2H+1, 2W+1, Cout], then blur+epilogue
       float* T = ws + L.scratchT;
@@ -366,12 +408,12 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
               g.dy[t] = (signed char)(ky == 2 ? -1 : 0); g.dx[t] = (signed char)(kx == 2 ? -1 : 0); g.widx[t] = (signed char)(ky * 3 + kx); ++t;
             }
           g.ntaps = t;
-          LFP_TRY(launch_conv_simt(x, smod, c.wf, T, g, EPI_STORE, ConvEpiArgs{}, s));
+          LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_simt(x, smod, c.wf, T, g, EPI_STORE, ConvEpiArgs{}, s));
         }
       FirArgs f{};
       f.batch = B; f.in_h = f.in_w = 2 * H + 1; f.out_h = f.out_w = 2 * H; f.C = c.cout; f.pad = 1; f.coef = h->fir + 0;
       f.act = true; f.demod = dmod; f.noise = noise[c.noise_idx]; f.noise_bstride = nstride; f.noise_w = c.noise_w; f.bias = c.act_bias;
-      LFP_TRY(launch_fir4x4_nhwc(T, act, f, s));
+      LFP_PROF(h, LFP_KIND_FIR, 0.0, 4.0 * B * c.cout * ((double)f.in_h * f.in_w + (double)f.out_h * f.out_w), s, launch_fir4x4_nhwc(T, act, f, s));
     }
     x = act;
     x_bstride = (int64_t)c.res_out * c.res_out * c.cout;
@@ -381,7 +423,8 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
       const bool last = ri + 1 == h->rgbs.size();
       float* dst = last ? image : ws + r.skip_off;
       const float* skip = ri == 0 ? nullptr : ws + h->rgbs[ri - 1].skip_off;
-      LFP_TRY(launch_torgb_fwd(act, s_all + (size_t)B * r.row0, r.wrgb, r.bias, skip, h->fir + 32, dst, B, r.res, r.res, r.cin, s));
+      LFP_PROF(h, LFP_KIND_TORGB, 0.0, 4.0 * B * r.res * r.res * (r.cin + 3.75), s,
+               launch_torgb_fwd(act, s_all + (size_t)B * r.row0, r.wrgb, r.bias, skip, h->fir + 32, dst, B, r.res, r.res, r.cin, s));
     }
   }
   h->fwd_batch = batch;
@@ -424,7 +467,7 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     ab.noise_w = c.noise_w; ab.bias = c.act_bias;
     if (r) { ab.drgb = dskip; ab.s_rgb = s_all + (size_t)B * r->row0; ab.wrgb = r->wrgb; }
     ab.pT = ws + L.pT; ab.pR = ws + L.pR;
-    LFP_TRY(launch_act_bwd(ab, s));
+    LFP_PROF(h, LFP_KIND_ACTBWD, 0.0, 4.0 * B * hw * c.cout * (g != nullptr ? 3.0 : 2.0), s, launch_act_bwd(ab, s));
     const int Q = hw / actbwd_seglen(hw, c.cout);
     LFP_TRY(launch_partial_reduce(ab.pT, T_all + (size_t)B * c.demod_off, B, Q, c.cout, c.cout, s));
     if (r) LFP_TRY(launch_partial_reduce(ab.pR, ds_all + (size_t)B * r->row0, B, Q, c.cout, c.cout, s));
@@ -447,7 +490,7 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
       float* T = ws + L.scratchT;
       FirArgs f{};
       f.batch = B; f.in_h = f.in_w = c.res_out; f.out_h = f.out_w = c.res_out + 1; f.C = c.cout; f.pad = 2; f.coef = h->fir + 16;
-      LFP_TRY(launch_fir4x4_nhwc(g, T, f, s));
+      LFP_PROF(h, LFP_KIND_FIR, 0.0, 4.0 * B * c.cout * ((double)f.in_h * f.in_w + (double)f.out_h * f.out_w), s, launch_fir4x4_nhwc(g, T, f, s));
       gin = T;
       gg.in_h = gg.in_w = c.res_out + 1; gg.in_stride = 2; gg.in_bstride = (int64_t)(c.res_out + 1) * (c.res_out + 1) * c.cout;
       gg.ntaps = 9;
@@ -457,7 +500,8 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     ConvEpiArgs e;
     e.mod_out = s_all + (size_t)B * c.row0; e.xsave = xin; e.xsave_bstride = xin_bstride; e.partial = ws + L.pX;
     float* dx = li == 0 ? nullptr : other;
-    LFP_TRY(launch_conv_simt(gin, nullptr, c.wg, dx, gg, EPI_DGRAD, e, s));
+    LFP_PROF(h, LFP_KIND_CONV_DGRAD, conv_flops(gg), conv_bytes(gg) + 4.0 * B * c.res_in * c.res_in * c.cin, s,
+             launch_conv_simt(gin, nullptr, c.wg, dx, gg, EPI_DGRAD, e, s));
     const int hwi = c.res_in * c.res_in;
     LFP_TRY(launch_partial_reduce(e.partial, R1_all + (size_t)B * c.row0, B, hwi / conv_dgrad_seglen(gg), c.cin, c.cin, s));
     LFP_TRY(launch_style_grad(R1_all + (size_t)B * c.row0, s_all + (size_t)B * c.row0, c.cin, T_all + (size_t)B * c.demod_off,
@@ -516,4 +560,25 @@ extern "C" int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const fl
   if (rc == 0 && e != cudaSuccess) { set_error("synth_host: %s", cudaGetErrorString(e)); rc = (int)e; }
   cleanup();
   return rc;
+}
+
+extern "C" int lfp_synth_profile_begin(lfp_synth* h, int kind_mask) {
+  LFP_CHECK_ARG(h != nullptr, "profile_begin: null plan");
+  h->prof_on = true; h->prof_mask = kind_mask; h->prof_used = 0;
+  for (int k = 0; k < LFP_KIND_COUNT; ++k) { h->prof_flops[k] = 0; h->prof_bytes[k] = 0; h->prof_launches[k] = 0; }
+  return 0;
+}
+
+extern "C" int lfp_synth_profile_end(lfp_synth* h, double* ms, int64_t* launches, double* flops, double* bytes) {
+  LFP_CHECK_ARG(h != nullptr && ms && launches && flops && bytes, "profile_end: null argument");
+  h->prof_on = false;
+  for (int k = 0; k < LFP_KIND_COUNT; ++k) { ms[k] = 0; launches[k] = h->prof_launches[k]; flops[k] = h->prof_flops[k]; bytes[k] = h->prof_bytes[k]; }
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    LFP_CUDA(cudaEventSynchronize(h->prof_ev[i + 1]));
+    float t = 0.f;
+    LFP_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+    ms[h->prof_kind[i / 2]] += t;
+  }
+  h->prof_used = 0;
+  return 0;
 }

@@ -11,6 +11,7 @@ _LOCK = threading.Lock()
 
 F32, F64, F16 = 0, 1, 2
 PREC_FP32, PREC_TF32 = 0, 1
+KINDS = ("conv_fwd", "conv_dgrad", "fir", "torgb", "act_bwd")
 
 
 class LfpError(RuntimeError):
@@ -43,6 +44,9 @@ _PROTOS = {
     "lfp_synth_forward": (_i, [_vp, _i, _vp, C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _sz, _i, _vp]),
     "lfp_synth_backward": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "lfp_synth_forward_backward_host": (_i, [_vp, _i, _vp, C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _vp, _i]),
+    "lfp_synth_profile_begin": (_i, [_vp, _i]),
+    "lfp_synth_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]),
     "lfp_embed_forward": (_i, [_vp] * 6 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_embed_backward": (_i, [_vp] * 5 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_mse_loss_grad": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),

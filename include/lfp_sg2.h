@@ -143,6 +143,20 @@ int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const float* latent
                                     float* image, const float* d_image, float* d_latent,
                                     int precision);
 
+/* Per-kernel-class timing with CUDA events recorded on the launching stream (bench.py's
+ * roofline leg).  profile_begin(mask) starts recording every launch whose class bit is set;
+ * profile_end synchronises the recorded events and returns, per class, the summed device time
+ * in ms, the launch count and the algorithmic flops / bytes of those launches (arrays of
+ * LFP_KIND_COUNT entries). */
+#define LFP_KIND_CONV_FWD 0
+#define LFP_KIND_CONV_DGRAD 1
+#define LFP_KIND_FIR 2
+#define LFP_KIND_TORGB 3
+#define LFP_KIND_ACTBWD 4
+#define LFP_KIND_COUNT 5
+int lfp_synth_profile_begin(lfp_synth* h, int kind_mask);
+int lfp_synth_profile_end(lfp_synth* h, double* ms, int64_t* launches, double* flops, double* bytes);
+
 /* ---------------------------------------------------------------------------------
  * 4. Fingerprint embed + loss glue used by the attribution loop (additive).
  *    w0 = U^T alpha + mu (src/main.py:60); wx = w0 + sd * V^T diag(sigma) sigmoid(key)

@@ -1,0 +1,112 @@
+"""GPU parity of the batched attribution engine (attribution.AttributionEngine) against the
+reference's own loop (golden vectors from main.optimization) and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import fixtures as fx
+import oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def make_engine(size, seed, **kw):
+    from lfp_native.synthesis import SynthesisPlan
+    from attribution import AttributionEngine
+    params = fx.make_params(size, seed)
+    noise = fx.make_noise(size, seed + 1)
+    pc, sigma, mean = fx.make_pca_basis(2)
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(params)
+    eng = AttributionEngine(plan, noise, pc, sigma, mean, key_len=64, shift=448, sigma=1.0, sd=1.0, lr=0.2, **kw)
+    return eng, params, noise, fx.split_basis(pc, sigma, 64, 448, 1.0), mean
+
+
+def test_embed_matches_reference(golden):
+    eng, params, noise, sp, mean = make_engine(32, 11)
+    logits = fx.seeded((64, 1), 31)
+    w0 = fx.seeded((512, 1), 32)
+    # engine computes w0 itself; feed alpha = U (w0 - mu) so that U^T alpha + mu reproduces a w0 in span(U)
+    alpha = sp["u_cap"] @ (w0 - mean)
+    w0_e, wx_e = eng.embed(alpha.t().contiguous().to(DEV), logits.t().contiguous().to(DEV))
+    w0_o = oracle.latent_from_alpha(sp["u_cap"], alpha, mean)
+    wx_o = oracle.embed_fingerprint(sp["v_cap"], sp["sigma_key"], torch.sigmoid(logits), w0_o, 1.0)
+    np.testing.assert_allclose(w0_e.cpu().numpy()[0], w0_o.numpy()[:, 0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(wx_e.cpu().numpy()[0], wx_o.numpy()[:, 0], rtol=1e-5, atol=1e-5)
+    # embed gradient against autograd of the oracle
+    a = alpha.clone().requires_grad_(True)
+    k = logits.clone().requires_grad_(True)
+    wx = oracle.embed_fingerprint(sp["v_cap"], sp["sigma_key"], torch.sigmoid(k), oracle.latent_from_alpha(sp["u_cap"], a, mean), 1.0)
+    ct = fx.seeded((512, 1), 36)
+    ga, gk = torch.autograd.grad((wx * ct).sum(), [a, k])
+    from lfp_native import capi
+    from lfp_native.torch_glue import ptr, stream_ptr
+    d_alpha = torch.empty(1, 448, device=DEV)
+    d_key = torch.empty(1, 64, device=DEV)
+    capi.check(capi.lib().lfp_embed_backward(ptr(ct.t().contiguous().to(DEV)), ptr(logits.t().contiguous().to(DEV)), ptr(eng.U),
+                                             ptr(eng.V), ptr(eng.sigma_key), 1.0, 1, 448, 64, 512, ptr(d_alpha), ptr(d_key),
+                                             stream_ptr(eng.device)))
+    np.testing.assert_allclose(d_alpha.cpu().numpy()[0], ga.numpy()[:, 0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(d_key.cpu().numpy()[0], gk.numpy()[:, 0], rtol=1e-4, atol=1e-6)
+
+
+def test_loop_matches_reference_optimization(golden):
+    """Both LHS guesses of the golden run, batched (B=2), 12 steps: per-guess final loss, alpha and key
+    logits against the reference's main.optimization (MSE stand-in loss)."""
+    eng, params, noise, sp, mean = make_engine(32, 11)
+    target = torch.from_numpy(golden["embed/gwa_img"]).to(DEV)
+    lhs = torch.from_numpy(golden["loop/lhs"])
+    st = eng.run(eng.alpha0_from_lhs(lhs), target, steps=12)
+    np.testing.assert_allclose(st["loss"].cpu().numpy(), golden["loop/loss"], rtol=5e-4)
+    np.testing.assert_allclose(st["alpha"].cpu().numpy(), golden["loop/alpha"][:, :, 0], rtol=0, atol=3e-3)
+    np.testing.assert_allclose(st["key"].cpu().numpy(), golden["loop/key"][:, :, 0], rtol=0, atol=3e-3)
+    best = int(torch.argmin(st["loss"]))
+    true_key = torch.from_numpy(golden["embed/gwa_key"]).float()[:, 0]
+    acc = (eng.decode(st["key"][best]).cpu() == true_key).float().mean().item()
+    assert abs(acc - float(golden["loop/acc"])) < 1e-6
+    # batched == one at a time, bit for bit (trajectories are independent)
+    st0 = eng.run(eng.alpha0_from_lhs(lhs[:1]), target, steps=12)
+    assert torch.equal(st0["key"][0], st["key"][0]) and torch.equal(st0["alpha"][0], st["alpha"][0])
+
+
+def test_key_only_fixture_recovers_the_true_key():
+    """The well-posed known-answer test for 'decoded keys identical' (SURVEY.md 7.3): alpha frozen at
+    the truth, only the key logits optimised; engine and oracle must both decode the TRUE key, with
+    margins, and agree with each other."""
+    size, seed, steps = 32, 11, 100
+    eng, params, noise, sp, mean = make_engine(size, seed)
+    alpha = sp["sigma_main"] * fx.seeded((448, 1), 33)
+    key = (fx.seeded((64, 1), 35) > 0).long()
+    with torch.no_grad():
+        target, _, _ = oracle.generate_with_alpha(params, size, alpha, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean,
+                                                  key, noise)
+    # engine's own target must match the oracle's
+    _, wx_t = eng.embed_with_key(alpha.t().to(DEV), key.t().to(DEV))
+    tgt = eng.render(wx_t).clone()
+    assert (tgt.cpu() - target).abs().max() <= 1e-4 * max(1.0, target.abs().max())
+    st = eng.run(alpha.t().contiguous(), tgt, steps=steps, optimise_alpha=False)
+
+    def render(wx):
+        return oracle.generator_forward(params, [wx.reshape(1, -1)], size, input_is_latent=True, noise=noise)
+
+    _, _, k_or = oracle.attribute_one_guess(render, target, alpha, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean,
+                                            sp["max_alpha"], sp["min_alpha"], steps=steps, optimise_alpha=False)
+    dec_e = eng.decode(st["key"][0]).cpu()
+    dec_o = oracle.decode_key(k_or)[:, 0]
+    assert torch.equal(dec_e, key[:, 0].float()), "engine did not recover the true key"
+    assert torch.equal(dec_o, key[:, 0].float()), "oracle did not recover the true key"
+    margin = (torch.sigmoid(st["key"][0]) - 0.5).abs().min().item()
+    assert margin >= 0.2, margin
+    np.testing.assert_allclose(st["key"][0].cpu().numpy(), k_or[:, 0].numpy(), rtol=0, atol=5e-3)
+
+
+def test_host_buffer_step_matches_device_step():
+    eng, params, noise, sp, mean = make_engine(16, 21)
+    B = 3
+    wx = fx.seeded((B, 512), 22)
+    target = eng.render(fx.seeded((1, 512), 23).to(DEV)).clone()
+    loss_d, dwx_d, _ = eng.loss_and_grad(wx.to(DEV), target)
+    wx_h, loss_h, dwx_h = wx.pin_memory(), torch.empty(B).pin_memory(), torch.empty(B, 512).pin_memory()
+    eng.loss_and_grad_host(wx_h, target, loss_h, dwx_h)
+    assert torch.equal(loss_h, loss_d.cpu()) and torch.equal(dwx_h, dwx_d.cpu())
