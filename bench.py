@@ -127,7 +127,7 @@ def oracle_step_fn(size, torch):
         est = oracle.generator_forward(params, [wx.reshape(1, -1)], size, input_is_latent=True, noise=noise)
         loss = oracle.mse_loss(target, est) + 0.1 * oracle.alpha_bound(a, sp["max_alpha"], sp["min_alpha"])
         torch.autograd.grad(loss, [a, k])
-        return float(loss)
+        return float(loss.detach())
 
     return step
 

@@ -44,7 +44,8 @@ def test_embed_matches_reference(golden):
     from lfp_native.torch_glue import ptr, stream_ptr
     d_alpha = torch.empty(1, 448, device=DEV)
     d_key = torch.empty(1, 64, device=DEV)
-    capi.check(capi.lib().lfp_embed_backward(ptr(ct.t().contiguous().to(DEV)), ptr(logits.t().contiguous().to(DEV)), ptr(eng.U),
+    ct_d, logits_d = ct.t().contiguous().to(DEV), logits.t().contiguous().to(DEV)   # keep alive across the launch
+    capi.check(capi.lib().lfp_embed_backward(ptr(ct_d), ptr(logits_d), ptr(eng.U),
                                              ptr(eng.V), ptr(eng.sigma_key), 1.0, 1, 448, 64, 512, ptr(d_alpha), ptr(d_key),
                                              stream_ptr(eng.device)))
     np.testing.assert_allclose(d_alpha.cpu().numpy()[0], ga.numpy()[:, 0], rtol=1e-4, atol=1e-5)
