@@ -519,6 +519,22 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
   return 0;
 }
 
+extern "C" int lfp_synth_num_convs(const lfp_synth* h) { return h ? (int)h->convs.size() : 0; }
+
+extern "C" int lfp_synth_read_activation(lfp_synth* h, int batch, int conv_index, const void* workspace,
+                                         float* out, int* channels, int* res, void* stream) {
+  LFP_CHECK_ARG(h != nullptr, "read_activation: null plan");
+  LFP_CHECK_ARG(conv_index >= 0 && conv_index < (int)h->convs.size(), "read_activation: conv index %d out of range", conv_index);
+  const ConvLayer& c = h->convs[conv_index];
+  if (channels) *channels = c.cout;
+  if (res) *res = c.res_out;
+  if (out == nullptr) return 0;
+  LFP_CHECK_ARG(workspace != nullptr && batch >= 1, "read_activation: null workspace or bad batch");
+  if (h->fwd_batch != batch) { set_error("read_activation: no forward with batch %d on this plan", batch); return LFP_ESTATE; }
+  h->layout(batch);
+  return launch_nhwc_to_nchw((const float*)workspace + c.act_off, out, batch, c.cout, c.res_out * c.res_out, (cudaStream_t)stream);
+}
+
 extern "C" int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const float* latent,
                                                const float* const* noise, const int* noise_batch,
                                                float* image, const float* d_image, float* d_latent,

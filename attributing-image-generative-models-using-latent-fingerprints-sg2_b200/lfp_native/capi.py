@@ -43,6 +43,8 @@ _PROTOS = {
     "lfp_synth_workspace_bytes": (_sz, [_vp, _i]),
     "lfp_synth_forward": (_i, [_vp, _i, _vp, C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _sz, _i, _vp]),
     "lfp_synth_backward": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "lfp_synth_num_convs": (_i, [_vp]),
+    "lfp_synth_read_activation": (_i, [_vp, _i, _i, _vp, _vp, C.POINTER(_i), C.POINTER(_i), _vp]),
     "lfp_synth_forward_backward_host": (_i, [_vp, _i, _vp, C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _vp, _i]),
     "lfp_synth_profile_begin": (_i, [_vp, _i]),
     "lfp_synth_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),

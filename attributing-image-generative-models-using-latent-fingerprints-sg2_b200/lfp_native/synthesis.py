@@ -130,6 +130,21 @@ class SynthesisPlan:
         self._keep = (latent, nz)  # pointers recorded by the plan must outlive the backward
         return image
 
+    def read_activations(self, batch: int, ws: torch.Tensor) -> List[torch.Tensor]:
+        """Saved StyledConv outputs of the last forward on ``ws`` as [B, C, res, res] tensors."""
+        L = capi.lib()
+        outs = []
+        base = self._aligned(ws)
+        with torch.cuda.device(self.device):
+            for i in range(L.lfp_synth_num_convs(self._h)):
+                ch, res = C.c_int(), C.c_int()
+                capi.check(L.lfp_synth_read_activation(self._h, batch, i, None, None, C.byref(ch), C.byref(res), None))
+                t = torch.empty((batch, ch.value, res.value, res.value), dtype=torch.float32, device=self.device)
+                capi.check(L.lfp_synth_read_activation(self._h, batch, i, base, ptr(t), None, None,
+                                                       stream_ptr(self.device)), "read_activation")
+                outs.append(t)
+        return outs
+
     def backward(self, d_image: torch.Tensor, batch: int, ws: torch.Tensor,
                  precision: int = capi.PREC_FP32) -> torch.Tensor:
         d_image = d_image.to(torch.float32).contiguous()

@@ -135,6 +135,15 @@ int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, const float*
 int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image, float* d_latent,
                        void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* Inspection: copy the saved output of StyledConv `conv_index` (0 = conv1, 1 + i = convs.i,
+ * src/model.py:552-563) of the last forward on `workspace` to `out` as [B, C, res, res] (NCHW,
+ * device pointer).  Returns the channel count and resolution through `channels` / `res` (either
+ * may be NULL; `out` may be NULL to query only).  Parity tests use it to compare leaky-ReLU
+ * branch patterns with the oracle. */
+int lfp_synth_num_convs(const lfp_synth* h);
+int lfp_synth_read_activation(lfp_synth* h, int batch, int conv_index, const void* workspace,
+                              float* out, int* channels, int* res, void* stream);
+
 /* Host-buffer convenience (what a non-torch caller binds): latent / noise / image / d_image /
  * d_latent are HOST pointers; copies are inside the call; synchronous.  d_image may be NULL
  * (forward only). */

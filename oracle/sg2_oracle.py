@@ -276,7 +276,24 @@ def modulated_conv2d_unfused(x, style, weight, mod_weight, mod_bias, *, demodula
     return y
 
 
-def styled_conv(params, prefix, x, style, noise, *, upsample=False, fused=True):
+def lrelu_with_sign(x, bias, sign_mask, negative_slope: float = 0.2, scale: float = 2 ** 0.5):
+    """``fused_leaky_relu`` with the branch of every unit taken from ``sign_mask`` (bool, True =
+    positive side) instead of from ``x + b > 0``.
+
+    Checker-only helper: leaky-ReLU is continuous, so for a unit whose pre-activation is
+    numerically zero the value is the same on either branch but the derivative is not
+    (1 vs ``negative_slope``).  Two correct fp32 implementations pick different branches
+    for such units (measured: 1-2 units per 10^5 between the reference's own fused and
+    unfused algebra), which moves the latent gradient by ~1e-3.  Gradient parity is
+    therefore checked with the branch pattern of the implementation under test imposed
+    here, and the pattern itself is checked separately (it may differ only where
+    ``|x + b|`` is at rounding level).
+    """
+    v = x + bias.reshape([1, -1] + [1] * (x.ndim - 2)).to(x.dtype)
+    return torch.where(sign_mask, v, v * negative_slope) * scale
+
+
+def styled_conv(params, prefix, x, style, noise, *, upsample=False, fused=True, sign_mask=None):
     """ModulatedConv2d -> noise injection -> bias + lrelu*sqrt2 (src/model.py:360-366)."""
     conv = modulated_conv2d if fused else modulated_conv2d_unfused
     y = conv(x, style, params[f"{prefix}.conv.weight"], params[f"{prefix}.conv.modulation.weight"],
@@ -284,6 +301,8 @@ def styled_conv(params, prefix, x, style, noise, *, upsample=False, fused=True):
     if noise is None:  # src/model.py:312-314
         noise = torch.randn(y.shape[0], 1, y.shape[2], y.shape[3], dtype=y.dtype)
     y = y + params[f"{prefix}.noise.weight"] * noise              # src/model.py:316
+    if sign_mask is not None:
+        return lrelu_with_sign(y, params[f"{prefix}.activate.bias"], sign_mask)
     return fused_leaky_relu(y, params[f"{prefix}.activate.bias"])
 
 
@@ -299,19 +318,29 @@ def to_rgb(params, prefix, x, style, skip=None, *, fused=True):
     return y
 
 
-def synthesis(params, latent, noise: Sequence[Optional[torch.Tensor]], *, fused=True):
-    """Latent ``[B, n_latent, 512]`` -> image ``[B, 3, S, S]`` (src/model.py:551-566)."""
+def synthesis(params, latent, noise: Sequence[Optional[torch.Tensor]], *, fused=True,
+              sign_masks=None, activations=None):
+    """Latent ``[B, n_latent, 512]`` -> image ``[B, 3, S, S]`` (src/model.py:551-566).
+
+    ``sign_masks`` (checker-only, see ``lrelu_with_sign``): one bool tensor per StyledConv in
+    execution order.  ``activations``: optional list that receives every StyledConv output.
+    """
     b = latent.shape[0]
+    masks = list(sign_masks) if sign_masks is not None else [None] * (latent.shape[1] - 1)
+    keep = activations if activations is not None else []
     x = params["input.input"].repeat(b, 1, 1, 1)                  # src/model.py:325-329
-    x = styled_conv(params, "conv1", x, latent[:, 0], noise[0], fused=fused)
+    x = styled_conv(params, "conv1", x, latent[:, 0], noise[0], fused=fused, sign_mask=masks[0])
+    keep.append(x)
     skip = to_rgb(params, "to_rgb1", x, latent[:, 1], fused=fused)
     n_blocks = (latent.shape[1] - 2) // 2
     slot = 1
     for j in range(n_blocks):
         x = styled_conv(params, f"convs.{2 * j}", x, latent[:, slot], noise[1 + 2 * j],
-                        upsample=True, fused=fused)
+                        upsample=True, fused=fused, sign_mask=masks[1 + 2 * j])
+        keep.append(x)
         x = styled_conv(params, f"convs.{2 * j + 1}", x, latent[:, slot + 1], noise[2 + 2 * j],
-                        fused=fused)
+                        fused=fused, sign_mask=masks[2 + 2 * j])
+        keep.append(x)
         skip = to_rgb(params, f"to_rgbs.{j}", x, latent[:, slot + 2], skip, fused=fused)
         slot += 2
     return skip

@@ -54,14 +54,33 @@ def test_embed_matches_reference(golden):
 
 def test_loop_matches_reference_optimization(golden):
     """Both LHS guesses of the golden run, batched (B=2), 12 steps: per-guess final loss, alpha and key
-    logits against the reference's main.optimization (MSE stand-in loss)."""
+    logits against the reference's main.optimization (MSE stand-in loss).
+
+    The loop amplifies rounding differences (Adam at lr 0.2 divides by |g| for the first steps; the MSE
+    gradient is a difference of nearly equal images): measured against the CPU oracle the free-running
+    drift is 5e-4 in alpha after 2 steps and 1.6e-2 after 12 while every teacher-forced step agrees to
+    1e-6 in the loss (tools/diag_loop.py; the reference's own fused vs unfused algebra drift alike,
+    SURVEY.md 7.3).  Hence: tight after 2 steps against the oracle, loose after 12 against the golden run."""
     eng, params, noise, sp, mean = make_engine(32, 11)
     target = torch.from_numpy(golden["embed/gwa_img"]).to(DEV)
     lhs = torch.from_numpy(golden["loop/lhs"])
+    # 2 steps against the oracle loop
+    st2 = eng.run(eng.alpha0_from_lhs(lhs[:1]), target, steps=2)
+
+    def render(wx):
+        return oracle.generator_forward(params, [wx.reshape(1, -1)], 32, input_is_latent=True, noise=noise)
+
+    a0 = (2 * lhs[:1] * sp["sigma_main"].t() - sp["sigma_main"].t()).t().contiguous()
+    l_o, a_o, k_o = oracle.attribute_one_guess(render, target.cpu(), a0, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean,
+                                               sp["max_alpha"], sp["min_alpha"], steps=2)
+    np.testing.assert_allclose(float(st2["loss"][0]), float(l_o), rtol=1e-5)
+    np.testing.assert_allclose(st2["alpha"][0].cpu().numpy(), a_o[:, 0].detach().numpy(), rtol=0, atol=2e-3)
+    np.testing.assert_allclose(st2["key"][0].cpu().numpy(), k_o[:, 0].detach().numpy(), rtol=0, atol=2e-3)
+    # 12 steps against the reference's own run
     st = eng.run(eng.alpha0_from_lhs(lhs), target, steps=12)
-    np.testing.assert_allclose(st["loss"].cpu().numpy(), golden["loop/loss"], rtol=5e-4)
-    np.testing.assert_allclose(st["alpha"].cpu().numpy(), golden["loop/alpha"][:, :, 0], rtol=0, atol=3e-3)
-    np.testing.assert_allclose(st["key"].cpu().numpy(), golden["loop/key"][:, :, 0], rtol=0, atol=3e-3)
+    np.testing.assert_allclose(st["loss"].cpu().numpy(), golden["loop/loss"], rtol=2e-2)
+    np.testing.assert_allclose(st["alpha"].cpu().numpy(), golden["loop/alpha"][:, :, 0], rtol=0, atol=6e-2)
+    np.testing.assert_allclose(st["key"].cpu().numpy(), golden["loop/key"][:, :, 0], rtol=0, atol=6e-2)
     best = int(torch.argmin(st["loss"]))
     true_key = torch.from_numpy(golden["embed/gwa_key"]).float()[:, 0]
     acc = (eng.decode(st["key"][best]).cpu() == true_key).float().mean().item()

@@ -3,8 +3,17 @@ the reference-generated golden vectors and the CPU oracle.
 
 Tolerances (fp32 path): images are compared on their own scale - random-init images are not in
 [-1,1] - so the north-star bar "max-abs <= 1e-3 on [-1,1] pixels" is applied as
-max-abs <= 1e-3 * max(1, max|ref|); latent gradients to 1e-3 relative L2.  Measured differences are
-two orders of magnitude below both."""
+max-abs <= 1e-3 * max(1, max|ref|) (asserted at 1e-4; measured ~1e-5).
+
+Latent gradients: leaky-ReLU has a kink at 0.  A unit whose pre-activation is at rounding level
+(|v| ~ 1e-6; there are a few per 10^5 units) lands on either side depending on summation order,
+which changes its derivative from 1 to 0.2 and the latent gradient by ~1e-3 relative - the
+reference's own fused vs unfused algebra differ by exactly that much on the same fixtures
+(measured on CPU: 1 flipped unit -> 1.1e-3).  So the gradient bar is split in two:
+  * `grad_parity`: with the branch pattern of the CUDA path imposed on the oracle
+    (oracle.lrelu_with_sign), gradients agree to 5e-5 relative L2 (pure arithmetic parity);
+  * the branch patterns themselves may differ only at units with |activation| < 1e-4.
+Free-running comparisons (golden vectors from the reference, Generator-level tests) use 5e-3."""
 import numpy as np
 import pytest
 import torch
@@ -23,6 +32,46 @@ def build_generator(size, seed, cm=2):
     missing = g.load_state_dict(fx.make_params(size, seed, cm), strict=False)
     assert not missing.unexpected_keys
     return g.eval().to(DEV)
+
+
+KINK_TOL = 5e-3   # free-running gradient tolerance (see module docstring)
+
+
+def grad_parity(size, seed, lat, noise, cm=2, precision=None, img_tol=1e-4, grad_tol=5e-5, flip_band=1e-4):
+    """Plan-level forward/backward against the oracle with the CUDA path's lrelu branches imposed."""
+    from lfp_native import capi
+    from lfp_native.synthesis import SynthesisPlan
+    precision = capi.PREC_FP32 if precision is None else precision
+    params = fx.make_params(size, seed, cm)
+    plan = SynthesisPlan(size, channel_multiplier=cm, device=DEV)
+    plan.load(params)
+    B = lat.shape[0]
+    ws = plan.new_workspace(B)
+    img = plan.forward(lat.to(DEV), [n.to(DEV) for n in noise], ws, precision)
+    acts = [a.cpu() for a in plan.read_activations(B, ws)]
+    ct = fx.seeded(tuple(img.shape), seed + 3)
+    d_lat = plan.backward(ct.to(DEV), B, ws, precision).cpu()
+    # oracle, free-running: image and activations
+    ref_acts = []
+    with torch.no_grad():
+        ref = oracle.synthesis(params, lat, noise, activations=ref_acts)
+    img_close(img.cpu().numpy(), ref.numpy(), img_tol)
+    flips = 0
+    for a, r in zip(acts, ref_acts):
+        assert a.shape == r.shape
+        diff = (a > 0) != (r > 0)
+        flips += int(diff.sum())
+        if diff.any():   # branches may differ only where the activation is numerically zero
+            assert float(r[diff].abs().max()) < flip_band * max(1.0, float(r.abs().max()))
+    # oracle with the CUDA path's branch pattern: arithmetic parity of the gradient
+    lr = lat.clone().requires_grad_(True)
+    refm = oracle.synthesis(params, lr, noise, sign_masks=[a > 0 for a in acts])
+    (gref,) = torch.autograd.grad((refm * ct).sum(), lr)
+    rel = float((d_lat - gref).norm() / gref.norm())
+    assert rel <= grad_tol, (rel, flips)
+    per_slot = ((d_lat - gref).flatten(2).norm(dim=2) / gref.flatten(2).norm(dim=2)).max()
+    assert float(per_slot) <= 4 * grad_tol, float(per_slot)
+    return rel, flips
 
 
 def img_close(a, ref, tol=1e-3):
@@ -45,7 +94,7 @@ def test_generator_golden(golden, case):
     (gw,) = torch.autograd.grad((img * ct).sum(), w)
     gref = golden[f"gen/{name}/gw"]
     rel = np.linalg.norm(gw.cpu().numpy() - gref) / np.linalg.norm(gref)
-    assert rel <= 1e-4, rel
+    assert rel <= KINK_TOL, rel
     # mapping network + z input
     z = fx.seeded((3, 512), seed + 4).to(DEV)
     with torch.no_grad():
@@ -71,7 +120,18 @@ def test_generator_vs_oracle(size, B):
     img_close(img.detach().cpu().numpy(), ref.detach().numpy(), 1e-4)
     (gw,) = torch.autograd.grad((img * ct.to(DEV)).sum(), wg)
     rel = np.linalg.norm(gw.cpu().numpy() - gref.numpy()) / np.linalg.norm(gref.numpy())
-    assert rel <= 2e-4, rel
+    assert rel <= KINK_TOL, rel
+    # arithmetic parity proper: per-slot latents, CUDA branch pattern imposed on the oracle
+    lat = fx.seeded((B, oracle.n_latent(size), 512), seed + 5)
+    grad_parity(size, seed, lat, noise)
+
+
+@pytest.mark.parametrize("size,cm,B", [(64, 1, 2), (32, 2, 4)])
+def test_gradient_parity_with_imposed_branches(size, cm, B):
+    seed = 90 + size
+    noise = fx.make_noise(size, seed + 1, batch=B)
+    lat = fx.seeded((B, oracle.n_latent(size), 512), seed + 2)
+    grad_parity(size, seed, lat, noise, cm=cm)
 
 
 def test_per_sample_noise_style_mixing_and_per_slot_gradient():
@@ -90,7 +150,8 @@ def test_per_sample_noise_style_mixing_and_per_slot_gradient():
     (gl,) = torch.autograd.grad((img * ct.to(DEV)).sum(), lg)
     assert gl.shape == lat.shape
     rel = np.linalg.norm(gl.cpu().numpy() - gref.numpy()) / np.linalg.norm(gref.numpy())
-    assert rel <= 2e-4, rel
+    assert rel <= KINK_TOL, rel
+    grad_parity(size, seed, lat, noise)
     # style mixing goes through the same latent assembly as the reference (src/model.py:536-548)
     w1, w2 = fx.seeded((B, 512), 40), fx.seeded((B, 512), 41)
     mixed = torch.cat([w1[:, None].repeat(1, 4, 1), w2[:, None].repeat(1, oracle.n_latent(size) - 4, 1)], 1)
@@ -161,4 +222,4 @@ def test_host_buffer_entry_point_matches():
     ref = oracle.synthesis(params, lr, noise)
     (gref,) = torch.autograd.grad((ref * ct).sum(), lr)
     img_close(img.numpy(), ref.detach().numpy(), 1e-4)
-    assert np.linalg.norm(dlat.numpy() - gref.numpy()) <= 2e-4 * np.linalg.norm(gref.numpy())
+    assert np.linalg.norm(dlat.numpy() - gref.numpy()) <= KINK_TOL * np.linalg.norm(gref.numpy())
