@@ -1,0 +1,403 @@
+// Implicit-GEMM modulated convolution on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   D[128 pixels, BN channels] (fp32, TMEM)  +=  A[128 pixels, 32 ch] (tf32, smem) * B[BN, 32 ch]^T (tf32, smem)
+//
+// * One CTA = one 8 (x) x 16 (y) tile of output-grid pixels of one sample x one BN-wide slice of the
+//   output channels.  M = 128 is the UMMA M; a pixel is row m = 8*y + x of the accumulator.
+// * A: TMA loads the haloed 10 x 18 window of the NHWC activation (32 channels = one 128-byte row per
+//   pixel, SWIZZLE_128B, out-of-range pixels zero-filled by TMA = the conv padding) ONCE per 32-channel
+//   chunk; every filter tap (dy,dx) then reads the same image through a UMMA descriptor whose start
+//   address is shifted by (dy*10+dx) rows and whose 8-row-group pitch (SBO) is 10 rows.  The swizzle
+//   XOR is a function of the absolute smem address, so shifted starts stay consistent with what TMA
+//   wrote (verified on hardware by tools/umma_probe.cu).  No im2col, no 9x re-read.
+// * B: one TMA load of the [BN, 32] K-major weight slice per (chunk, tap); the weight is shared by
+//   all samples (activation-modulated algebra, src/model.py:229-256).
+// * Style modulation (src/model.py:259, folded onto the activations) is applied to the A image in
+//   shared memory by the four transform warps between TMA arrival and MMA issue, together with the
+//   round-to-nearest tf32 conversion; demodulation, noise, bias and leaky-ReLU are the epilogue
+//   (src/model.py:261-263, 316, src/op/fused_act.py:110-127).
+// * Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-5 = A transform
+//   during the main loop, then TMEM -> register epilogue (each warp owns the 32 TMEM lanes
+//   32*(warp%4)..).  mbarrier rings: A (2 stages), B (4 stages).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "synth_kernels.cuh"
+
+namespace lfp {
+namespace tc {
+
+constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
+constexpr int A_ROWS = HALO_W * HALO_H;   // 180 rows of 128 bytes
+constexpr int A_BYTES = A_ROWS * 128;     // 23040
+constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
+constexpr int SA = 2, SB = 4;
+constexpr int NTHREADS = 192;
+constexpr int NBARS = 3 * SA + 2 * SB + 1;
+
+struct Args {
+  int batch, gh, gw, tiles_x, tiles_y, K, N, BN;
+  int in_bcast;
+  TcTaps taps;
+  float* out;
+  int out_planes, out_plane, out_h, out_w;
+  const float* mod;
+  ConvEpiArgs e;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (tcgen05), see tools/umma_probe.cu
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float lrelu(float v) { return (v > 0.f ? v : v * kLreluSlope) * kLreluGain; }
+
+template <int EPI, bool MOD>
+__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB, const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[NBARS];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_mod[MOD ? 512 : 4];
+  __shared__ float s_red[EPI == EPI_DGRAD ? 4 * 256 : 4];
+
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per = a.tiles_x * a.tiles_y;
+  const int b = blockIdx.x / tiles_per;
+  const int tile = blockIdx.x - b * tiles_per;
+  const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
+  const int y0 = ty * TILE_H, x0 = tx * TILE_W;
+  const int n0 = blockIdx.y * a.BN;
+  const uint32_t b_stage_bytes = (uint32_t)a.BN * 128u;
+  const uint32_t a_base = smem0, b_base = smem0 + SA * A_STAGE;
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_a_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_a_ready = [&](int s) { return bar0 + 8u * (SA + s); };
+  auto bar_a_empty = [&](int s) { return bar0 + 8u * (2 * SA + s); };
+  auto bar_b_full = [&](int s) { return bar0 + 8u * (3 * SA + s); };
+  auto bar_b_empty = [&](int s) { return bar0 + 8u * (3 * SA + SB + s); };
+  const uint32_t bar_acc = bar0 + 8u * (3 * SA + 2 * SB);
+
+  if (tid == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_ready(s), 128); mbar_init(bar_a_empty(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)a.BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (MOD)
+    for (int i = tid; i < a.K; i += NTHREADS) s_mod[i] = __ldg(a.mod + (int64_t)b * a.K + i);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const int kchunks = a.K >> 5;
+  const int ngroups = a.taps.ngroups;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int bin = a.in_bcast ? 0 : b;
+      for (int kc = 0; kc < kchunks; ++kc)
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(bar_a_empty(sa), pa ^ 1u);
+          mbar_expect_tx(bar_a_full(sa), A_BYTES);
+          tma_load_5d(a_base + sa * A_STAGE, &tmA, bar_a_full(sa), kc * 32, x0 - 1, y0 - 1, a.taps.group_plane[g], bin);
+          for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
+            mbar_wait(bar_b_empty(sb), pb ^ 1u);
+            mbar_expect_tx(bar_b_full(sb), b_stage_bytes);
+            tma_load_2d(b_base + sb * b_stage_bytes, &tmB, bar_b_full(sb), kc * 32, (int)a.taps.widx[t] * a.N + n0);
+            if (++sb == SB) { sb = 0; pb ^= 1u; }
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t accumulate = 0;
+      for (int kc = 0; kc < kchunks; ++kc)
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(MOD ? bar_a_ready(sa) : bar_a_full(sa), pa);
+          for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
+            mbar_wait(bar_b_full(sb), pb);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t shift = (uint32_t)(((int)a.taps.dy[t] + 1) * HALO_W + ((int)a.taps.dx[t] + 1));
+            const uint32_t a_addr = a_base + sa * A_STAGE + shift * 128u;
+            const uint32_t b_addr = b_base + sb * b_stage_bytes;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              umma_tf32(tmem, make_desc(a_addr + k8 * 32, HALO_W * 128), make_desc(b_addr + k8 * 32, 1024), idesc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(bar_b_empty(sb));
+            if (++sb == SB) { sb = 0; pb ^= 1u; }
+          }
+          umma_commit(bar_a_empty(sa));
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
+        }
+      umma_commit(bar_acc);
+    }
+  } else {
+    const int et = tid - 64;  // 0..127
+    if (MOD) {
+      // ---------------- A transform: x * s[b, k], rounded to tf32 ----------------
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int kc = 0; kc < kchunks; ++kc)
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(bar_a_full(sa), pa);
+          uint8_t* stage = smem_raw + (a_base - smem_u32(smem_raw)) + sa * A_STAGE;
+          const float* sm = s_mod + kc * 32;
+          for (int idx = et; idx < A_ROWS * 8; idx += 128) {
+            const int row = idx >> 3, pos = idx & 7;
+            const int ch = (pos ^ (row & 7)) << 2;
+            float4* p = reinterpret_cast<float4*>(stage + row * 128 + pos * 16);
+            float4 v = *p;
+            v.x = to_tf32(v.x * sm[ch + 0]);
+            v.y = to_tf32(v.y * sm[ch + 1]);
+            v.z = to_tf32(v.z * sm[ch + 2]);
+            v.w = to_tf32(v.w * sm[ch + 3]);
+            *p = v;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(bar_a_ready(sa));
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
+        }
+    }
+    // ---------------- epilogue ----------------
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int gy = y0 + (m >> 3), gx = x0 + (m & 7);
+    const bool valid = gy < a.gh && gx < a.gw;
+    const int pix = gy * a.gw + gx;
+    float nz = 0.f;
+    if (EPI == EPI_ACT && valid) nz = __ldg(a.e.noise_w) * __ldg(a.e.noise + (int64_t)b * a.e.noise_bstride + pix);
+    float* outp = nullptr;
+    if (a.out != nullptr && valid)
+      outp = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
+    const float* xs = nullptr;
+    if (EPI == EPI_DGRAD && valid) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
+    float* scr = reinterpret_cast<float*>(smem_raw + (a_base - smem_u32(smem_raw))) + q * (32 * 33);
+
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int nchunk = a.BN >> 5;
+    for (int c = 0; c < nchunk; ++c) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+          "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int nc = n0 + c * 32;
+      if (EPI == EPI_ACT) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.e.demod + (int64_t)b * a.N + nc + j * 4));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.e.bias + nc + j * 4));
+          float4 v;
+          v.x = lrelu(fmaf(__uint_as_float(r[j * 4 + 0]), d4.x, nz) + b4.x);
+          v.y = lrelu(fmaf(__uint_as_float(r[j * 4 + 1]), d4.y, nz) + b4.y);
+          v.z = lrelu(fmaf(__uint_as_float(r[j * 4 + 2]), d4.z, nz) + b4.z);
+          v.w = lrelu(fmaf(__uint_as_float(r[j * 4 + 3]), d4.w, nz) + b4.w);
+          if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = v;
+        }
+      } else if (EPI == EPI_STORE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (outp)
+            *reinterpret_cast<float4*>(outp + c * 32 + j * 4) =
+                make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
+                            __uint_as_float(r[j * 4 + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (xs) x4 = __ldg(reinterpret_cast<const float4*>(xs + c * 32 + j * 4));
+          const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.e.mod_out + (int64_t)b * a.N + nc + j * 4));
+          const float v0 = __uint_as_float(r[j * 4 + 0]), v1 = __uint_as_float(r[j * 4 + 1]);
+          const float v2 = __uint_as_float(r[j * 4 + 2]), v3 = __uint_as_float(r[j * 4 + 3]);
+          scr[lane * 33 + j * 4 + 0] = x4.x * v0;
+          scr[lane * 33 + j * 4 + 1] = x4.y * v1;
+          scr[lane * 33 + j * 4 + 2] = x4.z * v2;
+          scr[lane * 33 + j * 4 + 3] = x4.w * v3;
+          if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = make_float4(v0 * m4.x, v1 * m4.y, v2 * m4.z, v3 * m4.w);
+        }
+        __syncwarp();
+        float sum = 0.f;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) sum += scr[l * 33 + lane];  // fixed order: deterministic
+        __syncwarp();
+        s_red[q * 256 + c * 32 + lane] = sum;
+      }
+    }
+    if (EPI == EPI_DGRAD) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int n = et; n < a.BN; n += 128)
+        a.e.partial[((int64_t)b * tiles_per + tile) * a.N + n0 + n] =
+            ((s_red[n] + s_red[256 + n]) + s_red[512 + n]) + s_red[768 + n];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)a.BN));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+  if (fn == nullptr) { set_error("conv_tc: cuTensorMapEncodeTiled is not available from this driver"); return LFP_EUNSUPPORTED; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return LFP_EINVAL; }
+  return 0;
+}
+
+}  // namespace tc
+
+int tc_block_n(int N) { return N >= 256 ? 256 : N; }
+int tc_tiles_per_sample(int gh, int gw) { return (int)(ceil_div(gw, tc::TILE_W) * ceil_div(gh, tc::TILE_H)); }
+bool tc_supported(int K, int N, int gh, int gw) {
+  const int bn = tc_block_n(N);
+  const bool n_ok = (bn == 32 || bn == 64 || bn == 128 || bn == 256) && N % bn == 0;
+  return K % 32 == 0 && K <= 512 && n_ok && gh >= 8 && gw >= 8;
+}
+
+int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N) {
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)tc_block_n(N)};
+  return tc::encode(reinterpret_cast<CUtensorMap*>(map_out), table, 2, dims, strides, box);
+}
+
+template <int EPI, bool MOD>
+static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Args& a, dim3 grid, size_t smem, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  tc::conv_tc_kernel<EPI, MOD><<<grid, tc::NTHREADS, smem, s>>>(tmA, tmB, a);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_conv_tc(const TcConv& c, cudaStream_t s) {
+  LFP_CHECK_ARG(tc_supported(c.K, c.N, c.gh, c.gw), "conv_tc: unsupported shape K=%d N=%d grid %dx%d", c.K, c.N, c.gh, c.gw);
+  LFP_CHECK_ARG(c.taps.ngroups >= 1 && c.taps.ngroups <= 4 && c.taps.group_tap0[c.taps.ngroups] <= 9, "conv_tc: bad tap table");
+  LFP_CHECK_ARG(((uintptr_t)c.in & 15) == 0 && c.wmap != nullptr, "conv_tc: input must be 16-byte aligned");
+  alignas(64) CUtensorMap tmA;
+  const int nb = c.in_bcast ? 1 : c.batch;
+  const cuuint64_t dims[5] = {(cuuint64_t)c.K, (cuuint64_t)c.in_w, (cuuint64_t)c.in_h, (cuuint64_t)c.in_planes, (cuuint64_t)nb};
+  const cuuint64_t strides[4] = {(cuuint64_t)c.K * 4, (cuuint64_t)c.in_w * c.K * 4, (cuuint64_t)c.in_h * c.in_w * c.K * 4,
+                                 (cuuint64_t)c.in_planes * c.in_h * c.in_w * c.K * 4};
+  const cuuint32_t box[5] = {32, tc::HALO_W, tc::HALO_H, 1, 1};
+  LFP_TRY(tc::encode(&tmA, c.in, 5, dims, strides, box));
+  tc::Args a{};
+  a.batch = c.batch; a.gh = c.gh; a.gw = c.gw;
+  a.tiles_x = (int)ceil_div(c.gw, tc::TILE_W); a.tiles_y = (int)ceil_div(c.gh, tc::TILE_H);
+  a.K = c.K; a.N = c.N; a.BN = tc_block_n(c.N);
+  a.in_bcast = c.in_bcast ? 1 : 0;
+  a.taps = c.taps;
+  a.out = c.out; a.out_planes = c.out_planes; a.out_plane = c.out_plane; a.out_h = c.out_h; a.out_w = c.out_w;
+  a.mod = c.mod; a.e = c.e;
+  const dim3 grid((unsigned)(a.tiles_x * a.tiles_y * c.batch), (unsigned)(c.N / a.BN));
+  const size_t smem = (size_t)tc::SA * tc::A_STAGE + (size_t)tc::SB * a.BN * 128 + 1024;
+  const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(c.wmap);
+  const bool mod = c.mod != nullptr;
+  if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, a, grid, smem, s) : tc_launch<EPI_ACT, false>(tmA, tmB, a, grid, smem, s);
+  if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, a, grid, smem, s) : tc_launch<EPI_STORE, false>(tmA, tmB, a, grid, smem, s);
+  LFP_CHECK_ARG(!mod, "conv_tc: the data-gradient kernel takes an unmodulated input");
+  return tc_launch<EPI_DGRAD, false>(tmA, tmB, a, grid, smem, s);
+}
+
+}  // namespace lfp

@@ -235,15 +235,23 @@ __global__ void __launch_bounds__(256) fir4x4_nhwc_kernel(const float* __restric
 #pragma unroll
   for (int i = 0; i < 16; ++i) coef[i] = __ldg(a.coef + i);
   const int C = a.C;
-  const float* src = in + (int64_t)b * a.in_h * a.in_w * C + c4 * 4;
+  const int64_t in_per = a.in_planar ? (int64_t)4 * ((a.in_h + 1) >> 1) * ((a.in_w + 1) >> 1) : (int64_t)a.in_h * a.in_w;
+  const int64_t out_per = a.out_planar ? (int64_t)4 * ((a.out_h + 1) >> 1) * ((a.out_w + 1) >> 1) : (int64_t)a.out_h * a.out_w;
+  const float* src = in + (int64_t)b * in_per * C + c4 * 4;
   float4 win[4][4];
   auto load_row = [&](int iy, float4(&row)[4]) {
 #pragma unroll
     for (int tx = 0; tx < 4; ++tx) {
       const int ix = ox + tx - a.pad;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < a.in_h && ix >= 0 && ix < a.in_w)
-        v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)iy * a.in_w + ix) * C));
+      if (iy >= 0 && iy < a.in_h && ix >= 0 && ix < a.in_w) {
+        int64_t e = (int64_t)iy * a.in_w + ix;
+        if (a.in_planar) {
+          const int ph = (a.in_h + 1) >> 1, pw = (a.in_w + 1) >> 1;
+          e = ((int64_t)((iy & 1) * 2 + (ix & 1)) * ph + (iy >> 1)) * pw + (ix >> 1);
+        }
+        v = __ldg(reinterpret_cast<const float4*>(src + e * C));
+      }
       row[tx] = v;
     }
   };
@@ -275,7 +283,12 @@ __global__ void __launch_bounds__(256) fir4x4_nhwc_kernel(const float* __restric
         acc.z = lrelu_fwd(fmaf(acc.z, d4.z, nz) + bias4.z);
         acc.w = lrelu_fwd(fmaf(acc.w, d4.w, nz) + bias4.w);
       }
-      *reinterpret_cast<float4*>(out + (((int64_t)b * a.out_h + oy) * a.out_w + ox) * C + c4 * 4) = acc;
+      int64_t oe = (int64_t)oy * a.out_w + ox;
+      if (a.out_planar) {
+        const int ph = (a.out_h + 1) >> 1, pw = (a.out_w + 1) >> 1;
+        oe = ((int64_t)((oy & 1) * 2 + (ox & 1)) * ph + (oy >> 1)) * pw + (ox >> 1);
+      }
+      *reinterpret_cast<float4*>(out + ((int64_t)b * out_per + oe) * C + c4 * 4) = acc;
     }
   }
 }
@@ -657,6 +670,22 @@ __global__ void prep_conv3x3_kernel(const float* __restrict__ W, float scale, fl
 int launch_prep_conv3x3(const float* W, float scale, float* wf, float* wg, float* wsq, int cin,
                         int cout, cudaStream_t st) {
   prep_conv3x3_kernel<<<(unsigned)ceil_div((int64_t)cin * cout, 256), 256, 0, st>>>(W, scale, wf, wg, wsq, cin, cout);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(src[i]));
+    dst[i] = __uint_as_float(r);
+  }
+}
+int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 4096) blocks = 4096;
+  round_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n);
   LFP_LAUNCH_CHECK();
   return 0;
 }

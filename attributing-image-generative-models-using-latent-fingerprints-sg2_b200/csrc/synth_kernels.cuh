@@ -51,11 +51,38 @@ int launch_conv_simt(const float* in, const float* mod, const float* wtab, float
                      const ConvGeom& g, int epi, const ConvEpiArgs& e, cudaStream_t s);
 int conv_dgrad_seglen(const ConvGeom& g);   // pixels per partial row (power of two <= 128)
 
+// ---- tensor-core (tcgen05, tf32) version of the same gather convolution, csrc/conv_tc.cu ----
+// Taps are organised in up to four groups; every group reads one "plane" of the input tensor
+// [B, in_planes, in_h, in_w, K] (planes = the four sub-pixel phases of the stride-2 transposed
+// conv's [2H+1, 2W+1] intermediate stored phase-major; 1 plane for ordinary activations).
+// Tap t of group g contributes in[b, plane_g, gy + dy[t], gx + dx[t], :] * wtab[widx[t]], dy,dx in [-1,1].
+struct TcTaps {
+  int ngroups;
+  int group_plane[4];
+  int group_tap0[5];  // taps of group g are [group_tap0[g], group_tap0[g+1])
+  signed char dy[9], dx[9], widx[9];
+};
+struct TcConv {
+  const float* in; int in_planes, in_h, in_w; bool in_bcast;
+  const float* mod;   // [B, K] style (forward) or null
+  const void* wmap;   // CUtensorMap of the K-major weight table [ntaps * N, K] (tc_make_weight_map)
+  float* out; int out_planes, out_plane, out_h, out_w;   // out tensor [B, out_planes, out_h, out_w, N]
+  int batch, gh, gw, K, N;
+  TcTaps taps;
+  int epi; ConvEpiArgs e;   // EPI_DGRAD: partial rows are [b * tc_tiles_per_sample + tile]
+};
+int launch_conv_tc(const TcConv& c, cudaStream_t s);
+bool tc_supported(int K, int N, int gh, int gw);
+int tc_tiles_per_sample(int gh, int gw);
+int tc_make_weight_map(void* map_out_128B, const float* table, int rows, int K, int N);
+
 // 4x4 FIR on NHWC: out[b,oy,ox,c] = sum_{ty,tx} in[b, oy+ty-pad, ox+tx-pad, c] * coef[ty*4+tx]
 // optional fused epilogue (same as EPI_ACT).  coef is a device pointer to 16 floats.
 struct FirArgs {
   int batch, in_h, in_w, out_h, out_w, C, pad;
   const float* coef;
+  // phase-major storage of the odd-sized side ([B, 4, (n+1)/2, (n+1)/2, C], plane = (y&1)*2 + (x&1))
+  bool in_planar = false, out_planar = false;
   bool act = false;
   const float* demod = nullptr; const float* noise = nullptr; int64_t noise_bstride = 0;
   const float* noise_w = nullptr; const float* bias = nullptr;
@@ -114,6 +141,7 @@ int launch_style_grad(const float* r1, const float* s, int64_t s_bstride, const 
 //   wf[t][ci][co] = scale*W[co][ci][t], wg[t][co][ci] = scale*W[co][ci][t], wsq[co][ci] = sum_t (scale*W)^2
 int launch_prep_conv3x3(const float* W, float scale, float* wf, float* wg, float* wsq, int cin,
                         int cout, cudaStream_t st);
+int launch_round_tf32(const float* src, float* dst, int64_t n, cudaStream_t st);
 int launch_scale_copy(const float* src, float* dst, float scale, int64_t n, cudaStream_t st);
 
 // NHWC [B,H,W,C] <-> NCHW [B,C,H,W] (layer-level entry points / tests only)

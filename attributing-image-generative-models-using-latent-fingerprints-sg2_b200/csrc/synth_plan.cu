@@ -4,6 +4,7 @@
 // Replaces the module chain of Generator.forward(input_is_latent=True), src/model.py:551-566.
 // Layer order, channel table and latent-slot indexing follow src/model.py:418-474, 551-564.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -27,6 +28,8 @@ static double conv_bytes(const ConvGeom& g) {
   return 4.0 * (in_px * g.K + (double)g.batch * g.gh * g.gw * g.N + (double)g.ntaps * g.K * g.N);
 }
 
+struct alignas(64) TmapBuf { unsigned char bytes[128]; };  // a CUtensorMap
+
 struct ConvLayer {
   std::string name;
   int cin = 0, cout = 0, res_in = 0, res_out = 0;
@@ -34,6 +37,9 @@ struct ConvLayer {
   int slot = 0, noise_idx = 0;
   float *W = nullptr, *modw = nullptr, *modb = nullptr, *noise_w = nullptr, *act_bias = nullptr;
   float *wf = nullptr, *wg = nullptr, *wsq = nullptr;
+  float *wf_t = nullptr, *wg_t = nullptr;   // tf32-rounded copies for the tensor-core path
+  TmapBuf map_fwd, map_bwd;                 // weight tensor maps: forward reads wg_t [t][co][ci], dgrad wf_t [t][ci][co]
+  bool tc_fwd = false, tc_bwd = false;
   int row0 = 0;       // first row in the stacked modulation matrix
   int demod_off = 0;  // offset into the demod table (units of cout, times batch at run time)
   size_t act_off = 0; // workspace offset (floats) of the saved output activation
@@ -68,6 +74,7 @@ struct lfp_synth {
   float* fir = nullptr;  // 4 x 16 floats: blur fwd coef, blur bwd coef, upsample kernel, flipped upsample kernel
   float blur1d[4] = {1, 3, 3, 1};
   bool finalized = false;
+  int tc_min_res = 8;   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
   int fwd_batch = -1;
   std::vector<const float*> fwd_noise;
   std::vector<int> fwd_noise_batch;
@@ -142,14 +149,17 @@ Layout lfp_synth::layout(int B) const {
     const size_t nin = (size_t)B * c.res_in * c.res_in * c.cin;
     if (nin > max_act) max_act = nin;
     if (c.up) {
-      const size_t t = (size_t)B * (c.res_out + 1) * (c.res_out + 1) * c.cout;
+      // interleaved [2H+1, 2H+1] (fp32 path) or phase-major [4, H+1, H+1] (tensor-core path)
+      const size_t t = (size_t)B * (c.res_out + 2) * (c.res_out + 2) * c.cout;
       if (t > max_T) max_T = t;
     }
     const int hw = c.res_out * c.res_out;
     const size_t pt = (size_t)B * (hw / actbwd_seglen(hw, c.cout)) * c.cout;
     if (pt > max_pT) max_pT = pt;
     const int hwi = c.res_in * c.res_in;
-    const size_t px = (size_t)B * (hwi / (hwi < 128 ? hwi : 128)) * c.cin;
+    size_t px = (size_t)B * (hwi / (hwi < 128 ? hwi : 128)) * c.cin;
+    const size_t px_tc = (size_t)B * tc_tiles_per_sample(c.res_in, c.res_in) * c.cin;
+    if (px_tc > px) px = px_tc;
     if (px > max_pX) max_pX = px;
   }
   for (size_t i = 0; i < rgbs.size(); ++i)
@@ -186,6 +196,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   h->n_latent = ls * 2 - 2;
   h->num_noise = (ls - 2) * 2 + 1;
   if (blur_kernel_1d) memcpy(h->blur1d, blur_kernel_1d, 4 * sizeof(float));
+  if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 8) h->tc_min_res = v; }
   for (int r = 4; r <= size; r *= 2) {
     const int c = h->channels(r);
     if (c % 16 != 0 || 1024 % c != 0) {
@@ -228,6 +239,8 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
     rc |= h->alloc(&c.wf, (size_t)9 * c.cin * c.cout);
     rc |= h->alloc(&c.wg, (size_t)9 * c.cin * c.cout);
     rc |= h->alloc(&c.wsq, (size_t)c.cin * c.cout);
+    rc |= h->alloc(&c.wf_t, (size_t)9 * c.cin * c.cout);
+    rc |= h->alloc(&c.wg_t, (size_t)9 * c.cin * c.cout);
   }
   for (RgbLayer& r : h->rgbs) {
     rc |= h->alloc(&r.W, (size_t)3 * r.cin);
@@ -323,6 +336,12 @@ extern "C" int lfp_synth_finalize(lfp_synth* h, void* stream) {
   for (ConvLayer& c : h->convs) {
     const float wscale = 1.f / sqrtf((float)(c.cin * 9));  // src/model.py:208-209
     LFP_TRY(launch_prep_conv3x3(c.W, wscale, c.wf, c.wg, c.wsq, c.cin, c.cout, s));
+    LFP_TRY(launch_round_tf32(c.wf, c.wf_t, (int64_t)9 * c.cin * c.cout, s));
+    LFP_TRY(launch_round_tf32(c.wg, c.wg_t, (int64_t)9 * c.cin * c.cout, s));
+    c.tc_fwd = tc_supported(c.cin, c.cout, 8, 8);
+    c.tc_bwd = tc_supported(c.cout, c.cin, 8, 8);
+    if (c.tc_fwd) LFP_TRY(tc_make_weight_map(c.map_fwd.bytes, c.wg_t, 9 * c.cout, c.cin, c.cout));
+    if (c.tc_bwd) LFP_TRY(tc_make_weight_map(c.map_bwd.bytes, c.wf_t, 9 * c.cin, c.cout, c.cin));
     LFP_TRY(launch_scale_copy(c.modw, h->A_all + (size_t)c.row0 * h->style_dim, mscale, (int64_t)c.cin * h->style_dim, s));
     LFP_TRY(launch_scale_copy(c.modb, h->b_all + c.row0, 1.f, c.cin, s));
   }
@@ -353,7 +372,7 @@ static int check_run(const lfp_synth* h, int batch, const void* ws, size_t ws_by
   if (!h->finalized) { set_error("synth: lfp_synth_finalize has not been called since the last set_param"); return LFP_ESTATE; }
   if (ws_bytes < h->layout(batch).total * sizeof(float)) { set_error("synth: workspace too small (%zu < %zu bytes)", ws_bytes, h->layout(batch).total * sizeof(float)); return LFP_ENOMEM; }
   LFP_CHECK_ARG(((uintptr_t)ws & 255) == 0, "synth: workspace must be 256-byte aligned");
-  if (precision != LFP_PREC_FP32) { set_error("synth: precision mode %d not available in this build", precision); return LFP_EUNSUPPORTED; }
+  if (precision != LFP_PREC_FP32 && precision != LFP_PREC_TF32) { set_error("synth: unknown precision mode %d", precision); return LFP_EINVAL; }
   return 0;
 }
 
@@ -384,6 +403,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
     const float* dmod = d_all + (size_t)B * c.demod_off;
     const int nb = noise_batch[c.noise_idx];
     const int64_t nstride = nb == 1 ? 0 : (int64_t)c.res_out * c.res_out;
+    const bool use_tc = precision == LFP_PREC_TF32 && c.tc_fwd && c.res_in >= h->tc_min_res;
     if (!c.up) {
       ConvGeom g{};
       g.batch = B; g.gh = g.gw = c.res_out; g.in_h = g.in_w = c.res_in; g.in_bstride = x_bstride; g.in_stride = 1;
@@ -391,7 +411,18 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
       plain_taps(g);
       ConvEpiArgs e;
       e.demod = dmod; e.noise = noise[c.noise_idx]; e.noise_bstride = nstride; e.noise_w = c.noise_w; e.bias = c.act_bias;
-      LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_simt(x, smod, c.wf, act, g, EPI_ACT, e, s));
+      if (use_tc) {
+        TcConv t{};
+        t.in = x; t.in_planes = 1; t.in_h = t.in_w = c.res_in; t.in_bcast = x_bstride == 0; t.mod = smod; t.wmap = c.map_fwd.bytes;
+        t.out = act; t.out_planes = 1; t.out_plane = 0; t.out_h = t.out_w = c.res_out;
+        t.batch = B; t.gh = t.gw = c.res_out; t.K = c.cin; t.N = c.cout;
+        t.taps.ngroups = 1; t.taps.group_plane[0] = 0; t.taps.group_tap0[0] = 0; t.taps.group_tap0[1] = 9;
+        for (int i = 0; i < 9; ++i) { t.taps.dy[i] = g.dy[i]; t.taps.dx[i] = g.dx[i]; t.taps.widx[i] = g.widx[i]; }
+        t.epi = EPI_ACT; t.e = e;
+        LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_tc(t, s));
+      } else {
+        LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_simt(x, smod, c.wf, act, g, EPI_ACT, e, s));
+      }
     } else {
       // stride-2 transposed conv as four sub-pixel phases into [B, 2H+1, 2W+1, Cout], then blur+epilogue
       float* T = ws + L.scratchT;
@@ -408,9 +439,22 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
               g.dy[t] = (signed char)(ky == 2 ? -1 : 0); g.dx[t] = (signed char)(kx == 2 ? -1 : 0); g.widx[t] = (signed char)(ky * 3 + kx); ++t;
             }
           g.ntaps = t;
-          LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_simt(x, smod, c.wf, T, g, EPI_STORE, ConvEpiArgs{}, s));
+          if (use_tc) {
+            // same phase, written dense into plane a*2+bb of the phase-major intermediate [B, 4, H+1, H+1, Cout]
+            TcConv q{};
+            q.in = x; q.in_planes = 1; q.in_h = q.in_w = H; q.in_bcast = x_bstride == 0; q.mod = smod; q.wmap = c.map_fwd.bytes;
+            q.out = T; q.out_planes = 4; q.out_plane = a * 2 + bb; q.out_h = q.out_w = H + 1;
+            q.batch = B; q.gh = g.gh; q.gw = g.gw; q.K = c.cin; q.N = c.cout;
+            q.taps.ngroups = 1; q.taps.group_plane[0] = 0; q.taps.group_tap0[0] = 0; q.taps.group_tap0[1] = t;
+            for (int i = 0; i < t; ++i) { q.taps.dy[i] = g.dy[i]; q.taps.dx[i] = g.dx[i]; q.taps.widx[i] = g.widx[i]; }
+            q.epi = EPI_STORE;
+            LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_tc(q, s));
+          } else {
+            LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_simt(x, smod, c.wf, T, g, EPI_STORE, ConvEpiArgs{}, s));
+          }
         }
       FirArgs f{};
+      f.in_planar = use_tc;
       f.batch = B; f.in_h = f.in_w = 2 * H + 1; f.out_h = f.out_w = 2 * H; f.C = c.cout; f.pad = 1; f.coef = h->fir + 0;
       f.act = true; f.demod = dmod; f.noise = noise[c.noise_idx]; f.noise_bstride = nstride; f.noise_w = c.noise_w; f.bias = c.act_bias;
       LFP_PROF(h, LFP_KIND_FIR, 0.0, 4.0 * B * c.cout * ((double)f.in_h * f.in_w + (double)f.out_h * f.out_w), s, launch_fir4x4_nhwc(T, act, f, s));
@@ -480,7 +524,15 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     gg.batch = B; gg.gh = gg.gw = c.res_in; gg.in_bstride = 0; gg.K = c.cout; gg.N = c.cin;
     gg.out_h = gg.out_w = c.res_in; gg.out_stride = 1; gg.out_oy = gg.out_ox = 0;
     const float* gin = g;
+    const bool use_tc = precision == LFP_PREC_TF32 && c.tc_bwd && c.res_in >= h->tc_min_res;
+    TcConv tq{};
+    tq.in_bcast = false; tq.mod = nullptr; tq.wmap = c.map_bwd.bytes;
+    tq.out_planes = 1; tq.out_plane = 0; tq.out_h = tq.out_w = c.res_in;
+    tq.batch = B; tq.gh = tq.gw = c.res_in; tq.K = c.cout; tq.N = c.cin; tq.epi = EPI_DGRAD;
     if (!c.up) {
+      tq.in_planes = 1; tq.in_h = tq.in_w = c.res_out;
+      tq.taps.ngroups = 1; tq.taps.group_plane[0] = 0; tq.taps.group_tap0[0] = 0; tq.taps.group_tap0[1] = 9;
+      for (int i = 0; i < 9; ++i) { tq.taps.dy[i] = (signed char)(1 - i / 3); tq.taps.dx[i] = (signed char)(1 - i % 3); tq.taps.widx[i] = (signed char)i; }
       gg.in_h = gg.in_w = c.res_out; gg.in_stride = 1; gg.in_bstride = (int64_t)hw * c.cout;
       gg.ntaps = 9;
       for (int ky = 0; ky < 3; ++ky)
@@ -490,6 +542,22 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
       float* T = ws + L.scratchT;
       FirArgs f{};
       f.batch = B; f.in_h = f.in_w = c.res_out; f.out_h = f.out_w = c.res_out + 1; f.C = c.cout; f.pad = 2; f.coef = h->fir + 16;
+      f.out_planar = use_tc;
+      // tensor-core path: T' is phase-major [B, 4, H+1, H+1, Cout]; dx(y,x) = sum T'(2y+ky, 2x+kx) W[ky,kx] reads plane
+      // (ky&1, kx&1) at (y + (ky>>1), x + (kx>>1))
+      tq.in_planes = 4; tq.in_h = tq.in_w = c.res_in + 1;
+      tq.taps.ngroups = 4;
+      {
+        int t = 0;
+        for (int py = 0; py < 2; ++py)
+          for (int px = 0; px < 2; ++px) {
+            const int gi = py * 2 + px;
+            tq.taps.group_plane[gi] = gi; tq.taps.group_tap0[gi] = t;
+            for (int ky = py; ky < 3; ky += 2)
+              for (int kx = px; kx < 3; kx += 2) { tq.taps.dy[t] = (signed char)(ky >> 1); tq.taps.dx[t] = (signed char)(kx >> 1); tq.taps.widx[t] = (signed char)(ky * 3 + kx); ++t; }
+          }
+        tq.taps.group_tap0[4] = t;
+      }
       LFP_PROF(h, LFP_KIND_FIR, 0.0, 4.0 * B * c.cout * ((double)f.in_h * f.in_w + (double)f.out_h * f.out_w), s, launch_fir4x4_nhwc(g, T, f, s));
       gin = T;
       gg.in_h = gg.in_w = c.res_out + 1; gg.in_stride = 2; gg.in_bstride = (int64_t)(c.res_out + 1) * (c.res_out + 1) * c.cout;
@@ -500,10 +568,18 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     ConvEpiArgs e;
     e.mod_out = s_all + (size_t)B * c.row0; e.xsave = xin; e.xsave_bstride = xin_bstride; e.partial = ws + L.pX;
     float* dx = li == 0 ? nullptr : other;
-    LFP_PROF(h, LFP_KIND_CONV_DGRAD, conv_flops(gg), conv_bytes(gg) + 4.0 * B * c.res_in * c.res_in * c.cin, s,
-             launch_conv_simt(gin, nullptr, c.wg, dx, gg, EPI_DGRAD, e, s));
     const int hwi = c.res_in * c.res_in;
-    LFP_TRY(launch_partial_reduce(e.partial, R1_all + (size_t)B * c.row0, B, hwi / conv_dgrad_seglen(gg), c.cin, c.cin, s));
+    int Qx = 0;
+    if (use_tc) {
+      tq.in = gin; tq.out = dx; tq.e = e;
+      LFP_PROF(h, LFP_KIND_CONV_DGRAD, conv_flops(gg), conv_bytes(gg) + 4.0 * B * c.res_in * c.res_in * c.cin, s, launch_conv_tc(tq, s));
+      Qx = tc_tiles_per_sample(c.res_in, c.res_in);
+    } else {
+      LFP_PROF(h, LFP_KIND_CONV_DGRAD, conv_flops(gg), conv_bytes(gg) + 4.0 * B * c.res_in * c.res_in * c.cin, s,
+               launch_conv_simt(gin, nullptr, c.wg, dx, gg, EPI_DGRAD, e, s));
+      Qx = hwi / conv_dgrad_seglen(gg);
+    }
+    LFP_TRY(launch_partial_reduce(e.partial, R1_all + (size_t)B * c.row0, B, Qx, c.cin, c.cin, s));
     LFP_TRY(launch_style_grad(R1_all + (size_t)B * c.row0, s_all + (size_t)B * c.row0, c.cin, T_all + (size_t)B * c.demod_off,
                               d_all + (size_t)B * c.demod_off, c.cout, c.wsq, ds_all + (size_t)B * c.row0, B, c.cin, c.cout, s));
     g = dx;

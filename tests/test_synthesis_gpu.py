@@ -134,6 +134,21 @@ def test_gradient_parity_with_imposed_branches(size, cm, B):
     grad_parity(size, seed, lat, noise, cm=cm)
 
 
+@pytest.mark.parametrize("size,cm,B", [(64, 2, 2), (128, 1, 1), (256, 2, 1)])
+def test_tf32_tensor_core_path_parity(size, cm, B):
+    """tcgen05 kind::tf32 path (operands rounded to 10-bit mantissa, fp32 accumulation in TMEM) - the
+    numerics the reference itself runs on GPU (cuDNN TF32 convs).  Stated tolerance:
+    image max-abs <= 5e-3 * max(1, max|ref|); latent gradient <= 1e-2 relative L2 with the CUDA path's
+    leaky-ReLU branches imposed on the fp32 oracle; branches may differ where |activation| < 2e-2."""
+    from lfp_native import capi
+    seed = 120 + size
+    noise = fx.make_noise(size, seed + 1)
+    lat = fx.seeded((B, oracle.n_latent(size), 512), seed + 2)
+    rel, flips = grad_parity(size, seed, lat, noise, cm=cm, precision=capi.PREC_TF32, img_tol=5e-3, grad_tol=1e-2,
+                             flip_band=2e-2)
+    print(f"tf32 size {size}: gradient rel err {rel:.2e}, {flips} branch flips")
+
+
 def test_per_sample_noise_style_mixing_and_per_slot_gradient():
     size, seed, B = 32, 31, 3
     params = fx.make_params(size, seed)
