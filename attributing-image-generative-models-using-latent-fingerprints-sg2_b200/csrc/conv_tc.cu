@@ -16,9 +16,13 @@
 //   shared memory by the four transform warps between TMA arrival and MMA issue, together with the
 //   round-to-nearest tf32 conversion; demodulation, noise, bias and leaky-ReLU are the epilogue
 //   (src/model.py:261-263, 316, src/op/fused_act.py:110-127).
-// * Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-5 = A transform
-//   during the main loop, then TMEM -> register epilogue (each warp owns the 32 TMEM lanes
-//   32*(warp%4)..).  mbarrier rings: A (2 stages), B (4 stages).
+// * Persistent CTAs (one per SM) walk the (sample, tile, n-tile) list with a stride of gridDim.x.
+//   Roles: warp 0 = TMA producer (runs ahead across tiles), warp 1 = MMA issuer (one elected thread),
+//   warps 2-5 = A transform, warps 6-9 and 10-13 = two epilogue sets that alternate tiles (TMEM ->
+//   registers -> global; warp w owns TMEM lanes 32*(w%4)..).  The accumulator has 2-4 TMEM stages, so
+//   the epilogue of tile i overlaps the MMAs of tiles i+1...  mbarrier rings: A (3-8 stages); B either streamed (4 stages) or, when the
+//   whole [taps, K, BN] weight slice fits in shared memory (the HBM-bound C <= 64 layers), loaded once
+//   and kept resident for the CTA's lifetime.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -31,16 +35,23 @@ constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
 constexpr int A_ROWS = HALO_W * HALO_H;   // 180 rows of 128 bytes
 constexpr int A_BYTES = A_ROWS * 128;     // 23040
 constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
-constexpr int SA = 2, SB = 4;
-constexpr int NTHREADS = 192;
-constexpr int NBARS = 3 * SA + 2 * SB + 1;
+constexpr int MAX_SA = 8, MAX_SB = 4;
+constexpr int NTHREADS = 448;             // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-9 / 10-13 two epilogue sets
+constexpr int MAX_ACC = 4;                // TMEM accumulator stages
+constexpr int NBARS = 3 * MAX_SA + 2 * MAX_SB + 1 + 2 * MAX_ACC;
+constexpr int SMEM_OPTIN = 232448;        // 227 KB: static + dynamic shared memory available to one CTA
+// static shared memory of the kernel (barriers, and for the data-gradient epilogue the reduction scratch), rounded up
+constexpr int STATIC_SMEM_RESERVE(int epi) { return epi == EPI_DGRAD ? 44 * 1024 : 1024; }
 
 struct Args {
   int batch, gh, gw, tiles_x, tiles_y, K, N, BN;
+  int n_ntiles, total_work;   // work item = (sample, tile, n-tile)
+  int SA, SB, b_resident;     // A stages; B stages (streaming) or 0 with the whole weight slice resident
+  int nacc;                   // TMEM accumulator stages (2 or 4)
   int in_bcast;
   TcTaps taps;
   float* out;
-  int out_planes, out_plane, out_h, out_w;
+  int out_planes, out_plane, out_h, out_w, out_stride, out_oy, out_ox;
   const float* mod;
   ConvEpiArgs e;
 };
@@ -96,6 +107,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// descriptor = {lo, hi}: lo = (addr >> 4) | LBO field, hi = SBO | version | SWIZZLE_128B (constant per operand)
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -106,213 +132,328 @@ __device__ __forceinline__ float to_tf32(float v) {
 }
 __device__ __forceinline__ float lrelu(float v) { return (v > 0.f ? v : v * kLreluSlope) * kLreluGain; }
 
-template <int EPI, bool MOD>
-__global__ void __launch_bounds__(NTHREADS) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                          const __grid_constant__ CUtensorMap tmB, const Args a) {
+struct Work { int b, tile, nt, y0, x0, n0; };
+__device__ __forceinline__ Work decode(const Args& a, int w) {
+  Work r;
+  r.nt = w % a.n_ntiles;
+  const int bt = w / a.n_ntiles;
+  const int tiles_per = a.tiles_x * a.tiles_y;
+  r.b = bt / tiles_per;
+  r.tile = bt - r.b * tiles_per;
+  const int ty = r.tile / a.tiles_x;
+  r.y0 = ty * TILE_H;
+  r.x0 = (r.tile - ty * a.tiles_x) * TILE_W;
+  r.n0 = r.nt * a.BN;
+  return r;
+}
+
+// Persistent: CTA c processes work items c, c + gridDim.x, ...  (consecutive CTAs work on neighbouring
+// tiles at the same time, so halo rows and weight slices are L2 hits).
+template <int EPI, bool MOD, bool RES>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[NBARS];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float s_mod[MOD ? 512 : 4];
-  __shared__ float s_red[EPI == EPI_DGRAD ? 4 * 256 : 4];
+  __shared__ float s_scr[EPI == EPI_DGRAD ? 8 * 32 * 33 : 4];
+  __shared__ float s_red[EPI == EPI_DGRAD ? 2 * 4 * 256 : 4];
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_al = smem_raw + (smem0 - smem_u32(smem_raw));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_per = a.tiles_x * a.tiles_y;
-  const int b = blockIdx.x / tiles_per;
-  const int tile = blockIdx.x - b * tiles_per;
-  const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
-  const int y0 = ty * TILE_H, x0 = tx * TILE_W;
-  const int n0 = blockIdx.y * a.BN;
-  const uint32_t b_stage_bytes = (uint32_t)a.BN * 128u;
+  const int SA = a.SA, SB = a.SB;
+  const uint32_t b_slice_bytes = (uint32_t)a.BN * 128u;
   const uint32_t a_base = smem0, b_base = smem0 + SA * A_STAGE;
   const uint32_t bar0 = smem_u32(bars);
   auto bar_a_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_a_ready = [&](int s) { return bar0 + 8u * (SA + s); };
-  auto bar_a_empty = [&](int s) { return bar0 + 8u * (2 * SA + s); };
-  auto bar_b_full = [&](int s) { return bar0 + 8u * (3 * SA + s); };
-  auto bar_b_empty = [&](int s) { return bar0 + 8u * (3 * SA + SB + s); };
-  const uint32_t bar_acc = bar0 + 8u * (3 * SA + 2 * SB);
+  auto bar_a_ready = [&](int s) { return bar0 + 8u * (MAX_SA + s); };
+  auto bar_a_empty = [&](int s) { return bar0 + 8u * (2 * MAX_SA + s); };
+  auto bar_b_full = [&](int s) { return bar0 + 8u * (3 * MAX_SA + s); };
+  auto bar_b_empty = [&](int s) { return bar0 + 8u * (3 * MAX_SA + MAX_SB + s); };
+  const uint32_t bar_b_all = bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB);
+  auto bar_acc_full = [&](int s) { return bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB + 1 + s); };
+  auto bar_acc_empty = [&](int s) { return bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB + 1 + MAX_ACC + s); };
 
   if (tid == 0) {
-    for (int s = 0; s < SA; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_ready(s), 128); mbar_init(bar_a_empty(s), 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
-    mbar_init(bar_acc, 1);
+    for (int s = 0; s < MAX_SA; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_ready(s), 128); mbar_init(bar_a_empty(s), 1); }
+    for (int s = 0; s < MAX_SB; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
+    mbar_init(bar_b_all, 1);
+    for (int s = 0; s < MAX_ACC; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  const uint32_t tmem_cols = (uint32_t)(a.nacc * a.BN);
+  const int acc_shift = a.nacc == 4 ? 2 : 1;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)a.BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (MOD)
-    for (int i = tid; i < a.K; i += NTHREADS) s_mod[i] = __ldg(a.mod + (int64_t)b * a.K + i);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_s;
   const int kchunks = a.K >> 5;
   const int ngroups = a.taps.ngroups;
+  const int ntaps = a.taps.group_tap0[ngroups];
+  const int tiles_per = a.tiles_x * a.tiles_y;
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
+      if (RES) {
+        // whole weight slice of this launch: slot (tap t, chunk kc) at b_base + (t*kchunks + kc) * slice
+        mbar_expect_tx(bar_b_all, (uint32_t)(ntaps * kchunks) * b_slice_bytes);
+        for (int t = 0; t < ntaps; ++t)
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_2d(b_base + (uint32_t)(t * kchunks + kc) * b_slice_bytes, &tmB, bar_b_all, kc * 32, (int)a.taps.widx[t] * a.N);
+      }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      const int bin = a.in_bcast ? 0 : b;
-      for (int kc = 0; kc < kchunks; ++kc)
-        for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(bar_a_empty(sa), pa ^ 1u);
-          mbar_expect_tx(bar_a_full(sa), A_BYTES);
-          tma_load_5d(a_base + sa * A_STAGE, &tmA, bar_a_full(sa), kc * 32, x0 - 1, y0 - 1, a.taps.group_plane[g], bin);
-          for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
-            mbar_wait(bar_b_empty(sb), pb ^ 1u);
-            mbar_expect_tx(bar_b_full(sb), b_stage_bytes);
-            tma_load_2d(b_base + sb * b_stage_bytes, &tmB, bar_b_full(sb), kc * 32, (int)a.taps.widx[t] * a.N + n0);
-            if (++sb == SB) { sb = 0; pb ^= 1u; }
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+        const Work wk = decode(a, w);
+        const int bin = a.in_bcast ? 0 : wk.b;
+        for (int kc = 0; kc < kchunks; ++kc)
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(bar_a_empty(sa), pa ^ 1u);
+            mbar_expect_tx(bar_a_full(sa), A_BYTES);
+            tma_load_5d(a_base + sa * A_STAGE, &tmA, bar_a_full(sa), kc * 32, wk.x0 - 1, wk.y0 - 1, a.taps.group_plane[g], bin);
+            if (!RES)
+              for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
+                mbar_wait(bar_b_empty(sb), pb ^ 1u);
+                mbar_expect_tx(bar_b_full(sb), b_slice_bytes);
+                tma_load_2d(b_base + sb * b_slice_bytes, &tmB, bar_b_full(sb), kc * 32, (int)a.taps.widx[t] * a.N + wk.n0);
+                if (++sb == SB) { sb = 0; pb ^= 1u; }
+              }
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
-          if (++sa == SA) { sa = 0; pa ^= 1u; }
-        }
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+    // ---------------- MMA issuer ----------------
+    // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / commit.
+    // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_hi = (uint32_t)((HALO_W * 128) >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t b_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lo0 = (a_base >> 4) | 0x10000u, b_lo0 = (b_base >> 4) | 0x10000u;
+    const uint32_t b_slice16 = b_slice_bytes >> 4;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    // per-tap descriptor offsets (16-byte units), kept in registers: the issue loop below is fully unrolled
+    uint32_t tap_a[9], tap_b[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int tt = t < ntaps ? t : 0;
+      tap_a[t] = (uint32_t)((((int)a.taps.dy[tt] + 1) * HALO_W + ((int)a.taps.dx[tt] + 1)) * 8);
+      tap_b[t] = b_lo0 + (uint32_t)(tt * kchunks) * b_slice16;
+    }
+    if (RES) mbar_wait(bar_b_all, 0);
+    int it = 0;
+    for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++it) {
+      const int as = it & (a.nacc - 1);
+      mbar_wait(bar_acc_empty(as), (((uint32_t)it >> acc_shift) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem + (uint32_t)(as * a.BN);
       uint32_t accumulate = 0;
       for (int kc = 0; kc < kchunks; ++kc)
         for (int g = 0; g < ngroups; ++g) {
           mbar_wait(MOD ? bar_a_ready(sa) : bar_a_full(sa), pa);
-          for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
-            mbar_wait(bar_b_full(sb), pb);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t shift = (uint32_t)(((int)a.taps.dy[t] + 1) * HALO_W + ((int)a.taps.dx[t] + 1));
-            const uint32_t a_addr = a_base + sa * A_STAGE + shift * 128u;
-            const uint32_t b_addr = b_base + sb * b_stage_bytes;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_stage_lo = a_lo0 + (uint32_t)sa * (A_STAGE >> 4);
+          const int t0 = a.taps.group_tap0[g], t1 = a.taps.group_tap0[g + 1];
+          if (RES) {
+            // weights resident: every MMA of this activation stage is issued in one elected region
+            const uint32_t kc_off = (uint32_t)kc * b_slice16;
+            if (elect_one()) {
 #pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-              umma_tf32(tmem, make_desc(a_addr + k8 * 32, HALO_W * 128), make_desc(b_addr + k8 * 32, 1024), idesc, accumulate);
-              accumulate = 1;
+              for (int t = 0; t < 9; ++t)
+                if (t >= t0 && t < t1) {
+                  const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = tap_b[t] + kc_off;
+                  umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+                  umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                  umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                  umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                  accumulate = 1;
+                }
+              umma_commit(bar_a_empty(sa));
             }
-            umma_commit(bar_b_empty(sb));
-            if (++sb == SB) { sb = 0; pb ^= 1u; }
+            __syncwarp();
+            accumulate = 1;
+          } else {
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+              if (t >= t0 && t < t1) {
+                mbar_wait(bar_b_full(sb), pb);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)sb * b_slice16;
+                if (elect_one()) {
+                  umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+                  umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                  umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                  umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                  umma_commit(bar_b_empty(sb));
+                }
+                __syncwarp();
+                accumulate = 1;
+                if (++sb == SB) { sb = 0; pb ^= 1u; }
+              }
+            if (elect_one()) umma_commit(bar_a_empty(sa));
+            __syncwarp();
           }
-          umma_commit(bar_a_empty(sa));
           if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
-      umma_commit(bar_acc);
+      if (elect_one()) umma_commit(bar_acc_full(as));
+      __syncwarp();
     }
-  } else {
-    const int et = tid - 64;  // 0..127
+  } else if (warp < 6) {
     if (MOD) {
       // ---------------- A transform: x * s[b, k], rounded to tf32 ----------------
+      const int et = tid - 64;  // 0..127
       int sa = 0;
       uint32_t pa = 0;
-      for (int kc = 0; kc < kchunks; ++kc)
-        for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(bar_a_full(sa), pa);
-          uint8_t* stage = smem_raw + (a_base - smem_u32(smem_raw)) + sa * A_STAGE;
-          const float* sm = s_mod + kc * 32;
-          for (int idx = et; idx < A_ROWS * 8; idx += 128) {
-            const int row = idx >> 3, pos = idx & 7;
-            const int ch = (pos ^ (row & 7)) << 2;
-            float4* p = reinterpret_cast<float4*>(stage + row * 128 + pos * 16);
-            float4 v = *p;
-            v.x = to_tf32(v.x * sm[ch + 0]);
-            v.y = to_tf32(v.y * sm[ch + 1]);
-            v.z = to_tf32(v.z * sm[ch + 2]);
-            v.w = to_tf32(v.w * sm[ch + 3]);
-            *p = v;
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+        const Work wk = decode(a, w);
+        const float* sm = a.mod + (int64_t)wk.b * a.K;
+        for (int kc = 0; kc < kchunks; ++kc)
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(bar_a_full(sa), pa);
+            // thread -> fixed 16-byte column `pos` of rows r0, r0+16, ...: (row & 7) is then constant, and so is
+            // the channel quad this thread scales (SWIZZLE_128B stores quad c of row r at position c ^ (r & 7))
+            const int pos = et & 7, r0 = et >> 3;
+            const int ch = (pos ^ (r0 & 7)) << 2;
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sm + kc * 32 + ch));
+            float4* p = reinterpret_cast<float4*>(smem_al + sa * A_STAGE + r0 * 128 + pos * 16);
+            float4 v[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+              if (i < 11 || r0 + 176 < A_ROWS) v[i] = p[i * 128];   // row r0 + 16 i, 128 float4 apart
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+              if (i < 11 || r0 + 176 < A_ROWS) {
+                v[i].x = to_tf32(v[i].x * s4.x);
+                v[i].y = to_tf32(v[i].y * s4.y);
+                v[i].z = to_tf32(v[i].z * s4.z);
+                v[i].w = to_tf32(v[i].w * s4.w);
+                p[i * 128] = v[i];
+              }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(bar_a_ready(sa));
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(bar_a_ready(sa));
-          if (++sa == SA) { sa = 0; pa ^= 1u; }
-        }
-    }
-    // ---------------- epilogue ----------------
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int gy = y0 + (m >> 3), gx = x0 + (m & 7);
-    const bool valid = gy < a.gh && gx < a.gw;
-    const int pix = gy * a.gw + gx;
-    float nz = 0.f;
-    if (EPI == EPI_ACT && valid) nz = __ldg(a.e.noise_w) * __ldg(a.e.noise + (int64_t)b * a.e.noise_bstride + pix);
-    float* outp = nullptr;
-    if (a.out != nullptr && valid)
-      outp = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
-    const float* xs = nullptr;
-    if (EPI == EPI_DGRAD && valid) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
-    float* scr = reinterpret_cast<float*>(smem_raw + (a_base - smem_u32(smem_raw))) + q * (32 * 33);
-
-    mbar_wait(bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int nchunk = a.BN >> 5;
-    for (int c = 0; c < nchunk; ++c) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
-          "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-            "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-            "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-            "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nc = n0 + c * 32;
-      if (EPI == EPI_ACT) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.e.demod + (int64_t)b * a.N + nc + j * 4));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.e.bias + nc + j * 4));
-          float4 v;
-          v.x = lrelu(fmaf(__uint_as_float(r[j * 4 + 0]), d4.x, nz) + b4.x);
-          v.y = lrelu(fmaf(__uint_as_float(r[j * 4 + 1]), d4.y, nz) + b4.y);
-          v.z = lrelu(fmaf(__uint_as_float(r[j * 4 + 2]), d4.z, nz) + b4.z);
-          v.w = lrelu(fmaf(__uint_as_float(r[j * 4 + 3]), d4.w, nz) + b4.w);
-          if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = v;
-        }
-      } else if (EPI == EPI_STORE) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (outp)
-            *reinterpret_cast<float4*>(outp + c * 32 + j * 4) =
-                make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
-                            __uint_as_float(r[j * 4 + 3]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (xs) x4 = __ldg(reinterpret_cast<const float4*>(xs + c * 32 + j * 4));
-          const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.e.mod_out + (int64_t)b * a.N + nc + j * 4));
-          const float v0 = __uint_as_float(r[j * 4 + 0]), v1 = __uint_as_float(r[j * 4 + 1]);
-          const float v2 = __uint_as_float(r[j * 4 + 2]), v3 = __uint_as_float(r[j * 4 + 3]);
-          scr[lane * 33 + j * 4 + 0] = x4.x * v0;
-          scr[lane * 33 + j * 4 + 1] = x4.y * v1;
-          scr[lane * 33 + j * 4 + 2] = x4.z * v2;
-          scr[lane * 33 + j * 4 + 3] = x4.w * v3;
-          if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = make_float4(v0 * m4.x, v1 * m4.y, v2 * m4.z, v3 * m4.w);
-        }
-        __syncwarp();
-        float sum = 0.f;
-#pragma unroll 8
-        for (int l = 0; l < 32; ++l) sum += scr[l * 33 + lane];  // fixed order: deterministic
-        __syncwarp();
-        s_red[q * 256 + c * 32 + lane] = sum;
       }
     }
-    if (EPI == EPI_DGRAD) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int n = et; n < a.BN; n += 128)
-        a.e.partial[((int64_t)b * tiles_per + tile) * a.N + n0 + n] =
-            ((s_red[n] + s_red[256 + n]) + s_red[512 + n]) + s_red[768 + n];
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // two sets of four warps alternate tiles, so one tile's operand-load / store latency overlaps the next tile
+    const int eset = warp >= 10 ? 1 : 0;
+    const int et = tid - 192 - eset * 128;  // 0..127 within the set
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int m = q * 32 + lane;
+    float* scr = s_scr + (eset * 4 + q) * (32 * 33);
+    float* red = s_red + eset * (4 * 256);
+    int it = eset;
+    for (int w = blockIdx.x + eset * gridDim.x; w < a.total_work; w += 2 * gridDim.x, it += 2) {
+      const Work wk = decode(a, w);
+      const int as = it & (a.nacc - 1);
+      const int b = wk.b, n0 = wk.n0;
+      const int gy = wk.y0 + (m >> 3), gx = wk.x0 + (m & 7);
+      const bool valid = gy < a.gh && gx < a.gw;
+      const int pix = gy * a.gw + gx;
+      float nz = 0.f;
+      if (EPI == EPI_ACT && valid) nz = __ldg(a.e.noise_w) * __ldg(a.e.noise + (int64_t)b * a.e.noise_bstride + pix);
+      float* outp = nullptr;
+      if (a.out != nullptr && valid)
+        outp = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
+                        (gx * a.out_stride + a.out_ox)) * a.N + n0;
+      const float* xs = nullptr;
+      if (EPI == EPI_DGRAD && valid) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
+
+      float4 xpre[8];   // first chunk of the saved forward input, requested before the accumulator wait
+      if (EPI == EPI_DGRAD) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (xs) xpre[j] = __ldg(reinterpret_cast<const float4*>(xs + j * 4));
+        }
+      }
+      mbar_wait(bar_acc_full(as), ((uint32_t)it >> acc_shift) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int nchunk = a.BN >> 5;
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * a.BN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+            "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == nchunk - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(bar_acc_empty(as));
+        }
+        const int nc = n0 + c * 32;
+        if (EPI == EPI_ACT) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.e.demod + (int64_t)b * a.N + nc + j * 4));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.e.bias + nc + j * 4));
+            float4 v;
+            v.x = lrelu(fmaf(__uint_as_float(r[j * 4 + 0]), d4.x, nz) + b4.x);
+            v.y = lrelu(fmaf(__uint_as_float(r[j * 4 + 1]), d4.y, nz) + b4.y);
+            v.z = lrelu(fmaf(__uint_as_float(r[j * 4 + 2]), d4.z, nz) + b4.z);
+            v.w = lrelu(fmaf(__uint_as_float(r[j * 4 + 3]), d4.w, nz) + b4.w);
+            if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = v;
+          }
+        } else if (EPI == EPI_STORE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (outp)
+              *reinterpret_cast<float4*>(outp + c * 32 + j * 4) =
+                  make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
+                              __uint_as_float(r[j * 4 + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x4 = xpre[j];
+            if (c > 0) {
+              x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (xs) x4 = __ldg(reinterpret_cast<const float4*>(xs + c * 32 + j * 4));
+            }
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.e.mod_out + (int64_t)b * a.N + nc + j * 4));
+            const float v0 = __uint_as_float(r[j * 4 + 0]), v1 = __uint_as_float(r[j * 4 + 1]);
+            const float v2 = __uint_as_float(r[j * 4 + 2]), v3 = __uint_as_float(r[j * 4 + 3]);
+            scr[lane * 33 + j * 4 + 0] = x4.x * v0;
+            scr[lane * 33 + j * 4 + 1] = x4.y * v1;
+            scr[lane * 33 + j * 4 + 2] = x4.z * v2;
+            scr[lane * 33 + j * 4 + 3] = x4.w * v3;
+            if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = make_float4(v0 * m4.x, v1 * m4.y, v2 * m4.z, v3 * m4.w);
+          }
+          __syncwarp();
+          float sum = 0.f;
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) sum += scr[l * 33 + lane];  // fixed order: deterministic
+          __syncwarp();
+          red[q * 256 + c * 32 + lane] = sum;
+        }
+      }
+      if (EPI == EPI_DGRAD) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+        for (int n = et; n < a.BN; n += 128)
+          a.e.partial[((int64_t)b * tiles_per + wk.tile) * a.N + n0 + n] =
+              ((red[n] + red[256 + n]) + red[512 + n]) + red[768 + n];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)a.BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
   }
 }
 
@@ -349,7 +490,7 @@ int tc_tiles_per_sample(int gh, int gw) { return (int)(ceil_div(gw, tc::TILE_W) 
 bool tc_supported(int K, int N, int gh, int gw) {
   const int bn = tc_block_n(N);
   const bool n_ok = (bn == 32 || bn == 64 || bn == 128 || bn == 256) && N % bn == 0;
-  return K % 32 == 0 && K <= 512 && n_ok && gh >= 8 && gw >= 8;
+  return K % 32 == 0 && K <= 512 && n_ok && gh >= 4 && gw >= 4;
 }
 
 int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N) {
@@ -359,16 +500,38 @@ int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N
   return tc::encode(reinterpret_cast<CUtensorMap*>(map_out), table, 2, dims, strides, box);
 }
 
-template <int EPI, bool MOD>
-static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Args& a, dim3 grid, size_t smem, cudaStream_t s) {
+template <int EPI, bool MOD, bool RES>
+static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE(EPI))));
     attr_done = true;
   }
-  tc::conv_tc_kernel<EPI, MOD><<<grid, tc::NTHREADS, smem, s>>>(tmA, tmB, a);
+  const int max_ctas = num_sms();
+  const dim3 grid((unsigned)(a.total_work < max_ctas ? a.total_work : max_ctas));
+  tc::conv_tc_kernel<EPI, MOD, RES><<<grid, tc::NTHREADS, dyn_smem, s>>>(tmA, tmB, a);
   LFP_LAUNCH_CHECK();
   return 0;
+}
+
+template <int EPI, bool MOD>
+static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, tc::Args& a, int ntaps, cudaStream_t s) {
+  // shared-memory plan: the weight slice stays resident when it fits beside >= 3 activation stages
+  const size_t b_all = (size_t)ntaps * (a.K / 32) * a.BN * 128;
+  const size_t budget = (size_t)tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE(EPI) - 1024;
+  if (a.n_ntiles == 1 && b_all + 3 * (size_t)tc::A_STAGE <= budget) {
+    a.b_resident = 1; a.SB = 0;
+    a.SA = (int)((budget - b_all) / tc::A_STAGE);
+  } else {
+    a.b_resident = 0; a.SB = tc::MAX_SB;
+    a.SA = (int)((budget - (size_t)a.SB * a.BN * 128) / tc::A_STAGE);
+  }
+  if (a.SA > tc::MAX_SA) a.SA = tc::MAX_SA;
+  a.nacc = a.BN <= 128 ? 4 : 2;
+  LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
+  const size_t smem = (size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128) + 1024;
+  return a.b_resident ? tc_launch2<EPI, MOD, true>(tmA, tmB, a, smem, s) : tc_launch2<EPI, MOD, false>(tmA, tmB, a, smem, s);
 }
 
 int launch_conv_tc(const TcConv& c, cudaStream_t s) {
@@ -389,15 +552,19 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   a.in_bcast = c.in_bcast ? 1 : 0;
   a.taps = c.taps;
   a.out = c.out; a.out_planes = c.out_planes; a.out_plane = c.out_plane; a.out_h = c.out_h; a.out_w = c.out_w;
+  a.out_stride = c.out_stride > 0 ? c.out_stride : 1; a.out_oy = c.out_oy; a.out_ox = c.out_ox;
   a.mod = c.mod; a.e = c.e;
-  const dim3 grid((unsigned)(a.tiles_x * a.tiles_y * c.batch), (unsigned)(c.N / a.BN));
-  const size_t smem = (size_t)tc::SA * tc::A_STAGE + (size_t)tc::SB * a.BN * 128 + 1024;
+  a.n_ntiles = c.N / a.BN;
+  const int64_t total = (int64_t)a.tiles_x * a.tiles_y * c.batch * a.n_ntiles;
+  LFP_CHECK_ARG(total < (1ll << 31), "conv_tc: too many tiles");
+  a.total_work = (int)total;
+  const int ntaps = c.taps.group_tap0[c.taps.ngroups];
   const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(c.wmap);
   const bool mod = c.mod != nullptr;
-  if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, a, grid, smem, s) : tc_launch<EPI_ACT, false>(tmA, tmB, a, grid, smem, s);
-  if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, a, grid, smem, s) : tc_launch<EPI_STORE, false>(tmA, tmB, a, grid, smem, s);
+  if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, a, ntaps, s) : tc_launch<EPI_ACT, false>(tmA, tmB, a, ntaps, s);
+  if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, a, ntaps, s) : tc_launch<EPI_STORE, false>(tmA, tmB, a, ntaps, s);
   LFP_CHECK_ARG(!mod, "conv_tc: the data-gradient kernel takes an unmodulated input");
-  return tc_launch<EPI_DGRAD, false>(tmA, tmB, a, grid, smem, s);
+  return tc_launch<EPI_DGRAD, false>(tmA, tmB, a, ntaps, s);
 }
 
 }  // namespace lfp

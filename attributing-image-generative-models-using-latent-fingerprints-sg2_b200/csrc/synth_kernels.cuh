@@ -67,6 +67,7 @@ struct TcConv {
   const float* mod;   // [B, K] style (forward) or null
   const void* wmap;   // CUtensorMap of the K-major weight table [ntaps * N, K] (tc_make_weight_map)
   float* out; int out_planes, out_plane, out_h, out_w;   // out tensor [B, out_planes, out_h, out_w, N]
+  int out_stride = 1, out_oy = 0, out_ox = 0;            // grid pixel (gy,gx) is written at (gy*stride+oy, gx*stride+ox)
   int batch, gh, gw, K, N;
   TcTaps taps;
   int epi; ConvEpiArgs e;   // EPI_DGRAD: partial rows are [b * tc_tiles_per_sample + tile]

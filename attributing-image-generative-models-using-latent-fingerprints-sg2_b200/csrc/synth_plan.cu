@@ -74,7 +74,7 @@ struct lfp_synth {
   float* fir = nullptr;  // 4 x 16 floats: blur fwd coef, blur bwd coef, upsample kernel, flipped upsample kernel
   float blur1d[4] = {1, 3, 3, 1};
   bool finalized = false;
-  int tc_min_res = 8;   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
+  int tc_min_res = 4;   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
   int fwd_batch = -1;
   std::vector<const float*> fwd_noise;
   std::vector<int> fwd_noise_batch;
@@ -85,6 +85,9 @@ struct lfp_synth {
   int prof_mask = 0;
   std::vector<cudaEvent_t> prof_ev;       // pairs
   std::vector<int> prof_kind;
+  std::vector<double> prof_lflops, prof_lbytes;   // per recorded launch
+  std::vector<float> prof_lms;
+  std::vector<int> prof_lkind;
   size_t prof_used = 0;
   double prof_flops[LFP_KIND_COUNT] = {0}, prof_bytes[LFP_KIND_COUNT] = {0};
   int64_t prof_launches[LFP_KIND_COUNT] = {0};
@@ -100,8 +103,9 @@ struct lfp_synth {
       if (prof_ev.size() >= 400000) return false;
       for (int i = 0; i < 2; ++i) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return false; prof_ev.push_back(e); }
     }
-    if (prof_kind.size() < prof_ev.size() / 2) prof_kind.resize(prof_ev.size() / 2);
+    if (prof_kind.size() < prof_ev.size() / 2) { prof_kind.resize(prof_ev.size() / 2); prof_lflops.resize(prof_ev.size() / 2); prof_lbytes.resize(prof_ev.size() / 2); }
     prof_kind[prof_used / 2] = kind;
+    prof_lflops[prof_used / 2] = flops; prof_lbytes[prof_used / 2] = bytes;
     cudaEventRecord(prof_ev[prof_used], s);
     return true;
   }
@@ -196,7 +200,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   h->n_latent = ls * 2 - 2;
   h->num_noise = (ls - 2) * 2 + 1;
   if (blur_kernel_1d) memcpy(h->blur1d, blur_kernel_1d, 4 * sizeof(float));
-  if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 8) h->tc_min_res = v; }
+  if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 4) h->tc_min_res = v; }
   for (int r = 4; r <= size; r *= 2) {
     const int c = h->channels(r);
     if (c % 16 != 0 || 1024 % c != 0) {
@@ -338,8 +342,8 @@ extern "C" int lfp_synth_finalize(lfp_synth* h, void* stream) {
     LFP_TRY(launch_prep_conv3x3(c.W, wscale, c.wf, c.wg, c.wsq, c.cin, c.cout, s));
     LFP_TRY(launch_round_tf32(c.wf, c.wf_t, (int64_t)9 * c.cin * c.cout, s));
     LFP_TRY(launch_round_tf32(c.wg, c.wg_t, (int64_t)9 * c.cin * c.cout, s));
-    c.tc_fwd = tc_supported(c.cin, c.cout, 8, 8);
-    c.tc_bwd = tc_supported(c.cout, c.cin, 8, 8);
+    c.tc_fwd = tc_supported(c.cin, c.cout, 4, 4);
+    c.tc_bwd = tc_supported(c.cout, c.cin, 4, 4);
     if (c.tc_fwd) LFP_TRY(tc_make_weight_map(c.map_fwd.bytes, c.wg_t, 9 * c.cout, c.cin, c.cout));
     if (c.tc_bwd) LFP_TRY(tc_make_weight_map(c.map_bwd.bytes, c.wf_t, 9 * c.cin, c.cout, c.cin));
     LFP_TRY(launch_scale_copy(c.modw, h->A_all + (size_t)c.row0 * h->style_dim, mscale, (int64_t)c.cin * h->style_dim, s));
@@ -665,12 +669,26 @@ extern "C" int lfp_synth_profile_end(lfp_synth* h, double* ms, int64_t* launches
   LFP_CHECK_ARG(h != nullptr && ms && launches && flops && bytes, "profile_end: null argument");
   h->prof_on = false;
   for (int k = 0; k < LFP_KIND_COUNT; ++k) { ms[k] = 0; launches[k] = h->prof_launches[k]; flops[k] = h->prof_flops[k]; bytes[k] = h->prof_bytes[k]; }
+  h->prof_lms.clear(); h->prof_lkind.clear();
   for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
     LFP_CUDA(cudaEventSynchronize(h->prof_ev[i + 1]));
     float t = 0.f;
     LFP_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
     ms[h->prof_kind[i / 2]] += t;
+    h->prof_lms.push_back(t); h->prof_lkind.push_back(h->prof_kind[i / 2]);
   }
   h->prof_used = 0;
   return 0;
+}
+
+extern "C" int lfp_synth_profile_launches(lfp_synth* h, int max_launches, int* kinds, float* ms, double* flops, double* bytes) {
+  LFP_CHECK_ARG(h != nullptr, "profile_launches: null plan");
+  const int n = (int)h->prof_lms.size();
+  for (int i = 0; i < n && i < max_launches; ++i) {
+    if (kinds) kinds[i] = h->prof_lkind[i];
+    if (ms) ms[i] = h->prof_lms[i];
+    if (flops) flops[i] = h->prof_lflops[i];
+    if (bytes) bytes[i] = h->prof_lbytes[i];
+  }
+  return n;
 }

@@ -49,6 +49,8 @@ _PROTOS = {
     "lfp_synth_profile_begin": (_i, [_vp, _i]),
     "lfp_synth_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double)]),
+    "lfp_synth_profile_launches": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                        C.POINTER(C.c_double)]),
     "lfp_embed_forward": (_i, [_vp] * 6 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_embed_backward": (_i, [_vp] * 5 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_mse_loss_grad": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),

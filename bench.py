@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--guesses", type=int, default=20, help="trajectories in flight per rank (n of src/params.py:17)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="tf32 = tcgen05 tensor-core convs (the numerics the reference runs on GPU); fp32 = CUDA-core convs")
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -165,6 +165,9 @@ int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const float* latent
 #define LFP_KIND_COUNT 5
 int lfp_synth_profile_begin(lfp_synth* h, int kind_mask);
 int lfp_synth_profile_end(lfp_synth* h, double* ms, int64_t* launches, double* flops, double* bytes);
+/* After profile_end: the recorded launches one by one, in launch order (class, device ms, algorithmic
+ * flops and bytes); returns how many were recorded, fills at most max_launches entries. */
+int lfp_synth_profile_launches(lfp_synth* h, int max_launches, int* kinds, float* ms, double* flops, double* bytes);
 
 /* ---------------------------------------------------------------------------------
  * 4. Fingerprint embed + loss glue used by the attribution loop (additive).
