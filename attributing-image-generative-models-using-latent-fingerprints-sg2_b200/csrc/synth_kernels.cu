@@ -221,35 +221,36 @@ int launch_conv_simt(const float* in, const float* mod, const float* wtab, float
 // =============================================================================================
 // 4x4 FIR on NHWC with a register sliding window (blur after the transposed conv, and its adjoint)
 // =============================================================================================
-template <bool ACT>
+// Each thread owns a channel quad of XO adjacent output columns and slides a 4 x (XO+3) window of
+// input pixels down RY output rows: (XO+3) 128-bit loads per XO outputs per row.
+template <bool ACT, int XO>
 __global__ void __launch_bounds__(256) fir4x4_nhwc_kernel(const float* __restrict__ in,
                                                           float* __restrict__ out, const FirArgs a,
                                                           int C4, int PX, int RY) {
+  constexpr int WC = XO + 3;
   const int c4 = threadIdx.x % C4;
   const int px = threadIdx.x / C4;
-  const int ox = blockIdx.x * PX + px;
+  const int ox0 = (blockIdx.x * PX + px) * XO;
   const int oy0 = blockIdx.y * RY;
   const int b = blockIdx.z;
-  if (px >= PX || ox >= a.out_w) return;
+  if (px >= PX || ox0 >= a.out_w) return;
   float coef[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) coef[i] = __ldg(a.coef + i);
   const int C = a.C;
-  const int64_t in_per = a.in_planar ? (int64_t)4 * ((a.in_h + 1) >> 1) * ((a.in_w + 1) >> 1) : (int64_t)a.in_h * a.in_w;
-  const int64_t out_per = a.out_planar ? (int64_t)4 * ((a.out_h + 1) >> 1) * ((a.out_w + 1) >> 1) : (int64_t)a.out_h * a.out_w;
+  const int iph = (a.in_h + 1) >> 1, ipw = (a.in_w + 1) >> 1, oph = (a.out_h + 1) >> 1, opw = (a.out_w + 1) >> 1;
+  const int64_t in_per = a.in_planar ? (int64_t)4 * iph * ipw : (int64_t)a.in_h * a.in_w;
+  const int64_t out_per = a.out_planar ? (int64_t)4 * oph * opw : (int64_t)a.out_h * a.out_w;
   const float* src = in + (int64_t)b * in_per * C + c4 * 4;
-  float4 win[4][4];
-  auto load_row = [&](int iy, float4(&row)[4]) {
+  float4 win[4][WC];
+  auto load_row = [&](int iy, float4(&row)[WC]) {
 #pragma unroll
-    for (int tx = 0; tx < 4; ++tx) {
-      const int ix = ox + tx - a.pad;
+    for (int tx = 0; tx < WC; ++tx) {
+      const int ix = ox0 + tx - a.pad;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (iy >= 0 && iy < a.in_h && ix >= 0 && ix < a.in_w) {
         int64_t e = (int64_t)iy * a.in_w + ix;
-        if (a.in_planar) {
-          const int ph = (a.in_h + 1) >> 1, pw = (a.in_w + 1) >> 1;
-          e = ((int64_t)((iy & 1) * 2 + (ix & 1)) * ph + (iy >> 1)) * pw + (ix >> 1);
-        }
+        if (a.in_planar) e = ((int64_t)((iy & 1) * 2 + (ix & 1)) * iph + (iy >> 1)) * ipw + (ix >> 1);
         v = __ldg(reinterpret_cast<const float4*>(src + e * C));
       }
       row[tx] = v;
@@ -271,24 +272,26 @@ __global__ void __launch_bounds__(256) fir4x4_nhwc_kernel(const float* __restric
       const int oy = oy0 + o + u;
       if (oy >= a.out_h) return;
       load_row(oy + 3 - a.pad, win[(u + 3) & 3]);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int xo = 0; xo < XO; ++xo) {
+        const int ox = ox0 + xo;
+        if (ox >= a.out_w) break;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int tx = 0; tx < 4; ++tx) acc = f4_fma(coef[r * 4 + tx], win[(u + r) & 3][tx], acc);
-      if (ACT) {
-        const float nz = nw * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox);
-        acc.x = lrelu_fwd(fmaf(acc.x, d4.x, nz) + bias4.x);
-        acc.y = lrelu_fwd(fmaf(acc.y, d4.y, nz) + bias4.y);
-        acc.z = lrelu_fwd(fmaf(acc.z, d4.z, nz) + bias4.z);
-        acc.w = lrelu_fwd(fmaf(acc.w, d4.w, nz) + bias4.w);
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int tx = 0; tx < 4; ++tx) acc = f4_fma(coef[r * 4 + tx], win[(u + r) & 3][xo + tx], acc);
+        if (ACT) {
+          const float nz = nw * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox);
+          acc.x = lrelu_fwd(fmaf(acc.x, d4.x, nz) + bias4.x);
+          acc.y = lrelu_fwd(fmaf(acc.y, d4.y, nz) + bias4.y);
+          acc.z = lrelu_fwd(fmaf(acc.z, d4.z, nz) + bias4.z);
+          acc.w = lrelu_fwd(fmaf(acc.w, d4.w, nz) + bias4.w);
+        }
+        int64_t oe = (int64_t)oy * a.out_w + ox;
+        if (a.out_planar) oe = ((int64_t)((oy & 1) * 2 + (ox & 1)) * oph + (oy >> 1)) * opw + (ox >> 1);
+        *reinterpret_cast<float4*>(out + ((int64_t)b * out_per + oe) * C + c4 * 4) = acc;
       }
-      int64_t oe = (int64_t)oy * a.out_w + ox;
-      if (a.out_planar) {
-        const int ph = (a.out_h + 1) >> 1, pw = (a.out_w + 1) >> 1;
-        oe = ((int64_t)((oy & 1) * 2 + (ox & 1)) * ph + (oy >> 1)) * pw + (ox >> 1);
-      }
-      *reinterpret_cast<float4*>(out + ((int64_t)b * out_per + oe) * C + c4 * 4) = acc;
     }
   }
 }
@@ -297,10 +300,17 @@ int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream
   LFP_CHECK_ARG(a.C % 4 == 0 && a.C <= 1024, "fir: C=%d must be a multiple of 4 and <= 1024", a.C);
   const int C4 = a.C / 4;
   const int PX = 256 / C4 > 0 ? 256 / C4 : 1;
-  const int RY = 8;
-  dim3 grid((unsigned)ceil_div(a.out_w, PX), (unsigned)ceil_div(a.out_h, RY), (unsigned)a.batch);
-  if (a.act) fir4x4_nhwc_kernel<true><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
-  else fir4x4_nhwc_kernel<false><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+  const bool wide = a.out_w >= 32;   // two output columns per thread once rows are long enough to fill the grid
+  const int XO = wide ? 2 : 1;
+  const int RY = a.out_h >= 256 ? 16 : 8;
+  dim3 grid((unsigned)ceil_div(a.out_w, PX * XO), (unsigned)ceil_div(a.out_h, RY), (unsigned)a.batch);
+  if (a.act) {
+    if (wide) fir4x4_nhwc_kernel<true, 2><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+    else fir4x4_nhwc_kernel<true, 1><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+  } else {
+    if (wide) fir4x4_nhwc_kernel<false, 2><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+    else fir4x4_nhwc_kernel<false, 1><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+  }
   LFP_LAUNCH_CHECK();
   return 0;
 }
