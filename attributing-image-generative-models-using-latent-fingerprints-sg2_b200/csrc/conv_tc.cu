@@ -38,16 +38,25 @@ constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
 constexpr int MAX_SA = 8, MAX_SB = 4;
 constexpr int NTHREADS = 448;             // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-9 / 10-13 two epilogue sets
 constexpr int MAX_ACC = 4;                // TMEM accumulator stages
-constexpr int NBARS = 3 * MAX_SA + 2 * MAX_SB + 1 + 2 * MAX_ACC;
+constexpr int MAX_XS = 4;                 // stages of the saved-input (xsave) tile ring of the data-gradient epilogues
+constexpr int XS_CHUNK = 128 * 128;       // one 128-pixel x 32-channel tile
+constexpr int NBARS = 3 * MAX_SA + 2 * MAX_SB + 1 + 2 * MAX_ACC + 2 * MAX_XS;
 constexpr int SMEM_OPTIN = 232448;        // 227 KB: static + dynamic shared memory available to one CTA
 // static shared memory of the kernel (barriers, and for the data-gradient epilogue the reduction scratch), rounded up
-constexpr int STATIC_SMEM_RESERVE(int epi) { return epi == EPI_DGRAD ? 44 * 1024 : 1024; }
+constexpr int STATIC_SMEM_RESERVE = 1024;
+constexpr int EPI_NRED(int epi) { return epi == EPI_DGRAD_ACT ? 3 : (epi == EPI_DGRAD ? 1 : 0); }
+// per-warp 32x33 transpose scratch + per-set [kind][quarter][BN] column sums
+constexpr int EPI_SMEM(int epi, int nsets, int bn) { return EPI_NRED(epi) == 0 ? 0 : (nsets * 4 * 32 * 33 + nsets * EPI_NRED(epi) * 4 * bn) * 4; }
 
 struct Args {
   int batch, gh, gw, tiles_x, tiles_y, K, N, BN;
   int n_ntiles, total_work;   // work item = (sample, tile, n-tile)
   int SA, SB, b_resident;     // A stages; B stages (streaming) or 0 with the whole weight slice resident
   int nacc;                   // TMEM accumulator stages (2 or 4)
+  int epi_off;                // byte offset of the epilogue scratch in dynamic shared memory
+  int XS, xs_off;             // xsave ring: stages (0 = epilogue reads xsave from global) and byte offset in dynamic smem
+  int xs_bcast;
+  int nsets;                  // epilogue warp sets (2, or 3 when the transform warps are free and smem allows)
   int in_bcast;
   TcTaps taps;
   float* out;
@@ -151,15 +160,20 @@ __device__ __forceinline__ Work decode(const Args& a, int w) {
 // tiles at the same time, so halo rows and weight slices are L2 hits).
 template <int EPI, bool MOD, bool RES>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, const Args a) {
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ CUtensorMap tmX, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[NBARS];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_scr[EPI == EPI_DGRAD ? 8 * 32 * 33 : 4];
-  __shared__ float s_red[EPI == EPI_DGRAD ? 2 * 4 * 256 : 4];
+  constexpr bool DG = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
+  constexpr int NRED = EPI == EPI_DGRAD_ACT ? 3 : 1;   // column reductions per tile
+
 
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_al = smem_raw + (smem0 - smem_u32(smem_raw));
+  // data-gradient epilogues: per-warp transpose scratch (8 x 32 x 33 floats) and per-set column sums, behind the A/B rings
+  float* const s_scr = reinterpret_cast<float*>(smem_al + a.epi_off);
+  float* const s_red = s_scr + a.nsets * 4 * 32 * 33;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SA = a.SA, SB = a.SB;
   const uint32_t b_slice_bytes = (uint32_t)a.BN * 128u;
@@ -173,12 +187,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   const uint32_t bar_b_all = bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB);
   auto bar_acc_full = [&](int s) { return bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB + 1 + s); };
   auto bar_acc_empty = [&](int s) { return bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB + 1 + MAX_ACC + s); };
+  auto bar_xs_full = [&](int s) { return bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB + 1 + 2 * MAX_ACC + s); };
+  auto bar_xs_empty = [&](int s) { return bar0 + 8u * (3 * MAX_SA + 2 * MAX_SB + 1 + 2 * MAX_ACC + MAX_XS + s); };
 
   if (tid == 0) {
     for (int s = 0; s < MAX_SA; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_ready(s), 128); mbar_init(bar_a_empty(s), 1); }
     for (int s = 0; s < MAX_SB; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
     mbar_init(bar_b_all, 1);
     for (int s = 0; s < MAX_ACC; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), 128); }
+    for (int s = 0; s < MAX_XS; ++s) { mbar_init(bar_xs_full(s), 1); mbar_init(bar_xs_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t tmem_cols = (uint32_t)(a.nacc * a.BN);
@@ -206,8 +223,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
           for (int kc = 0; kc < kchunks; ++kc)
             tma_load_2d(b_base + (uint32_t)(t * kchunks + kc) * b_slice_bytes, &tmB, bar_b_all, kc * 32, (int)a.taps.widx[t] * a.N);
       }
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      int sa = 0, sb = 0, sx = 0;
+      uint32_t pa = 0, pb = 0, px = 0;
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
         const Work wk = decode(a, w);
         const int bin = a.in_bcast ? 0 : wk.b;
@@ -225,6 +242,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               }
             if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
+        if (DG && a.XS > 0) {
+          // saved forward input of this tile for the epilogue (128 px x BN channels, one 16 KB box per 32 channels)
+          const int nch = a.BN >> 5;
+          mbar_wait(bar_xs_empty(sx), px ^ 1u);
+          mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK);
+          for (int c = 0; c < nch; ++c)
+            tma_load_5d(smem0 + a.xs_off + (uint32_t)(sx * nch + c) * XS_CHUNK, &tmX, bar_xs_full(sx), wk.n0 + c * 32, wk.x0, wk.y0, 0,
+                        a.xs_bcast ? 0 : wk.b);
+          if (++sx == a.XS) { sx = 0; px ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -304,7 +331,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
       if (elect_one()) umma_commit(bar_acc_full(as));
       __syncwarp();
     }
-  } else if (warp < 6) {
+  } else if (warp < 6 && (MOD || a.nsets < 3)) {
     if (MOD) {
       // ---------------- A transform: x * s[b, k], rounded to tf32 ----------------
       const int et = tid - 64;  // 0..127
@@ -344,40 +371,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     // two sets of four warps alternate tiles, so one tile's operand-load / store latency overlaps the next tile
-    const int eset = warp >= 10 ? 1 : 0;
-    const int et = tid - 192 - eset * 128;  // 0..127 within the set
+    const int eset = warp >= 10 ? 1 : (warp >= 6 ? 0 : 2);
+    const int et = (tid - 64) & 127;        // 0..127 within the set
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
     float* scr = s_scr + (eset * 4 + q) * (32 * 33);
-    float* red = s_red + eset * (4 * 256);
+    const int rs = 4 * a.BN;                // stride between reduction kinds
+    float* red = s_red + eset * (NRED * rs);
+    // per-pixel scalars (noise, skip-image gradient) of a work item; fetched one work item ahead so that their
+    // DRAM latency is hidden behind the current tile
+    const bool need_nz = EPI == EPI_ACT || EPI == EPI_DGRAD_ACT;
+    const bool has_rgb = EPI == EPI_DGRAD_ACT && a.e.drgb != nullptr;
+    const float nw = need_nz ? __ldg(a.e.noise_w) : 0.f;
+    auto fetch = [&](int w, float& o_nz, float& o_r0, float& o_r1, float& o_r2) {
+      o_nz = 0.f; o_r0 = 0.f; o_r1 = 0.f; o_r2 = 0.f;
+      if (w >= a.total_work) return;
+      const Work k = decode(a, w);
+      const int gy = k.y0 + (m >> 3), gx = k.x0 + (m & 7);
+      if (gy >= a.gh || gx >= a.gw) return;
+      const int pix = gy * a.gw + gx;
+      if (need_nz) o_nz = nw * __ldg(a.e.noise + (int64_t)k.b * a.e.noise_bstride + pix);
+      if (has_rgb) {
+        const int64_t hw = (int64_t)a.gh * a.gw;
+        o_r0 = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 0) * hw + pix);
+        o_r1 = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 1) * hw + pix);
+        o_r2 = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 2) * hw + pix);
+      }
+    };
+    const int wstep = a.nsets * gridDim.x;
+    float nz_n, rg0_n, rg1_n, rg2_n;
+    fetch(blockIdx.x + eset * gridDim.x, nz_n, rg0_n, rg1_n, rg2_n);
+    const bool xs_smem = DG && a.XS > 0;
+    const int nchunk = a.BN >> 5;
     int it = eset;
-    for (int w = blockIdx.x + eset * gridDim.x; w < a.total_work; w += 2 * gridDim.x, it += 2) {
+    for (int w = blockIdx.x + eset * gridDim.x; w < a.total_work; w += wstep, it += a.nsets) {
       const Work wk = decode(a, w);
       const int as = it & (a.nacc - 1);
       const int b = wk.b, n0 = wk.n0;
       const int gy = wk.y0 + (m >> 3), gx = wk.x0 + (m & 7);
       const bool valid = gy < a.gh && gx < a.gw;
       const int pix = gy * a.gw + gx;
-      float nz = 0.f;
-      if (EPI == EPI_ACT && valid) nz = __ldg(a.e.noise_w) * __ldg(a.e.noise + (int64_t)b * a.e.noise_bstride + pix);
+      const float nz = nz_n, rg0 = rg0_n, rg1 = rg1_n, rg2 = rg2_n;
+      fetch(w + wstep, nz_n, rg0_n, rg1_n, rg2_n);
       float* outp = nullptr;
       if (a.out != nullptr && valid)
         outp = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
                         (gx * a.out_stride + a.out_ox)) * a.N + n0;
       const float* xs = nullptr;
-      if (EPI == EPI_DGRAD && valid) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
-
-      float4 xpre[8];   // first chunk of the saved forward input, requested before the accumulator wait
-      if (EPI == EPI_DGRAD) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xpre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (xs) xpre[j] = __ldg(reinterpret_cast<const float4*>(xs + j * 4));
-        }
-      }
+      if (DG && valid && !xs_smem) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
+      // saved-input tile in shared memory (TMA, SWIZZLE_128B): pixel m is row m, channel quad j at position j ^ (m & 7)
+      const int sx = xs_smem ? it % a.XS : 0;
+      const uint8_t* xrow = smem_al + a.xs_off + (size_t)sx * nchunk * XS_CHUNK + m * 128;
+      if (xs_smem) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
+      auto load_x = [&](int c, int j) -> float4 {
+        if (xs_smem) return *reinterpret_cast<const float4*>(xrow + c * XS_CHUNK + ((j ^ (m & 7)) << 4));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xs) v = __ldg(reinterpret_cast<const float4*>(xs + c * 32 + j * 4));
+        return v;
+      };
       mbar_wait(bar_acc_full(as), ((uint32_t)it >> acc_shift) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nchunk = a.BN >> 5;
       for (int c = 0; c < nchunk; ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * a.BN + c * 32);
@@ -415,14 +468,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
               *reinterpret_cast<float4*>(outp + c * 32 + j * 4) =
                   make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
                               __uint_as_float(r[j * 4 + 3]));
-        } else {
+        } else if (EPI == EPI_DGRAD) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 x4 = xpre[j];
-            if (c > 0) {
-              x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (xs) x4 = __ldg(reinterpret_cast<const float4*>(xs + c * 32 + j * 4));
-            }
+            const float4 x4 = load_x(c, j);
             const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.e.mod_out + (int64_t)b * a.N + nc + j * 4));
             const float v0 = __uint_as_float(r[j * 4 + 0]), v1 = __uint_as_float(r[j * 4 + 1]);
             const float v2 = __uint_as_float(r[j * 4 + 2]), v3 = __uint_as_float(r[j * 4 + 3]);
@@ -437,14 +486,85 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
 #pragma unroll 8
           for (int l = 0; l < 32; ++l) sum += scr[l * 33 + lane];  // fixed order: deterministic
           __syncwarp();
-          red[q * 256 + c * 32 + lane] = sum;
+          red[q * a.BN + c * 32 + lane] = sum;
+        } else {
+          // data gradient + backward through noise / bias / lrelu (+ ToRGB branch) of the layer that produced xsave
+          constexpr float G = kLreluGain, GS = kLreluGain * kLreluSlope, IG = 1.f / kLreluGain, IGS = 1.f / (kLreluGain * kLreluSlope);
+          float tv[32], rv[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x4 = load_x(c, j);
+            const int64_t bn = (int64_t)b * a.N + nc + j * 4;
+            const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.e.mod_out + bn));
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.e.demod + bn));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.e.bias + nc + j * 4));
+            float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = u4;
+            if (has_rgb) {
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.e.wrgb + 0 * a.N + nc + j * 4));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.e.wrgb + 1 * a.N + nc + j * 4));
+              const float4 w2 = __ldg(reinterpret_cast<const float4*>(a.e.wrgb + 2 * a.N + nc + j * 4));
+              s4 = __ldg(reinterpret_cast<const float4*>(a.e.s_rgb + bn));
+              u4.x = fmaf(rg2, w2.x, fmaf(rg1, w1.x, rg0 * w0.x));
+              u4.y = fmaf(rg2, w2.y, fmaf(rg1, w1.y, rg0 * w0.y));
+              u4.z = fmaf(rg2, w2.z, fmaf(rg1, w1.z, rg0 * w0.z));
+              u4.w = fmaf(rg2, w2.w, fmaf(rg1, w1.w, rg0 * w0.w));
+            }
+            float4 o4;
+#define LFP_DGA(comp, k)                                                        \
+  {                                                                             \
+    const float v = __uint_as_float(r[j * 4 + k]);                              \
+    const float x = x4.comp;                                                    \
+    scr[lane * 33 + j * 4 + k] = x * v;                                         \
+    const float gt = fmaf(u4.comp, s4.comp, v * m4.comp);                       \
+    const bool pos = x > 0.f;                                                   \
+    const float gpre = gt * (pos ? G : GS);                                     \
+    const float pre = x * (pos ? IG : IGS);                                     \
+    tv[j * 4 + k] = valid ? gpre * (pre - nz - b4.comp) : 0.f;                  \
+    rv[j * 4 + k] = x * u4.comp;                                                \
+    o4.comp = gpre * d4.comp;                                                   \
+  }
+            LFP_DGA(x, 0) LFP_DGA(y, 1) LFP_DGA(z, 2) LFP_DGA(w, 3)
+#undef LFP_DGA
+            if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = o4;
+          }
+          __syncwarp();
+          float sum = 0.f;
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) sum += scr[l * 33 + lane];
+          __syncwarp();
+          red[q * a.BN + c * 32 + lane] = sum;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) scr[lane * 33 + k] = tv[k];
+          __syncwarp();
+          sum = 0.f;
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) sum += scr[l * 33 + lane];
+          __syncwarp();
+          red[rs + q * a.BN + c * 32 + lane] = sum;
+          if (has_rgb) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) scr[lane * 33 + k] = rv[k];
+            __syncwarp();
+            sum = 0.f;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) sum += scr[l * 33 + lane];
+            __syncwarp();
+            red[2 * rs + q * a.BN + c * 32 + lane] = sum;
+          }
         }
       }
-      if (EPI == EPI_DGRAD) {
+      if (xs_smem) mbar_arrive(bar_xs_empty(sx));   // this thread has read its row of the saved-input tile
+      if (DG) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
-        for (int n = et; n < a.BN; n += 128)
-          a.e.partial[((int64_t)b * tiles_per + wk.tile) * a.N + n0 + n] =
-              ((red[n] + red[256 + n]) + red[512 + n]) + red[768 + n];
+        for (int n = et; n < a.BN; n += 128) {
+          const int64_t o = ((int64_t)b * tiles_per + wk.tile) * a.N + n0 + n;
+          const int bn = a.BN;
+          a.e.partial[o] = ((red[n] + red[bn + n]) + red[2 * bn + n]) + red[3 * bn + n];
+          if (EPI == EPI_DGRAD_ACT) {
+            a.e.partial_T[o] = ((red[rs + n] + red[rs + bn + n]) + red[rs + 2 * bn + n]) + red[rs + 3 * bn + n];
+            if (has_rgb) a.e.partial_R[o] = ((red[2 * rs + n] + red[2 * rs + bn + n]) + red[2 * rs + 2 * bn + n]) + red[2 * rs + 3 * bn + n];
+          }
+        }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
       }
     }
@@ -501,37 +621,52 @@ int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N
 }
 
 template <int EPI, bool MOD, bool RES>
-static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE(EPI))));
+                                  (int)(tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE)));
     attr_done = true;
   }
   const int max_ctas = num_sms();
   const dim3 grid((unsigned)(a.total_work < max_ctas ? a.total_work : max_ctas));
-  tc::conv_tc_kernel<EPI, MOD, RES><<<grid, tc::NTHREADS, dyn_smem, s>>>(tmA, tmB, a);
+  tc::conv_tc_kernel<EPI, MOD, RES><<<grid, tc::NTHREADS, dyn_smem, s>>>(tmA, tmB, tmX, a);
   LFP_LAUNCH_CHECK();
   return 0;
 }
 
 template <int EPI, bool MOD>
-static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, tc::Args& a, int ntaps, cudaStream_t s) {
+static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, tc::Args& a, int ntaps, cudaStream_t s) {
   // shared-memory plan: the weight slice stays resident when it fits beside >= 3 activation stages
   const size_t b_all = (size_t)ntaps * (a.K / 32) * a.BN * 128;
-  const size_t budget = (size_t)tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE(EPI) - 1024;
-  if (a.n_ntiles == 1 && b_all + 3 * (size_t)tc::A_STAGE <= budget) {
-    a.b_resident = 1; a.SB = 0;
-    a.SA = (int)((budget - b_all) / tc::A_STAGE);
-  } else {
-    a.b_resident = 0; a.SB = tc::MAX_SB;
-    a.SA = (int)((budget - (size_t)a.SB * a.BN * 128) / tc::A_STAGE);
+  a.nsets = (!MOD && a.BN <= 128) ? 3 : 2;
+  constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
+  // data-gradient epilogues of the HBM-bound layers (N <= 64) get their saved-input tiles through a TMA ring
+  const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : 0;
+  size_t xs_smem = 0, epi_smem = 0;
+  for (int xs = xs_max;; --xs) {
+    a.XS = xs;
+    xs_smem = (size_t)xs * (a.BN / 32) * tc::XS_CHUNK;
+    epi_smem = tc::EPI_SMEM(EPI, a.nsets, a.BN) + xs_smem;
+    const size_t budget = (size_t)tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE - 1024 - epi_smem;
+    if (a.n_ntiles == 1 && b_all + 3 * (size_t)tc::A_STAGE <= budget) {
+      a.b_resident = 1; a.SB = 0;
+      a.SA = (int)((budget - b_all) / tc::A_STAGE);
+    } else {
+      a.b_resident = 0; a.SB = tc::MAX_SB;
+      while (a.SB > 2 && (size_t)a.SB * a.BN * 128 + 3 * (size_t)tc::A_STAGE > budget) --a.SB;
+      a.SA = (int)((budget - (size_t)a.SB * a.BN * 128) / tc::A_STAGE);
+    }
+    if ((a.SA >= 3 && (a.b_resident || a.SB >= 3)) || xs <= (xs_max > 0 ? 2 : 0)) break;
   }
   if (a.SA > tc::MAX_SA) a.SA = tc::MAX_SA;
   a.nacc = a.BN <= 128 ? 4 : 2;
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
-  const size_t smem = (size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128) + 1024;
-  return a.b_resident ? tc_launch2<EPI, MOD, true>(tmA, tmB, a, smem, s) : tc_launch2<EPI, MOD, false>(tmA, tmB, a, smem, s);
+  // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
+  a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
+  a.epi_off = (int)((size_t)a.xs_off + xs_smem);
+  const size_t smem = (size_t)a.xs_off + epi_smem + 1024;
+  return a.b_resident ? tc_launch2<EPI, MOD, true>(tmA, tmB, tmX, a, smem, s) : tc_launch2<EPI, MOD, false>(tmA, tmB, tmX, a, smem, s);
 }
 
 int launch_conv_tc(const TcConv& c, cudaStream_t s) {
@@ -561,10 +696,21 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   const int ntaps = c.taps.group_tap0[c.taps.ngroups];
   const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(c.wmap);
   const bool mod = c.mod != nullptr;
-  if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, a, ntaps, s) : tc_launch<EPI_ACT, false>(tmA, tmB, a, ntaps, s);
-  if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, a, ntaps, s) : tc_launch<EPI_STORE, false>(tmA, tmB, a, ntaps, s);
+  if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_ACT, false>(tmA, tmB, tmA, a, ntaps, s);
+  if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_STORE, false>(tmA, tmB, tmA, a, ntaps, s);
   LFP_CHECK_ARG(!mod, "conv_tc: the data-gradient kernel takes an unmodulated input");
-  return tc_launch<EPI_DGRAD, false>(tmA, tmB, a, ntaps, s);
+  // saved forward input [B or 1, gh, gw, N]: 128-pixel x 32-channel boxes for the epilogue
+  alignas(64) CUtensorMap tmX;
+  a.xs_bcast = c.e.xsave_bstride == 0 ? 1 : 0;
+  {
+    const int xb = a.xs_bcast ? 1 : c.batch;
+    const cuuint64_t xd[5] = {(cuuint64_t)c.N, (cuuint64_t)c.gw, (cuuint64_t)c.gh, 1, (cuuint64_t)xb};
+    const cuuint64_t xst[4] = {(cuuint64_t)c.N * 4, (cuuint64_t)c.gw * c.N * 4, (cuuint64_t)c.gh * c.gw * c.N * 4, (cuuint64_t)c.gh * c.gw * c.N * 4};
+    const cuuint32_t xbox[5] = {32, tc::TILE_W, tc::TILE_H, 1, 1};
+    LFP_TRY(tc::encode(&tmX, c.e.xsave, 5, xd, xst, xbox));
+  }
+  if (c.epi == EPI_DGRAD_ACT) return tc_launch<EPI_DGRAD_ACT, false>(tmA, tmB, tmX, a, ntaps, s);
+  return tc_launch<EPI_DGRAD, false>(tmA, tmB, tmX, a, ntaps, s);
 }
 
 }  // namespace lfp

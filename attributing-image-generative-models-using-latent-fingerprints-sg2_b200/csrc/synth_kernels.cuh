@@ -30,6 +30,10 @@ enum ConvEpilogue {
   EPI_STORE = 0,  // raw accumulator
   EPI_ACT = 1,    // *demod[b,n] + noise_w*noise[b?,gy,gx] + bias[n] -> lrelu*sqrt2   (src/model.py:360-366)
   EPI_DGRAD = 2,  // dx = acc*mod_out[b,n];  partial[seg,n] = sum_pix xsave*acc       (style gradient)
+  // EPI_DGRAD followed, in the same epilogue, by the backward through noise/bias/lrelu (+ ToRGB branch) of the layer
+  // that produced xsave (what act_bwd_kernel does as a separate pass): out = gpre*demod, partial_T, partial_R.
+  // Tensor-core kernel only.
+  EPI_DGRAD_ACT = 3,
 };
 
 struct ConvEpiArgs {
@@ -44,6 +48,12 @@ struct ConvEpiArgs {
   const float* xsave = nullptr;      // [B or 1, gh, gw, N] forward input of that layer
   int64_t xsave_bstride = 0;
   float* partial = nullptr;          // [ceil(B*gh*gw / seglen), N]
+  // EPI_DGRAD_ACT (fields demod / noise / noise_w / bias above then describe the layer that produced xsave)
+  const float* drgb = nullptr;       // [B, 3, gh*gw] gradient of the skip image at this resolution, or null
+  const float* s_rgb = nullptr;      // [B, N] ToRGB style
+  const float* wrgb = nullptr;       // [3, N]
+  float* partial_T = nullptr;        // [B * tiles, N]
+  float* partial_R = nullptr;        // [B * tiles, N]
 };
 
 // `out` may be null for EPI_DGRAD (gradient wrt the constant input is not needed)

@@ -74,7 +74,8 @@ struct lfp_synth {
   float* fir = nullptr;  // 4 x 16 floats: blur fwd coef, blur bwd coef, upsample kernel, flipped upsample kernel
   float blur1d[4] = {1, 3, 3, 1};
   bool finalized = false;
-  int tc_min_res = 4;   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
+  int tc_min_res = 4;
+  bool fuse_actbwd = true;   // run act_bwd inside the upstream dgrad epilogue on the tensor-core path (env LFP_FUSE_ACTBWD=0 disables)   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
   int fwd_batch = -1;
   std::vector<const float*> fwd_noise;
   std::vector<int> fwd_noise_batch;
@@ -174,6 +175,7 @@ Layout lfp_synth::layout(int B) const {
   const size_t half = (size_t)B * 3 * (size / 2) * (size / 2);
   L.dskipA = take(half);
   L.dskipB = take(half);
+  if (max_pX > max_pT) max_pT = max_pX;
   L.pT = take(max_pT);
   L.pR = take(max_pT);
   L.pX = take(max_pX);
@@ -200,6 +202,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   h->n_latent = ls * 2 - 2;
   h->num_noise = (ls - 2) * 2 + 1;
   if (blur_kernel_1d) memcpy(h->blur1d, blur_kernel_1d, 4 * sizeof(float));
+  if (const char* e = getenv("LFP_FUSE_ACTBWD")) h->fuse_actbwd = atoi(e) != 0;
   if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 4) h->tc_min_res = v; }
   for (int r = 4; r <= size; r *= 2) {
     const int c = h->channels(r);
@@ -501,12 +504,14 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
   const float* dskip = d_image;       // gradient wrt the running skip image at the current level
   float* g = nullptr;                 // gradient wrt the current layer's output activation (null: none yet)
   int cur = 0, dcur = 0;
+  bool act_done = false;   // backward through this layer's noise/bias/lrelu already applied by the upstream dgrad epilogue
   for (int li = (int)h->convs.size() - 1; li >= 0; --li) {
     const ConvLayer& c = h->convs[li];
     const int hw = c.res_out * c.res_out;
     const bool feeds_rgb = li == 0 || (li % 2) == 0;
     const RgbLayer* r = feeds_rgb ? &h->rgbs[li / 2] : nullptr;
     float* gbuf = g != nullptr ? g : bufs[cur];
+    if (!act_done) {
     ActBwdArgs ab{};
     ab.batch = B; ab.hw = hw; ab.C = c.cout; ab.act = ws + c.act_off; ab.g = gbuf; ab.g_has_input = g != nullptr;
     ab.demod = d_all + (size_t)B * c.demod_off;
@@ -519,6 +524,7 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     const int Q = hw / actbwd_seglen(hw, c.cout);
     LFP_TRY(launch_partial_reduce(ab.pT, T_all + (size_t)B * c.demod_off, B, Q, c.cout, c.cout, s));
     if (r) LFP_TRY(launch_partial_reduce(ab.pR, ds_all + (size_t)B * r->row0, B, Q, c.cout, c.cout, s));
+    }
     if (g == nullptr) { g = gbuf; }
     // g now holds dRaw = d(loss)/d(conv output before demod) * demod, at the layer's output resolution
     float* other = (g == bufs[0]) ? bufs[1] : bufs[0];
@@ -572,6 +578,28 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     ConvEpiArgs e;
     e.mod_out = s_all + (size_t)B * c.row0; e.xsave = xin; e.xsave_bstride = xin_bstride; e.partial = ws + L.pX;
     float* dx = li == 0 ? nullptr : other;
+    // the skip gradient crosses a resolution boundary through the Upsample adjoint; done before the dgrad because the
+    // fused epilogue below needs it at this layer's input resolution
+    if (c.up) {
+      float* nd = dskips[dcur];
+      LFP_TRY(upfirdn2d_dispatch(dskip, h->fir + 48, nd, LFP_F32, (int64_t)B * 3, c.res_out, c.res_out, 1, 4, 4, 1, 1, 2, 2, 1, 1, 1, 1, s, true));
+      dskip = nd;
+      dcur ^= 1;
+    }
+    // tensor-core path: the dgrad epilogue also runs the backward through noise/bias/lrelu (+ ToRGB branch) of the
+    // layer below (what act_bwd_kernel does as a separate pass) - it already holds that layer's saved output
+    const bool fuse = use_tc && li >= 1 && h->fuse_actbwd;
+    const ConvLayer* below = fuse ? &h->convs[li - 1] : nullptr;
+    const RgbLayer* rbelow = (fuse && ((li - 1) % 2 == 0)) ? &h->rgbs[(li - 1) / 2] : nullptr;
+    if (fuse) {
+      tq.epi = EPI_DGRAD_ACT;
+      e.demod = d_all + (size_t)B * below->demod_off;
+      e.noise = h->fwd_noise[below->noise_idx];
+      e.noise_bstride = h->fwd_noise_batch[below->noise_idx] == 1 ? 0 : (int64_t)below->res_out * below->res_out;
+      e.noise_w = below->noise_w; e.bias = below->act_bias;
+      e.partial_T = ws + L.pT; e.partial_R = ws + L.pR;
+      if (rbelow) { e.drgb = dskip; e.s_rgb = s_all + (size_t)B * rbelow->row0; e.wrgb = rbelow->wrgb; }
+    }
     const int hwi = c.res_in * c.res_in;
     int Qx = 0;
     if (use_tc) {
@@ -587,12 +615,11 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     LFP_TRY(launch_style_grad(R1_all + (size_t)B * c.row0, s_all + (size_t)B * c.row0, c.cin, T_all + (size_t)B * c.demod_off,
                               d_all + (size_t)B * c.demod_off, c.cout, c.wsq, ds_all + (size_t)B * c.row0, B, c.cin, c.cout, s));
     g = dx;
-    // crossing a resolution boundary: the skip gradient goes through the Upsample adjoint
-    if (c.up) {
-      float* nd = dskips[dcur];
-      LFP_TRY(upfirdn2d_dispatch(dskip, h->fir + 48, nd, LFP_F32, (int64_t)B * 3, c.res_out, c.res_out, 1, 4, 4, 1, 1, 2, 2, 1, 1, 1, 1, s, true));
-      dskip = nd;
-      dcur ^= 1;
+    act_done = false;
+    if (fuse) {
+      LFP_TRY(launch_partial_reduce(e.partial_T, T_all + (size_t)B * below->demod_off, B, Qx, below->cout, below->cout, s));
+      if (rbelow) LFP_TRY(launch_partial_reduce(e.partial_R, ds_all + (size_t)B * rbelow->row0, B, Qx, below->cout, below->cout, s));
+      act_done = true;
     }
   }
   LFP_TRY(launch_style_affine_bwd(ds_all, h->A_all, h->slot_begin, h->slot_end, h->row_base, h->row_cin, d_latent, B, h->rows, h->n_latent, h->style_dim, s));
