@@ -24,6 +24,7 @@
 //   whole [taps, K, BN] weight slice fits in shared memory (the HBM-bound C <= 64 layers), loaded once
 //   and kept resident for the CTA's lifetime.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 #include "synth_kernels.cuh"
@@ -36,7 +37,9 @@ constexpr int A_ROWS = HALO_W * HALO_H;   // 180 rows of 128 bytes
 constexpr int A_BYTES = A_ROWS * 128;     // 23040
 constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
 constexpr int MAX_SA = 8, MAX_SB = 4;
-constexpr int NTHREADS = 448;             // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-9 / 10-13 two epilogue sets
+// warp 0 TMA, warp 1 MMA, warps 2-5 transform (or a third epilogue set when there is nothing to transform),
+// warps 6-9 / 10-13 epilogue sets, warps 14-17 a third epilogue set of the modulated (forward) kernels
+constexpr int NTHREADS_MOD = 576, NTHREADS_PLAIN = 448;
 constexpr int MAX_ACC = 4;                // TMEM accumulator stages
 constexpr int MAX_XS = 4;                 // stages of the saved-input (xsave) tile ring of the data-gradient epilogues
 constexpr int XS_CHUNK = 128 * 128;       // one 128-pixel x 32-channel tile
@@ -159,7 +162,7 @@ __device__ __forceinline__ Work decode(const Args& a, int w) {
 // Persistent: CTA c processes work items c, c + gridDim.x, ...  (consecutive CTAs work on neighbouring
 // tiles at the same time, so halo rows and weight slices are L2 hits).
 template <int EPI, bool MOD, bool RES>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmX, const Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     // two sets of four warps alternate tiles, so one tile's operand-load / store latency overlaps the next tile
-    const int eset = warp >= 10 ? 1 : (warp >= 6 ? 0 : 2);
+    const int eset = warp >= 14 ? 2 : (warp >= 10 ? 1 : (warp >= 6 ? 0 : 2));
     const int et = (tid - 64) & 127;        // 0..127 within the set
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
     const bool xs_smem = DG && a.XS > 0;
     const int nchunk = a.BN >> 5;
     int it = eset;
-    for (int w = blockIdx.x + eset * gridDim.x; w < a.total_work; w += wstep, it += a.nsets) {
+    for (int w = eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work; w < a.total_work; w += wstep, it += a.nsets) {
       const Work wk = decode(a, w);
       const int as = it & (a.nacc - 1);
       const int b = wk.b, n0 = wk.n0;
@@ -429,6 +432,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         if (xs) v = __ldg(reinterpret_cast<const float4*>(xs + c * 32 + j * 4));
         return v;
       };
+      const bool do_rgb = EPI == EPI_ACT && a.e.rgb_out != nullptr;
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
       mbar_wait(bar_acc_full(as), ((uint32_t)it >> acc_shift) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int c = 0; c < nchunk; ++c) {
@@ -460,6 +465,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
             v.z = lrelu(fmaf(__uint_as_float(r[j * 4 + 2]), d4.z, nz) + b4.z);
             v.w = lrelu(fmaf(__uint_as_float(r[j * 4 + 3]), d4.w, nz) + b4.w);
             if (outp) *reinterpret_cast<float4*>(outp + c * 32 + j * 4) = v;
+            if (do_rgb) {   // ToRGB: 1x1 modulated conv, no demodulation (src/model.py:379-383)
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.e.s_rgb + (int64_t)b * a.N + nc + j * 4));
+              const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.e.wrgb + 0 * a.N + nc + j * 4));
+              const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.e.wrgb + 1 * a.N + nc + j * 4));
+              const float4 w2 = __ldg(reinterpret_cast<const float4*>(a.e.wrgb + 2 * a.N + nc + j * 4));
+              const float4 vs = make_float4(v.x * s4.x, v.y * s4.y, v.z * s4.z, v.w * s4.w);
+              rgb0 = fmaf(vs.x, w0.x, fmaf(vs.y, w0.y, fmaf(vs.z, w0.z, fmaf(vs.w, w0.w, rgb0))));
+              rgb1 = fmaf(vs.x, w1.x, fmaf(vs.y, w1.y, fmaf(vs.z, w1.z, fmaf(vs.w, w1.w, rgb1))));
+              rgb2 = fmaf(vs.x, w2.x, fmaf(vs.y, w2.y, fmaf(vs.z, w2.z, fmaf(vs.w, w2.w, rgb2))));
+            }
           }
         } else if (EPI == EPI_STORE) {
 #pragma unroll
@@ -554,6 +569,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const __grid_const
         }
       }
       if (xs_smem) mbar_arrive(bar_xs_empty(sx));   // this thread has read its row of the saved-input tile
+      if (do_rgb && valid) {
+        const int64_t hw = (int64_t)a.gh * a.gw;
+        float* ro = a.e.rgb_out + (int64_t)b * 3 * hw + pix;
+        ro[0] = rgb0 + __ldg(a.e.rgb_bias + 0);
+        ro[hw] = rgb1 + __ldg(a.e.rgb_bias + 1);
+        ro[2 * hw] = rgb2 + __ldg(a.e.rgb_bias + 2);
+      }
       if (DG) {
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
         for (int n = et; n < a.BN; n += 128) {
@@ -630,7 +652,7 @@ static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   }
   const int max_ctas = num_sms();
   const dim3 grid((unsigned)(a.total_work < max_ctas ? a.total_work : max_ctas));
-  tc::conv_tc_kernel<EPI, MOD, RES><<<grid, tc::NTHREADS, dyn_smem, s>>>(tmA, tmB, tmX, a);
+  tc::conv_tc_kernel<EPI, MOD, RES><<<grid, MOD ? tc::NTHREADS_MOD : tc::NTHREADS_PLAIN, dyn_smem, s>>>(tmA, tmB, tmX, a);
   LFP_LAUNCH_CHECK();
   return 0;
 }
@@ -639,13 +661,20 @@ template <int EPI, bool MOD>
 static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, tc::Args& a, int ntaps, cudaStream_t s) {
   // shared-memory plan: the weight slice stays resident when it fits beside >= 3 activation stages
   const size_t b_all = (size_t)ntaps * (a.K / 32) * a.BN * 128;
-  a.nsets = (!MOD && a.BN <= 128) ? 3 : 2;
+  // an epilogue set that finished tile i waits next for tile i + nsets; the parity wait on that TMEM stage is only
+  // unambiguous when the stage's previous use (tile i + nsets - nacc) is already known to be complete, i.e.
+  // nsets <= nacc (BN = 256 leaves room for two accumulator stages only)
+  a.nsets = a.BN <= 128 ? 3 : 2;
+  if (const char* e = getenv("LFP_TC_NSETS")) { const int v = atoi(e); if (v == 2) a.nsets = 2; }
   constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
   // data-gradient epilogues of the HBM-bound layers (N <= 64) get their saved-input tiles through a TMA ring
   const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : 0;
   size_t xs_smem = 0, epi_smem = 0;
   for (int xs = xs_max;; --xs) {
     a.XS = xs;
+    // same parity argument for the saved-input ring: a set may only wait on stage (i + nsets) % XS when the stage's
+    // previous use (tile i + nsets - XS) is one it has already seen complete, i.e. nsets <= XS
+    if (xs > 0 && a.nsets > xs) a.nsets = xs;
     xs_smem = (size_t)xs * (a.BN / 32) * tc::XS_CHUNK;
     epi_smem = tc::EPI_SMEM(EPI, a.nsets, a.BN) + xs_smem;
     const size_t budget = (size_t)tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE - 1024 - epi_smem;
@@ -661,6 +690,7 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   }
   if (a.SA > tc::MAX_SA) a.SA = tc::MAX_SA;
   a.nacc = a.BN <= 128 ? 4 : 2;
+  if (const char* e = getenv("LFP_TC_NACC")) { const int v = atoi(e); if (v == 2 || (v == 4 && a.BN <= 128)) a.nacc = v; }
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
   // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
   a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));

@@ -418,6 +418,23 @@ int launch_torgb_fwd(const float* act, const float* s, const float* wrgb, const 
   return 0;
 }
 
+__global__ void __launch_bounds__(256) skip_add_kernel(float* __restrict__ rgb, const float* __restrict__ skip,
+                                                       const float* __restrict__ kup, int h, int w) {
+  const int64_t hw = (int64_t)h * w;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= hw) return;
+  const int plane = blockIdx.y;   // b*3 + o
+  const int y = (int)(i / w), x = (int)(i - (int64_t)y * w);
+  rgb[plane * hw + i] += up2_sample(skip + (int64_t)plane * (h / 2) * (w / 2), h / 2, w / 2, kup, y, x);
+}
+
+int launch_skip_add(float* rgb, const float* skip, const float* kup, int batch, int h, int w, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div((int64_t)h * w, 256), (unsigned)(batch * 3));
+  skip_add_kernel<<<grid, 256, 0, st>>>(rgb, skip, kup, h, w);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
 // =============================================================================================
 // Backward through noise / bias / lrelu (+ ToRGB branch), with the two style-gradient reductions
 // =============================================================================================
@@ -446,24 +463,47 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdArgs a, int C4
       w2 = __ldg(reinterpret_cast<const float4*>(a.wrgb + 2 * C + c4 * 4));
     }
     const float inv_pos = 1.f / kLreluGain, inv_neg = 1.f / (kLreluGain * kLreluSlope);
-    for (int i = py; i < seglen; i += PX) {
-      const int pix = pix0 + i;
-      const int64_t idx = ((int64_t)b * a.hw + pix) * C + c4 * 4;
-      const float4 act4 = __ldg(reinterpret_cast<const float4*>(a.act + idx));
-      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.g_has_input) g4 = *reinterpret_cast<const float4*>(a.g + idx);
-      if (has_rgb) {
-        const float r0 = __ldg(a.drgb + ((int64_t)b * 3 + 0) * a.hw + pix);
-        const float r1 = __ldg(a.drgb + ((int64_t)b * 3 + 1) * a.hw + pix);
-        const float r2 = __ldg(a.drgb + ((int64_t)b * 3 + 2) * a.hw + pix);
-        float4 q4 = make_float4(r0 * w0.x, r0 * w0.y, r0 * w0.z, r0 * w0.w);
-        q4 = f4_fma(r1, w1, q4);
-        q4 = f4_fma(r2, w2, q4);
-        g4 = f4_fma4(q4, s4, g4);
-        R4 = f4_fma4(act4, q4, R4);
+    // four pixels per trip with all loads issued first (memory-level parallelism); the accumulation order is the
+    // plain i order, so results do not depend on the unrolling
+    constexpr int U = 4;
+    for (int i0 = py; i0 < seglen; i0 += U * PX) {
+      float4 act_v[U], g_v[U];
+      float r0v[U], r1v[U], r2v[U], nzv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * PX;
+        const bool in = i < seglen;
+        const int pix = pix0 + (in ? i : py);
+        const int64_t idx = ((int64_t)b * a.hw + pix) * C + c4 * 4;
+        act_v[u] = __ldg(reinterpret_cast<const float4*>(a.act + idx));
+        g_v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.g_has_input) g_v[u] = *reinterpret_cast<const float4*>(a.g + idx);
+        r0v[u] = r1v[u] = r2v[u] = 0.f;
+        if (has_rgb) {
+          r0v[u] = __ldg(a.drgb + ((int64_t)b * 3 + 0) * a.hw + pix);
+          r1v[u] = __ldg(a.drgb + ((int64_t)b * 3 + 1) * a.hw + pix);
+          r2v[u] = __ldg(a.drgb + ((int64_t)b * 3 + 2) * a.hw + pix);
+        }
+        nzv[u] = nw * __ldg(a.noise + (int64_t)b * a.noise_bstride + pix);
       }
-      const float nz = nw * __ldg(a.noise + (int64_t)b * a.noise_bstride + pix);
-      float4 o4;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * PX;
+        if (i >= seglen) break;
+        const int pix = pix0 + i;
+        const int64_t idx = ((int64_t)b * a.hw + pix) * C + c4 * 4;
+        const float4 act4 = act_v[u];
+        float4 g4 = g_v[u];
+        if (has_rgb) {
+          const float r0 = r0v[u], r1 = r1v[u], r2 = r2v[u];
+          float4 q4 = make_float4(r0 * w0.x, r0 * w0.y, r0 * w0.z, r0 * w0.w);
+          q4 = f4_fma(r1, w1, q4);
+          q4 = f4_fma(r2, w2, q4);
+          g4 = f4_fma4(q4, s4, g4);
+          R4 = f4_fma4(act4, q4, R4);
+        }
+        const float nz = nzv[u];
+        float4 o4;
 #define LFP_ACTB(comp)                                                          \
   {                                                                             \
     const bool pos = act4.comp > 0.f;                                           \
@@ -472,9 +512,10 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdArgs a, int C4
     T4.comp = fmaf(gpre, pre - nz - bias4.comp, T4.comp);                       \
     o4.comp = gpre * d4.comp;                                                   \
   }
-      LFP_ACTB(x) LFP_ACTB(y) LFP_ACTB(z) LFP_ACTB(w)
+        LFP_ACTB(x) LFP_ACTB(y) LFP_ACTB(z) LFP_ACTB(w)
 #undef LFP_ACTB
-      *reinterpret_cast<float4*>(a.g + idx) = o4;
+        *reinterpret_cast<float4*>(a.g + idx) = o4;
+      }
     }
     *reinterpret_cast<float4*>(&redT[py * C + c4 * 4]) = T4;
     *reinterpret_cast<float4*>(&redR[py * C + c4 * 4]) = R4;

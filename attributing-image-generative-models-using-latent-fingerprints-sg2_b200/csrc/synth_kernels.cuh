@@ -54,6 +54,10 @@ struct ConvEpiArgs {
   const float* wrgb = nullptr;       // [3, N]
   float* partial_T = nullptr;        // [B * tiles, N]
   float* partial_R = nullptr;        // [B * tiles, N]
+  // EPI_ACT on the tensor-core kernel, layers feeding a ToRGB (s_rgb / wrgb above): rgb_out[b,o,pix] =
+  // sum_n act[b,pix,n]*s_rgb[b,n]*wrgb[o,n] + rgb_bias[o]; the FIR-upsampled skip is added by launch_skip_add
+  float* rgb_out = nullptr;          // [B, 3, gh*gw] or null
+  const float* rgb_bias = nullptr;   // [3]
 };
 
 // `out` may be null for EPI_DGRAD (gradient wrt the constant input is not needed)
@@ -105,6 +109,9 @@ int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream
 int launch_torgb_fwd(const float* act, const float* s, const float* wrgb, const float* bias,
                      const float* skip, const float* kup, float* rgb, int batch, int h, int w,
                      int C, cudaStream_t s_);
+
+// rgb[b,o,y,x] += up2(skip)[b,o,y,x]   (the Upsample branch of ToRGB, src/model.py:384-386)
+int launch_skip_add(float* rgb, const float* skip, const float* kup, int batch, int h, int w, cudaStream_t st);
 
 // Backward through noise/bias/lrelu (+ the ToRGB branch) of one StyledConv, in place on g:
 //   gtot = g (or 0) + sum_o drgb[b,o,pix]*s_rgb[b,c]*wrgb[o,c]

@@ -17,6 +17,11 @@
     const int _r = (call);                                  \
     (h)->prof_end(_p, s);                                   \
     if (_r != 0) return _r;                                 \
+    if ((h)->debug_sync) {                                  \
+      fprintf(stderr, "[lfp] kind %d flops %.3g bytes %.3g ...", (int)(kind), (double)(flops), (double)(bytes)); \
+      const cudaError_t _e = cudaStreamSynchronize(s);      \
+      fprintf(stderr, " %s\n", cudaGetErrorString(_e));     \
+    }                                                       \
   } while (0)
 
 namespace lfp {
@@ -75,6 +80,9 @@ struct lfp_synth {
   float blur1d[4] = {1, 3, 3, 1};
   bool finalized = false;
   int tc_min_res = 4;
+  bool debug_sync = false;   // env LFP_DEBUG_SYNC=1: synchronise and log after every profiled launch
+  bool fuse_rgb = false;     // ToRGB inside the forward conv epilogue on the tensor-core path (env LFP_FUSE_RGB=1 enables;
+                             // measured slower than the separate kernel: the epilogue is the longer pole at N <= 64)
   bool fuse_actbwd = true;   // run act_bwd inside the upstream dgrad epilogue on the tensor-core path (env LFP_FUSE_ACTBWD=0 disables)   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
   int fwd_batch = -1;
   std::vector<const float*> fwd_noise;
@@ -202,6 +210,8 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   h->n_latent = ls * 2 - 2;
   h->num_noise = (ls - 2) * 2 + 1;
   if (blur_kernel_1d) memcpy(h->blur1d, blur_kernel_1d, 4 * sizeof(float));
+  if (const char* e = getenv("LFP_DEBUG_SYNC")) h->debug_sync = atoi(e) != 0;
+  if (const char* e = getenv("LFP_FUSE_RGB")) h->fuse_rgb = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_ACTBWD")) h->fuse_actbwd = atoi(e) != 0;
   if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 4) h->tc_min_res = v; }
   for (int r = 4; r <= size; r *= 2) {
@@ -411,6 +421,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
     const int nb = noise_batch[c.noise_idx];
     const int64_t nstride = nb == 1 ? 0 : (int64_t)c.res_out * c.res_out;
     const bool use_tc = precision == LFP_PREC_TF32 && c.tc_fwd && c.res_in >= h->tc_min_res;
+    bool rgb_fused = false;
     if (!c.up) {
       ConvGeom g{};
       g.batch = B; g.gh = g.gw = c.res_out; g.in_h = g.in_w = c.res_in; g.in_bstride = x_bstride; g.in_stride = 1;
@@ -426,6 +437,14 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
         t.taps.ngroups = 1; t.taps.group_plane[0] = 0; t.taps.group_tap0[0] = 0; t.taps.group_tap0[1] = 9;
         for (int i = 0; i < 9; ++i) { t.taps.dy[i] = g.dy[i]; t.taps.dx[i] = g.dx[i]; t.taps.widx[i] = g.widx[i]; }
         t.epi = EPI_ACT; t.e = e;
+        // ToRGB of this layer inside the conv epilogue (all channels of a pixel are in one CTA when Cout <= 256)
+        if (h->fuse_rgb && (li == 0 || (li % 2) == 0) && c.cout <= 256) {
+          const size_t ri = li / 2;
+          const RgbLayer& r = h->rgbs[ri];
+          t.e.s_rgb = s_all + (size_t)B * r.row0; t.e.wrgb = r.wrgb; t.e.rgb_bias = r.bias;
+          t.e.rgb_out = (ri + 1 == h->rgbs.size()) ? image : ws + r.skip_off;
+          rgb_fused = true;
+        }
         LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_tc(t, s));
       } else {
         LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_simt(x, smod, c.wf, act, g, EPI_ACT, e, s));
@@ -474,6 +493,9 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
       const bool last = ri + 1 == h->rgbs.size();
       float* dst = last ? image : ws + r.skip_off;
       const float* skip = ri == 0 ? nullptr : ws + h->rgbs[ri - 1].skip_off;
+      if (rgb_fused) {
+        if (skip) LFP_PROF(h, LFP_KIND_TORGB, 0.0, 4.0 * B * r.res * r.res * 6.75, s, launch_skip_add(dst, skip, h->fir + 32, B, r.res, r.res, s));
+      } else
       LFP_PROF(h, LFP_KIND_TORGB, 0.0, 4.0 * B * r.res * r.res * (r.cin + 3.75), s,
                launch_torgb_fwd(act, s_all + (size_t)B * r.row0, r.wrgb, r.bias, skip, h->fir + 32, dst, B, r.res, r.res, r.cin, s));
     }
