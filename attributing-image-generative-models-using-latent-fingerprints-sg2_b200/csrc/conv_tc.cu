@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     for (int s = 0; s < MAX_XS; ++s) { mbar_init(bar_xs_full(s), 1); mbar_init(bar_xs_empty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t tmem_cols = (uint32_t)(a.nacc * a.BN);
+  const uint32_t tmem_cols = (uint32_t)(a.nacc * a.BN * a.taps.nphase);
   const int acc_shift = a.nacc == 4 ? 2 : 1;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
@@ -269,12 +269,15 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
     // per-tap descriptor offsets (16-byte units), kept in registers: the issue loop below is fully unrolled
-    uint32_t tap_a[9], tap_b[9];
+    uint32_t tap_a[9], tap_b[9], tap_p[9];
+    const int nphase = a.taps.nphase;
+    const uint32_t stage_cols = (uint32_t)(nphase * a.BN);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int tt = t < ntaps ? t : 0;
       tap_a[t] = (uint32_t)((((int)a.taps.dy[tt] + 1) * HALO_W + ((int)a.taps.dx[tt] + 1)) * 8);
       tap_b[t] = b_lo0 + (uint32_t)(tt * kchunks) * b_slice16;
+      tap_p[t] = nphase > 1 ? (uint32_t)a.taps.acc[tt] : 0u;
     }
     if (RES) mbar_wait(bar_b_all, 0);
     int it = 0;
@@ -282,8 +285,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       const int as = it & (a.nacc - 1);
       mbar_wait(bar_acc_empty(as), (((uint32_t)it >> acc_shift) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem + (uint32_t)(as * a.BN);
-      uint32_t accumulate = 0;
+      const uint32_t tacc0 = tmem + (uint32_t)as * stage_cols;
+      uint32_t started = 0;   // bit p: accumulator p of this tile has received its first MMA
       for (int kc = 0; kc < kchunks; ++kc)
         for (int g = 0; g < ngroups; ++g) {
           mbar_wait(MOD ? bar_a_ready(sa) : bar_a_full(sa), pa);
@@ -298,16 +301,17 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               for (int t = 0; t < 9; ++t)
                 if (t >= t0 && t < t1) {
                   const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = tap_b[t] + kc_off;
-                  umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+                  const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
+                  umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, (started >> tap_p[t]) & 1u);
                   umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
-                  accumulate = 1;
+                  started |= 1u << tap_p[t];
                 }
               umma_commit(bar_a_empty(sa));
             }
             __syncwarp();
-            accumulate = 1;
+            started = (1u << nphase) - 1u;   // every accumulator has taps in every activation stage
           } else {
 #pragma unroll
             for (int t = 0; t < 9; ++t)
@@ -315,6 +319,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                 mbar_wait(bar_b_full(sb), pb);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)sb * b_slice16;
+                const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
+                const uint32_t accumulate = (started >> tap_p[t]) & 1u;
                 if (elect_one()) {
                   umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
                   umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   umma_commit(bar_b_empty(sb));
                 }
                 __syncwarp();
-                accumulate = 1;
+                started |= 1u << tap_p[t];
                 if (++sb == SB) { sb = 0; pb ^= 1u; }
               }
             if (elect_one()) umma_commit(bar_a_empty(sa));
@@ -416,10 +422,11 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       const int pix = gy * a.gw + gx;
       const float nz = nz_n, rg0 = rg0_n, rg1 = rg1_n, rg2 = rg2_n;
       fetch(w + wstep, nz_n, rg0_n, rg1_n, rg2_n);
-      float* outp = nullptr;
+      float* outp0 = nullptr;
       if (a.out != nullptr && valid)
-        outp = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
+        outp0 = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
                         (gx * a.out_stride + a.out_ox)) * a.N + n0;
+      float* const outp = outp0;
       const float* xs = nullptr;
       if (DG && valid && !xs_smem) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
       // saved-input tile in shared memory (TMA, SWIZZLE_128B): pixel m is row m, channel quad j at position j ^ (m & 7)
@@ -436,9 +443,11 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
       mbar_wait(bar_acc_full(as), ((uint32_t)it >> acc_shift) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int nphase = a.taps.nphase;
+      for (int ph = 0; ph < nphase; ++ph)
       for (int c = 0; c < nchunk; ++c) {
         uint32_t r[32];
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * a.BN + c * 32);
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((as * nphase + ph) * a.BN + c * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
             "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -448,7 +457,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c == nchunk - 1) {
+        if (c == nchunk - 1 && ph == nphase - 1) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(bar_acc_empty(as));
@@ -477,6 +486,12 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             }
           }
         } else if (EPI == EPI_STORE) {
+          float* outp = outp0;
+          if (nphase > 1) {   // fused sub-pixel phases: accumulator ph -> output plane ph over its own (smaller) grid
+            outp = nullptr;
+            if (a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1))
+              outp = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (outp)
@@ -689,7 +704,8 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if ((a.SA >= 3 && (a.b_resident || a.SB >= 3)) || xs <= (xs_max > 0 ? 2 : 0)) break;
   }
   if (a.SA > tc::MAX_SA) a.SA = tc::MAX_SA;
-  a.nacc = a.BN <= 128 ? 4 : 2;
+  a.nacc = a.BN * a.taps.nphase <= 128 ? 4 : 2;
+  if (a.nsets > a.nacc) a.nsets = a.nacc;
   if (const char* e = getenv("LFP_TC_NACC")) { const int v = atoi(e); if (v == 2 || (v == 4 && a.BN <= 128)) a.nacc = v; }
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
   // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
@@ -702,6 +718,8 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   LFP_CHECK_ARG(tc_supported(c.K, c.N, c.gh, c.gw), "conv_tc: unsupported shape K=%d N=%d grid %dx%d", c.K, c.N, c.gh, c.gw);
   LFP_CHECK_ARG(c.taps.ngroups >= 1 && c.taps.ngroups <= 4 && c.taps.group_tap0[c.taps.ngroups] <= 9, "conv_tc: bad tap table");
+  LFP_CHECK_ARG(c.taps.nphase <= 1 || (c.taps.nphase == 4 && c.epi == EPI_STORE && c.taps.ngroups == 1 && tc_block_n(c.N) * 8 <= 512),
+                "conv_tc: fused phases need EPI_STORE, one tap group and N <= 64");
   LFP_CHECK_ARG(((uintptr_t)c.in & 15) == 0 && c.wmap != nullptr, "conv_tc: input must be 16-byte aligned");
   alignas(64) CUtensorMap tmA;
   const int nb = c.in_bcast ? 1 : c.batch;
@@ -716,6 +734,7 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   a.K = c.K; a.N = c.N; a.BN = tc_block_n(c.N);
   a.in_bcast = c.in_bcast ? 1 : 0;
   a.taps = c.taps;
+  if (a.taps.nphase <= 0) a.taps.nphase = 1;
   a.out = c.out; a.out_planes = c.out_planes; a.out_plane = c.out_plane; a.out_h = c.out_h; a.out_w = c.out_w;
   a.out_stride = c.out_stride > 0 ? c.out_stride : 1; a.out_oy = c.out_oy; a.out_ox = c.out_ox;
   a.mod = c.mod; a.e = c.e;

@@ -296,7 +296,96 @@ __global__ void __launch_bounds__(256) fir4x4_nhwc_kernel(const float* __restric
   }
 }
 
+// Separable variant: horizontal 4-tap pass on every input row as it is loaded (XO results per row), vertical 4-tap pass
+// over a sliding window of the last four horizontal rows.
+template <bool ACT, int XO>
+__global__ void __launch_bounds__(256) fir4x4_sep_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                              const FirArgs a, int C4, int PX, int RY) {
+  constexpr int WC = XO + 3;
+  const int c4 = threadIdx.x % C4;
+  const int px = threadIdx.x / C4;
+  const int ox0 = (blockIdx.x * PX + px) * XO;
+  const int oy0 = blockIdx.y * RY;
+  const int b = blockIdx.z;
+  if (px >= PX || ox0 >= a.out_w) return;
+  float kx[4], ky[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { kx[i] = __ldg(a.kx + i); ky[i] = __ldg(a.ky + i); }
+  const int C = a.C;
+  const int iph = (a.in_h + 1) >> 1, ipw = (a.in_w + 1) >> 1, oph = (a.out_h + 1) >> 1, opw = (a.out_w + 1) >> 1;
+  const int64_t in_per = a.in_planar ? (int64_t)4 * iph * ipw : (int64_t)a.in_h * a.in_w;
+  const int64_t out_per = a.out_planar ? (int64_t)4 * oph * opw : (int64_t)a.out_h * a.out_w;
+  const float* src = in + (int64_t)b * in_per * C + c4 * 4;
+  float4 hwin[4][XO];
+  auto hrow = [&](int iy, float4(&h)[XO]) {
+    float4 v[WC];
+#pragma unroll
+    for (int tx = 0; tx < WC; ++tx) {
+      const int ix = ox0 + tx - a.pad;
+      v[tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < a.in_h && ix >= 0 && ix < a.in_w) {
+        int64_t e = (int64_t)iy * a.in_w + ix;
+        if (a.in_planar) e = ((int64_t)((iy & 1) * 2 + (ix & 1)) * iph + (iy >> 1)) * ipw + (ix >> 1);
+        v[tx] = __ldg(reinterpret_cast<const float4*>(src + e * C));
+      }
+    }
+#pragma unroll
+    for (int xo = 0; xo < XO; ++xo) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int tx = 0; tx < 4; ++tx) acc = f4_fma(kx[tx], v[xo + tx], acc);
+      h[xo] = acc;
+    }
+  };
+  hrow(oy0 - a.pad + 0, hwin[0]);
+  hrow(oy0 - a.pad + 1, hwin[1]);
+  hrow(oy0 - a.pad + 2, hwin[2]);
+  float4 d4 = make_float4(1.f, 1.f, 1.f, 1.f), bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float nw = 0.f;
+  if (ACT) {
+    d4 = __ldg(reinterpret_cast<const float4*>(a.demod + (int64_t)b * C + c4 * 4));
+    bias4 = __ldg(reinterpret_cast<const float4*>(a.bias + c4 * 4));
+    nw = __ldg(a.noise_w);
+  }
+  for (int o = 0; o < RY; o += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int oy = oy0 + o + u;
+      if (oy >= a.out_h) return;
+      hrow(oy + 3 - a.pad, hwin[(u + 3) & 3]);
+#pragma unroll
+      for (int xo = 0; xo < XO; ++xo) {
+        const int ox = ox0 + xo;
+        if (ox >= a.out_w) break;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc = f4_fma(ky[r], hwin[(u + r) & 3][xo], acc);
+        if (ACT) {
+          const float nz = nw * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox);
+          acc.x = lrelu_fwd(fmaf(acc.x, d4.x, nz) + bias4.x);
+          acc.y = lrelu_fwd(fmaf(acc.y, d4.y, nz) + bias4.y);
+          acc.z = lrelu_fwd(fmaf(acc.z, d4.z, nz) + bias4.z);
+          acc.w = lrelu_fwd(fmaf(acc.w, d4.w, nz) + bias4.w);
+        }
+        int64_t oe = (int64_t)oy * a.out_w + ox;
+        if (a.out_planar) oe = ((int64_t)((oy & 1) * 2 + (ox & 1)) * oph + (oy >> 1)) * opw + (ox >> 1);
+        *reinterpret_cast<float4*>(out + ((int64_t)b * out_per + oe) * C + c4 * 4) = acc;
+      }
+    }
+  }
+}
+
 int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream_t s) {
+  if (a.kx != nullptr && a.ky != nullptr && a.out_w >= 64 && a.C % 4 == 0 && a.C <= 1024) {
+    const int C4 = a.C / 4;
+    const int PX = 256 / C4 > 0 ? 256 / C4 : 1;
+    const int RY = a.out_h >= 256 ? 32 : 16;
+    dim3 grid((unsigned)ceil_div(a.out_w, PX * 4), (unsigned)ceil_div(a.out_h, RY), (unsigned)a.batch);
+    if (a.act) fir4x4_sep_nhwc_kernel<true, 4><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+    else fir4x4_sep_nhwc_kernel<false, 4><<<grid, 256, 0, s>>>(in, out, a, C4, PX, RY);
+    LFP_LAUNCH_CHECK();
+    return 0;
+  }
   LFP_CHECK_ARG(a.C % 4 == 0 && a.C <= 1024, "fir: C=%d must be a multiple of 4 and <= 1024", a.C);
   const int C4 = a.C / 4;
   const int PX = 256 / C4 > 0 ? 256 / C4 : 1;

@@ -75,6 +75,10 @@ struct TcTaps {
   int group_plane[4];
   int group_tap0[5];  // taps of group g are [group_tap0[g], group_tap0[g+1])
   signed char dy[9], dx[9], widx[9];
+  // fused sub-pixel phases (EPI_STORE only): tap t accumulates into accumulator acc[t] in [0, nphase); accumulator p is
+  // written to output plane p over the grid (gh - (p >> 1), gw - (p & 1)).  nphase = 1: ordinary convolution.
+  signed char acc[9];
+  int nphase;
 };
 struct TcConv {
   const float* in; int in_planes, in_h, in_w; bool in_bcast;
@@ -98,6 +102,9 @@ struct FirArgs {
   const float* coef;
   // phase-major storage of the odd-sized side ([B, 4, (n+1)/2, (n+1)/2, C], plane = (y&1)*2 + (x&1))
   bool in_planar = false, out_planar = false;
+  // separable form of the same taps, coef[ty*4+tx] = ky[ty]*kx[tx] (device pointers to 4 floats each); when set the
+  // wide layers use the row/column two-pass kernel (half the FMAs, 1.75 loads per output instead of 2.5)
+  const float* kx = nullptr; const float* ky = nullptr;
   bool act = false;
   const float* demod = nullptr; const float* noise = nullptr; int64_t noise_bstride = 0;
   const float* noise_w = nullptr; const float* bias = nullptr;

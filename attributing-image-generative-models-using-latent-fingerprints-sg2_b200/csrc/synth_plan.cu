@@ -81,6 +81,7 @@ struct lfp_synth {
   bool finalized = false;
   int tc_min_res = 4;
   bool debug_sync = false;   // env LFP_DEBUG_SYNC=1: synchronise and log after every profiled launch
+  bool fuse_phases = true;   // one launch for the four sub-pixel phases of the C <= 64 transposed convs (env LFP_FUSE_PHASES=0 disables)
   bool fuse_rgb = false;     // ToRGB inside the forward conv epilogue on the tensor-core path (env LFP_FUSE_RGB=1 enables;
                              // measured slower than the separate kernel: the epilogue is the longer pole at N <= 64)
   bool fuse_actbwd = true;   // run act_bwd inside the upstream dgrad epilogue on the tensor-core path (env LFP_FUSE_ACTBWD=0 disables)   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
@@ -211,6 +212,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   h->num_noise = (ls - 2) * 2 + 1;
   if (blur_kernel_1d) memcpy(h->blur1d, blur_kernel_1d, 4 * sizeof(float));
   if (const char* e = getenv("LFP_DEBUG_SYNC")) h->debug_sync = atoi(e) != 0;
+  if (const char* e = getenv("LFP_FUSE_PHASES")) h->fuse_phases = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_RGB")) h->fuse_rgb = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_ACTBWD")) h->fuse_actbwd = atoi(e) != 0;
   if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 4) h->tc_min_res = v; }
@@ -286,7 +288,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   rc |= h->alloc_i(&h->row_cin, rows);
   rc |= h->alloc_i(&h->slot_begin, h->n_latent);
   rc |= h->alloc_i(&h->slot_end, h->n_latent);
-  rc |= h->alloc(&h->fir, 64);
+  rc |= h->alloc(&h->fir, 80);
   if (rc != 0) { delete h; return rc; }
   auto up = [&](void* d, const void* s, size_t n) { return cudaMemcpy(d, s, n, cudaMemcpyHostToDevice); };
   cudaError_t e = up(h->row_slot, row_slot.data(), rows * sizeof(int));
@@ -296,7 +298,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   if (e == cudaSuccess) e = up(h->slot_end, se.data(), h->n_latent * sizeof(int));
   // FIR tables.  k2 = outer(k,k)/sum * 4 is both Blur(upsample_factor=2) (src/model.py:75-86) and
   // Upsample (src/model.py:37-38).
-  float k2[16], tab[64];
+  float k2[16], tab[80];
   float sum = 0.f;
   for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { k2[i * 4 + j] = h->blur1d[i] * h->blur1d[j]; sum += k2[i * 4 + j]; }
   for (int i = 0; i < 16; ++i) k2[i] = k2[i] / sum * 4.f;
@@ -307,6 +309,15 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
       tab[32 + ty * 4 + tx] = k2[ty * 4 + tx];              // upsample kernel as stored by the module
       tab[48 + ty * 4 + tx] = k2[(3 - ty) * 4 + (3 - tx)];  // flipped, for the skip-upsample adjoint
     }
+  {
+    // separable factors of the same tables: k2 = outer(k, k) / sum(k)^2 * 4 = outer(g, g), g = 2 k / sum(k)
+    float s1 = 0.f;
+    for (int i = 0; i < 4; ++i) s1 += h->blur1d[i];
+    for (int i = 0; i < 4; ++i) {
+      tab[64 + i] = 2.f * h->blur1d[3 - i] / s1;   // blur forward (flipped taps)
+      tab[68 + i] = 2.f * h->blur1d[i] / s1;       // blur adjoint (un-flipped taps)
+    }
+  }
   if (e == cudaSuccess) e = up(h->fir, tab, sizeof(tab));
   if (e != cudaSuccess) { set_error("synth_create: %s", cudaGetErrorString(e)); delete h; return (int)e; }
   *out = h;
@@ -453,6 +464,29 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
       // stride-2 transposed conv as four sub-pixel phases into [B, 2H+1, 2W+1, Cout], then blur+epilogue
       float* T = ws + L.scratchT;
       const int H = c.res_in;
+      const bool fuse_phases = use_tc && c.cout <= 64 && h->fuse_phases;
+      if (fuse_phases) {
+        // all four sub-pixel phases in one launch: the activation tile is loaded and modulated once, every tap
+        // accumulates into its phase's TMEM accumulator, and the epilogue writes the four planes of [B, 4, H+1, H+1, Cout]
+        TcConv q{};
+        q.in = x; q.in_planes = 1; q.in_h = q.in_w = H; q.in_bcast = x_bstride == 0; q.mod = smod; q.wmap = c.map_fwd.bytes;
+        q.out = T; q.out_planes = 4; q.out_plane = 0; q.out_h = q.out_w = H + 1;
+        q.batch = B; q.gh = q.gw = H + 1; q.K = c.cin; q.N = c.cout;
+        q.taps.ngroups = 1; q.taps.group_plane[0] = 0; q.taps.group_tap0[0] = 0; q.taps.nphase = 4;
+        int t = 0;
+        for (int a = 0; a < 2; ++a)
+          for (int bb = 0; bb < 2; ++bb)
+            for (int ky = a == 0 ? 0 : 1; ky < 3; ky += 2)
+              for (int kx = bb == 0 ? 0 : 1; kx < 3; kx += 2) {
+                q.taps.dy[t] = (signed char)(ky == 2 ? -1 : 0); q.taps.dx[t] = (signed char)(kx == 2 ? -1 : 0);
+                q.taps.widx[t] = (signed char)(ky * 3 + kx); q.taps.acc[t] = (signed char)(a * 2 + bb); ++t;
+              }
+        q.taps.group_tap0[1] = t;
+        q.epi = EPI_STORE;
+        const double fl = 2.0 * B * 9.0 * c.cin * c.cout * H * H;   // the transposed conv's own MACs
+        const double by = 4.0 * ((double)B * H * H * c.cin + (double)B * 4 * (H + 1) * (H + 1) * c.cout + 9.0 * c.cin * c.cout);
+        LFP_PROF(h, LFP_KIND_CONV_FWD, fl, by, s, launch_conv_tc(q, s));
+      } else
       for (int a = 0; a < 2; ++a)
         for (int bb = 0; bb < 2; ++bb) {
           ConvGeom g{};
@@ -481,6 +515,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
         }
       FirArgs f{};
       f.in_planar = use_tc;
+      f.kx = f.ky = h->fir + 64;
       f.batch = B; f.in_h = f.in_w = 2 * H + 1; f.out_h = f.out_w = 2 * H; f.C = c.cout; f.pad = 1; f.coef = h->fir + 0;
       f.act = true; f.demod = dmod; f.noise = noise[c.noise_idx]; f.noise_bstride = nstride; f.noise_w = c.noise_w; f.bias = c.act_bias;
       LFP_PROF(h, LFP_KIND_FIR, 0.0, 4.0 * B * c.cout * ((double)f.in_h * f.in_w + (double)f.out_h * f.out_w), s, launch_fir4x4_nhwc(T, act, f, s));
@@ -575,6 +610,7 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
       FirArgs f{};
       f.batch = B; f.in_h = f.in_w = c.res_out; f.out_h = f.out_w = c.res_out + 1; f.C = c.cout; f.pad = 2; f.coef = h->fir + 16;
       f.out_planar = use_tc;
+      f.kx = f.ky = h->fir + 68;
       // tensor-core path: T' is phase-major [B, 4, H+1, H+1, Cout]; dx(y,x) = sum T'(2y+ky, 2x+kx) W[ky,kx] reads plane
       // (ky&1, kx&1) at (y + (ky>>1), x + (kx>>1))
       tq.in_planes = 4; tq.in_h = tq.in_w = c.res_in + 1;
