@@ -161,7 +161,7 @@ __device__ __forceinline__ Work decode(const Args& a, int w) {
 
 // Persistent: CTA c processes work items c, c + gridDim.x, ...  (consecutive CTAs work on neighbouring
 // tiles at the same time, so halo rows and weight slices are L2 hits).
-template <int EPI, bool MOD, bool RES>
+template <int EPI, bool MOD, bool RES, bool E2>
 __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmX, const Args a) {
@@ -387,6 +387,231 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     float* scr = s_scr + (eset * 4 + q) * (32 * 33);
     const int rs = 4 * a.BN;                // stride between reduction kinds
     float* red = s_red + eset * (NRED * rs);
+    if constexpr (E2) {
+      // ---- BN <= 64: accumulator read with tcgen05.ld.16x256b (layout verified by tools/tmem_layout_probe.cu) ----
+      // Thread t of quarter q owns pixel column x = t >> 2 of tile rows 4q .. 4q+3 and, per 32-channel chunk, the eight
+      // channels 8k + 2(t & 3) + e (k < 4, e < 2): per-channel vectors are eight values per thread, the pixel-sums of
+      // the data-gradient epilogues are in-thread adds over four rows plus three xor-shuffles, and global traffic stays
+      // in full 32-byte sectors (four lanes x 8 bytes per pixel).
+      const int x = lane >> 2, cq = lane & 3;
+      const bool need_nz2 = EPI == EPI_ACT || EPI == EPI_DGRAD_ACT;
+      const bool has_rgb2 = EPI == EPI_DGRAD_ACT && a.e.drgb != nullptr;
+      const bool do_rgb2 = EPI == EPI_ACT && a.e.rgb_out != nullptr;
+      const float nw2 = need_nz2 ? __ldg(a.e.noise_w) : 0.f;
+      const int64_t hw = (int64_t)a.gh * a.gw;
+      struct Scal { float nz[4]; float rg[4][3]; };
+      auto fetch2 = [&](int w, Scal& o) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { o.nz[r] = 0.f; o.rg[r][0] = o.rg[r][1] = o.rg[r][2] = 0.f; }
+        if (w >= a.total_work) return;
+        const Work k = decode(a, w);
+        const int gx = k.x0 + x;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int gy = k.y0 + 4 * q + r;
+          if (gy >= a.gh || gx >= a.gw) continue;
+          const int pix = gy * a.gw + gx;
+          if (need_nz2) o.nz[r] = __ldg(a.e.noise + (int64_t)k.b * a.e.noise_bstride + pix);   // scaled at use: no dependent op here
+          if (has_rgb2) {
+            o.rg[r][0] = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 0) * hw + pix);
+            o.rg[r][1] = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 1) * hw + pix);
+            o.rg[r][2] = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 2) * hw + pix);
+          }
+        }
+      };
+      constexpr float G = kLreluGain, GS = kLreluGain * kLreluSlope, IG = 1.f / kLreluGain, IGS = 1.f / (kLreluGain * kLreluSlope);
+      const int wstep = a.nsets * gridDim.x;
+      const int nchunk = a.BN >> 5;
+      const int nphase = a.taps.nphase;
+      Scal nxt;
+      fetch2(eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work, nxt);
+      int it = eset;
+      for (int w = eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work; w < a.total_work; w += wstep, it += a.nsets) {
+        const Work wk = decode(a, w);
+        const int as = it & (a.nacc - 1);
+        const int b = wk.b, n0 = wk.n0;
+        const int gx = wk.x0 + x;
+        Scal cur = nxt;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cur.nz[r] *= nw2;
+        fetch2(w + wstep, nxt);
+        bool valid[4];
+        float* outp[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int gy = wk.y0 + 4 * q + r;
+          valid[r] = gy < a.gh && gx < a.gw;
+          outp[r] = nullptr;
+          if (a.out != nullptr && valid[r])
+            outp[r] = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
+                               (gx * a.out_stride + a.out_ox)) * a.N + n0;
+        }
+        const int sx = DG ? it % a.XS : 0;
+        // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x
+        const uint8_t* xbase = smem_al + a.xs_off + (size_t)sx * nchunk * XS_CHUNK + (32 * q + x) * 128 + (cq & 1) * 8;
+        if (DG) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
+        float rgbacc[4][3];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rgbacc[r][0] = rgbacc[r][1] = rgbacc[r][2] = 0.f;
+        mbar_wait(bar_acc_full(as), ((uint32_t)it >> acc_shift) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int ph = 0; ph < nphase; ++ph)
+          for (int c = 0; c < nchunk; ++c) {
+            uint32_t acc[2][16];   // [half][4k + 2 j2 + e]: row r = 2 half + j2
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint32_t taddr = tmem + ((uint32_t)(q * 32 + hf * 16) << 16) + (uint32_t)((as * nphase + ph) * a.BN + c * 32);
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                  : "=r"(acc[hf][0]), "=r"(acc[hf][1]), "=r"(acc[hf][2]), "=r"(acc[hf][3]), "=r"(acc[hf][4]), "=r"(acc[hf][5]),
+                    "=r"(acc[hf][6]), "=r"(acc[hf][7]), "=r"(acc[hf][8]), "=r"(acc[hf][9]), "=r"(acc[hf][10]), "=r"(acc[hf][11]),
+                    "=r"(acc[hf][12]), "=r"(acc[hf][13]), "=r"(acc[hf][14]), "=r"(acc[hf][15])
+                  : "r"(taddr));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c == nchunk - 1 && ph == nphase - 1) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              mbar_arrive(bar_acc_empty(as));
+            }
+            float* op[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) op[r] = outp[r];
+            if (EPI == EPI_STORE && nphase > 1) {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const int gy = wk.y0 + 4 * q + r;
+                op[r] = nullptr;
+                if (a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1))
+                  op[r] = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ch = c * 32 + 8 * k + 2 * cq;       // channel offset inside this CTA's BN slice
+              const int64_t bn = (int64_t)b * a.N + n0 + ch;
+              auto av = [&](int r, int e) { return __uint_as_float(acc[r >> 1][4 * k + 2 * (r & 1) + e]); };
+              if (EPI == EPI_STORE) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(av(r, 0), av(r, 1));
+              } else if (EPI == EPI_ACT) {
+                const float2 d2 = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn));
+                const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + n0 + ch));
+                float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0;
+                if (do_rgb2) {
+                  const float2 s2 = __ldg(reinterpret_cast<const float2*>(a.e.s_rgb + bn));
+                  const float2 w0 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 0 * a.N + n0 + ch));
+                  const float2 w1 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 1 * a.N + n0 + ch));
+                  const float2 w2 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 2 * a.N + n0 + ch));
+                  q0 = make_float2(s2.x * w0.x, s2.y * w0.y);
+                  q1 = make_float2(s2.x * w1.x, s2.y * w1.y);
+                  q2 = make_float2(s2.x * w2.x, s2.y * w2.y);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const float o0 = lrelu(fmaf(av(r, 0), d2.x, cur.nz[r]) + b2.x);
+                  const float o1 = lrelu(fmaf(av(r, 1), d2.y, cur.nz[r]) + b2.y);
+                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(o0, o1);
+                  if (do_rgb2) {
+                    rgbacc[r][0] = fmaf(o0, q0.x, fmaf(o1, q0.y, rgbacc[r][0]));
+                    rgbacc[r][1] = fmaf(o0, q1.x, fmaf(o1, q1.y, rgbacc[r][1]));
+                    rgbacc[r][2] = fmaf(o0, q2.x, fmaf(o1, q2.y, rgbacc[r][2]));
+                  }
+                }
+              } else {
+                const float2 m2 = __ldg(reinterpret_cast<const float2*>(a.e.mod_out + bn));
+                float2 d2 = make_float2(0.f, 0.f), b2 = d2, s2 = d2, w0 = d2, w1 = d2, w2 = d2;
+                if (EPI == EPI_DGRAD_ACT) {
+                  d2 = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn));
+                  b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + n0 + ch));
+                  if (has_rgb2) {
+                    s2 = __ldg(reinterpret_cast<const float2*>(a.e.s_rgb + bn));
+                    w0 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 0 * a.N + n0 + ch));
+                    w1 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 1 * a.N + n0 + ch));
+                    w2 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 2 * a.N + n0 + ch));
+                  }
+                }
+                float X0 = 0.f, X1 = 0.f, T0 = 0.f, T1 = 0.f, R0 = 0.f, R1 = 0.f;
+                const int j16 = (c * 8 + 2 * k + (cq >> 1));   // 16-byte quad index of this channel pair in the chunk row
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const float2 x2 = *reinterpret_cast<const float2*>(xbase + (size_t)c * XS_CHUNK + r * 8 * 128 + (((j16 & 7) ^ x) << 4));
+                  const float v0 = av(r, 0), v1 = av(r, 1);
+                  X0 = fmaf(x2.x, v0, X0);
+                  X1 = fmaf(x2.y, v1, X1);
+                  if (EPI == EPI_DGRAD) {
+                    if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(v0 * m2.x, v1 * m2.y);
+                  } else {
+                    float u0 = 0.f, u1 = 0.f;
+                    if (has_rgb2) {
+                      u0 = fmaf(cur.rg[r][2], w2.x, fmaf(cur.rg[r][1], w1.x, cur.rg[r][0] * w0.x));
+                      u1 = fmaf(cur.rg[r][2], w2.y, fmaf(cur.rg[r][1], w1.y, cur.rg[r][0] * w0.y));
+                    }
+                    const float gt0 = fmaf(u0, s2.x, v0 * m2.x), gt1 = fmaf(u1, s2.y, v1 * m2.y);
+                    const bool p0 = x2.x > 0.f, p1 = x2.y > 0.f;
+                    const float gp0 = gt0 * (p0 ? G : GS), gp1 = gt1 * (p1 ? G : GS);
+                    const float pre0 = x2.x * (p0 ? IG : IGS), pre1 = x2.y * (p1 ? IG : IGS);
+                    if (valid[r]) {
+                      T0 = fmaf(gp0, pre0 - cur.nz[r] - b2.x, T0);
+                      T1 = fmaf(gp1, pre1 - cur.nz[r] - b2.y, T1);
+                    }
+                    R0 = fmaf(x2.x, u0, R0);
+                    R1 = fmaf(x2.y, u1, R1);
+                    if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(gp0 * d2.x, gp1 * d2.y);
+                  }
+                }
+                // sum over the eight pixel columns of this quarter (lanes that share t & 3): fixed xor tree
+#define LFP_XRED(v) v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                LFP_XRED(X0) LFP_XRED(X1)
+                if (EPI == EPI_DGRAD_ACT) { LFP_XRED(T0) LFP_XRED(T1) if (has_rgb2) { LFP_XRED(R0) LFP_XRED(R1) } }
+#undef LFP_XRED
+                if (x == 0) {
+                  red[q * a.BN + ch] = X0; red[q * a.BN + ch + 1] = X1;
+                  if (EPI == EPI_DGRAD_ACT) {
+                    red[rs + q * a.BN + ch] = T0; red[rs + q * a.BN + ch + 1] = T1;
+                    if (has_rgb2) { red[2 * rs + q * a.BN + ch] = R0; red[2 * rs + q * a.BN + ch + 1] = R1; }
+                  }
+                }
+              }
+            }
+          }
+        if (DG) mbar_arrive(bar_xs_empty(sx));
+        if (do_rgb2) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              float v = rgbacc[r][o];
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              rgbacc[r][o] = v;
+            }
+          if (cq == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (valid[r]) {
+                float* ro = a.e.rgb_out + (int64_t)b * 3 * hw + (int64_t)(wk.y0 + 4 * q + r) * a.gw + gx;
+                ro[0] = rgbacc[r][0] + __ldg(a.e.rgb_bias + 0);
+                ro[hw] = rgbacc[r][1] + __ldg(a.e.rgb_bias + 1);
+                ro[2 * hw] = rgbacc[r][2] + __ldg(a.e.rgb_bias + 2);
+              }
+          }
+        }
+        if (DG) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+          for (int n = et; n < a.BN; n += 128) {
+            const int64_t o = ((int64_t)b * tiles_per + wk.tile) * a.N + n0 + n;
+            const int bnn = a.BN;
+            a.e.partial[o] = ((red[n] + red[bnn + n]) + red[2 * bnn + n]) + red[3 * bnn + n];
+            if (EPI == EPI_DGRAD_ACT) {
+              a.e.partial_T[o] = ((red[rs + n] + red[rs + bnn + n]) + red[rs + 2 * bnn + n]) + red[rs + 3 * bnn + n];
+              if (has_rgb2) a.e.partial_R[o] = ((red[2 * rs + n] + red[2 * rs + bnn + n]) + red[2 * rs + 2 * bnn + n]) + red[2 * rs + 3 * bnn + n];
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
+        }
+      }
+    } else {
     // per-pixel scalars (noise, skip-image gradient) of a work item; fetched one work item ahead so that their
     // DRAM latency is hidden behind the current tile
     const bool need_nz = EPI == EPI_ACT || EPI == EPI_DGRAD_ACT;
@@ -399,7 +624,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       const int gy = k.y0 + (m >> 3), gx = k.x0 + (m & 7);
       if (gy >= a.gh || gx >= a.gw) return;
       const int pix = gy * a.gw + gx;
-      if (need_nz) o_nz = nw * __ldg(a.e.noise + (int64_t)k.b * a.e.noise_bstride + pix);
+      if (need_nz) o_nz = __ldg(a.e.noise + (int64_t)k.b * a.e.noise_bstride + pix);   // scaled at use
       if (has_rgb) {
         const int64_t hw = (int64_t)a.gh * a.gw;
         o_r0 = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 0) * hw + pix);
@@ -420,7 +645,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       const int gy = wk.y0 + (m >> 3), gx = wk.x0 + (m & 7);
       const bool valid = gy < a.gh && gx < a.gw;
       const int pix = gy * a.gw + gx;
-      const float nz = nz_n, rg0 = rg0_n, rg1 = rg1_n, rg2 = rg2_n;
+      const float nz = nw * nz_n, rg0 = rg0_n, rg1 = rg1_n, rg2 = rg2_n;
       fetch(w + wstep, nz_n, rg0_n, rg1_n, rg2_n);
       float* outp0 = nullptr;
       if (a.out != nullptr && valid)
@@ -605,6 +830,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
       }
     }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -657,19 +883,29 @@ int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N
   return tc::encode(reinterpret_cast<CUtensorMap*>(map_out), table, 2, dims, strides, box);
 }
 
-template <int EPI, bool MOD, bool RES>
-static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+template <int EPI, bool MOD, bool RES, bool E2>
+static int tc_launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES, E2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE)));
     attr_done = true;
   }
   const int max_ctas = num_sms();
   const dim3 grid((unsigned)(a.total_work < max_ctas ? a.total_work : max_ctas));
-  tc::conv_tc_kernel<EPI, MOD, RES><<<grid, MOD ? tc::NTHREADS_MOD : tc::NTHREADS_PLAIN, dyn_smem, s>>>(tmA, tmB, tmX, a);
+  tc::conv_tc_kernel<EPI, MOD, RES, E2><<<grid, MOD ? tc::NTHREADS_MOD : tc::NTHREADS_PLAIN, dyn_smem, s>>>(tmA, tmB, tmX, a);
   LFP_LAUNCH_CHECK();
   return 0;
+}
+
+template <int EPI, bool MOD, bool RES>
+static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+  // BN <= 64: 16x256b epilogue (needs the saved-input ring for the data-gradient epilogues)
+  static const bool e2_off = getenv("LFP_TC_E2") != nullptr && atoi(getenv("LFP_TC_E2")) == 0;
+  constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
+  static const bool e2_act_off = getenv("LFP_TC_E2_ACT") != nullptr && atoi(getenv("LFP_TC_E2_ACT")) == 0;
+  const bool e2 = !e2_off && a.BN <= 64 && (!dg || a.XS > 0) && !(EPI == EPI_ACT && e2_act_off);
+  return e2 ? tc_launch3<EPI, MOD, RES, true>(tmA, tmB, tmX, a, dyn_smem, s) : tc_launch3<EPI, MOD, RES, false>(tmA, tmB, tmX, a, dyn_smem, s);
 }
 
 template <int EPI, bool MOD>
