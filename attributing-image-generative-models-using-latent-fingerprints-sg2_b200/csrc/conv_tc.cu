@@ -446,10 +446,18 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             outp[r] = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
                                (gx * a.out_stride + a.out_ox)) * a.N + n0;
         }
-        const int sx = DG ? it % a.XS : 0;
+        const bool xs_smem2 = DG && a.XS > 0;
+        const int sx = xs_smem2 ? it % a.XS : 0;
         // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x
         const uint8_t* xbase = smem_al + a.xs_off + (size_t)sx * nchunk * XS_CHUNK + (32 * q + x) * 128 + (cq & 1) * 8;
-        if (DG) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
+        if (xs_smem2) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
+        const float* xg[4];   // without the ring (BN = 128): the saved input straight from global memory
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          xg[r] = nullptr;
+          if (DG && !xs_smem2 && valid[r])
+            xg[r] = a.e.xsave + (int64_t)b * a.e.xsave_bstride + ((int64_t)(wk.y0 + 4 * q + r) * a.gw + gx) * a.N + n0;
+        }
         float rgbacc[4][3];
 #pragma unroll
         for (int r = 0; r < 4; ++r) rgbacc[r][0] = rgbacc[r][1] = rgbacc[r][2] = 0.f;
@@ -535,7 +543,9 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                 const int j16 = (c * 8 + 2 * k + (cq >> 1));   // 16-byte quad index of this channel pair in the chunk row
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                  const float2 x2 = *reinterpret_cast<const float2*>(xbase + (size_t)c * XS_CHUNK + r * 8 * 128 + (((j16 & 7) ^ x) << 4));
+                  float2 x2 = make_float2(0.f, 0.f);
+                  if (xs_smem2) x2 = *reinterpret_cast<const float2*>(xbase + (size_t)c * XS_CHUNK + r * 8 * 128 + (((j16 & 7) ^ x) << 4));
+                  else if (xg[r]) x2 = __ldg(reinterpret_cast<const float2*>(xg[r] + ch));
                   const float v0 = av(r, 0), v1 = av(r, 1);
                   X0 = fmaf(x2.x, v0, X0);
                   X1 = fmaf(x2.y, v1, X1);
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               }
             }
           }
-        if (DG) mbar_arrive(bar_xs_empty(sx));
+        if (xs_smem2) mbar_arrive(bar_xs_empty(sx));
         if (do_rgb2) {
 #pragma unroll
           for (int r = 0; r < 4; ++r)
@@ -904,7 +914,8 @@ static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   static const bool e2_off = getenv("LFP_TC_E2") != nullptr && atoi(getenv("LFP_TC_E2")) == 0;
   constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
   static const bool e2_act_off = getenv("LFP_TC_E2_ACT") != nullptr && atoi(getenv("LFP_TC_E2_ACT")) == 0;
-  const bool e2 = !e2_off && a.BN <= 64 && (!dg || a.XS > 0) && !(EPI == EPI_ACT && e2_act_off);
+  const bool e2 = !e2_off && a.BN <= 128 && !(EPI == EPI_ACT && e2_act_off);
+  (void)dg;
   return e2 ? tc_launch3<EPI, MOD, RES, true>(tmA, tmB, tmX, a, dyn_smem, s) : tc_launch3<EPI, MOD, RES, false>(tmA, tmB, tmX, a, dyn_smem, s);
 }
 

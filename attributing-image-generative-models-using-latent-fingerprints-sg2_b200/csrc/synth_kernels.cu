@@ -762,29 +762,40 @@ int launch_demod(const float* s, int64_t s_bstride, const float* wsq, float* d, 
   return 0;
 }
 
-__global__ void __launch_bounds__(128) style_grad_kernel(const float* __restrict__ r1,
+// ds[b,ci] = r1[b,ci] - s[b,ci] * sum_co (T[b,co] d[b,co]^2) wsq[co,ci]: one CTA per (32 input channels, sample);
+// warp w walks co = w, w+8, ... (coalesced 128-byte rows of wsq), the eight partial sums are added in warp order.
+__global__ void __launch_bounds__(256) style_grad_kernel(const float* __restrict__ r1,
                                                          const float* __restrict__ s, int64_t s_bstride,
                                                          const float* __restrict__ T,
                                                          const float* __restrict__ d, int64_t d_bstride,
                                                          const float* __restrict__ wsq,
                                                          float* __restrict__ ds, int cin, int cout) {
-  const int ci = blockIdx.x * 128 + threadIdx.x;
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ci = blockIdx.x * 32 + lane;
   const int b = blockIdx.y;
-  if (ci >= cin) return;
   float acc = 0.f;
-  for (int co = 0; co < cout; ++co) {
-    const float dv = __ldg(d + (int64_t)b * d_bstride + co);
-    acc = fmaf(__ldg(T + (int64_t)b * d_bstride + co) * dv * dv, __ldg(wsq + (int64_t)co * cin + ci), acc);
+  if (ci < cin)
+    for (int co = w; co < cout; co += 8) {
+      const float dv = __ldg(d + (int64_t)b * d_bstride + co);
+      acc = fmaf(__ldg(T + (int64_t)b * d_bstride + co) * dv * dv, __ldg(wsq + (int64_t)co * cin + ci), acc);
+    }
+  part[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && ci < cin) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    const int64_t i = (int64_t)b * s_bstride + ci;
+    ds[i] = r1[i] - __ldg(s + i) * t;
   }
-  const int64_t i = (int64_t)b * s_bstride + ci;
-  ds[i] = r1[i] - __ldg(s + i) * acc;
 }
 
 int launch_style_grad(const float* r1, const float* s, int64_t s_bstride, const float* T,
                       const float* d, int64_t d_bstride, const float* wsq, float* ds, int batch,
                       int cin, int cout, cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(cin, 128), (unsigned)batch);
-  style_grad_kernel<<<grid, 128, 0, st>>>(r1, s, s_bstride, T, d, d_bstride, wsq, ds, cin, cout);
+  dim3 grid((unsigned)ceil_div(cin, 32), (unsigned)batch);
+  style_grad_kernel<<<grid, 256, 0, st>>>(r1, s, s_bstride, T, d, d_bstride, wsq, ds, cin, cout);
   LFP_LAUNCH_CHECK();
   return 0;
 }
