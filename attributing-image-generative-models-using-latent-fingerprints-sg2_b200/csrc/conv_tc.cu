@@ -49,7 +49,8 @@ constexpr int SMEM_OPTIN = 232448;        // 227 KB: static + dynamic shared mem
 constexpr int STATIC_SMEM_RESERVE = 1024;
 constexpr int EPI_NRED(int epi) { return epi == EPI_DGRAD_ACT ? 3 : (epi == EPI_DGRAD ? 1 : 0); }
 // per-warp 32x33 transpose scratch + per-set [kind][quarter][BN] column sums
-constexpr int EPI_SMEM(int epi, int nsets, int bn) { return EPI_NRED(epi) == 0 ? 0 : (nsets * 4 * 32 * 33 + nsets * EPI_NRED(epi) * 4 * bn) * 4; }
+__host__ __device__ constexpr int EPI_SCR(bool e2, int nsets) { return e2 ? 0 : nsets * 4 * 32 * 33; }   // floats; the 16x256b epilogue reduces with shuffles
+constexpr int EPI_SMEM(int epi, int nsets, int bn, bool e2) { return EPI_NRED(epi) == 0 ? 0 : (EPI_SCR(e2, nsets) + nsets * EPI_NRED(epi) * 4 * bn) * 4; }
 
 struct Args {
   int batch, gh, gw, tiles_x, tiles_y, K, N, BN;
@@ -161,7 +162,7 @@ __device__ __forceinline__ Work decode(const Args& a, int w) {
 
 // Persistent: CTA c processes work items c, c + gridDim.x, ...  (consecutive CTAs work on neighbouring
 // tiles at the same time, so halo rows and weight slices are L2 hits).
-template <int EPI, bool MOD, bool RES, bool E2>
+template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
 __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmX, const Args a) {
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
   uint8_t* const smem_al = smem_raw + (smem0 - smem_u32(smem_raw));
   // data-gradient epilogues: per-warp transpose scratch (8 x 32 x 33 floats) and per-set column sums, behind the A/B rings
   float* const s_scr = reinterpret_cast<float*>(smem_al + a.epi_off);
-  float* const s_red = s_scr + a.nsets * 4 * 32 * 33;
+  float* const s_red = s_scr + EPI_SCR(E2, a.nsets);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SA = a.SA, SB = a.SB;
   const uint32_t b_slice_bytes = (uint32_t)a.BN * 128u;
@@ -395,46 +396,49 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       // in full 32-byte sectors (four lanes x 8 bytes per pixel).
       const int x = lane >> 2, cq = lane & 3;
       const bool need_nz2 = EPI == EPI_ACT || EPI == EPI_DGRAD_ACT;
-      const bool has_rgb2 = EPI == EPI_DGRAD_ACT && a.e.drgb != nullptr;
+      constexpr bool has_rgb2 = EPI == EPI_DGRAD_ACT && RGB;   // compile-time: the skip-gradient registers exist only where used
       const bool do_rgb2 = EPI == EPI_ACT && a.e.rgb_out != nullptr;
       const float nw2 = need_nz2 ? __ldg(a.e.noise_w) : 0.f;
       const int64_t hw = (int64_t)a.gh * a.gw;
-      struct Scal { float nz[4]; float rg[4][3]; };
-      auto fetch2 = [&](int w, Scal& o) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) { o.nz[r] = 0.f; o.rg[r][0] = o.rg[r][1] = o.rg[r][2] = 0.f; }
-        if (w >= a.total_work) return;
-        const Work k = decode(a, w);
-        const int gx = k.x0 + x;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int gy = k.y0 + 4 * q + r;
-          if (gy >= a.gh || gx >= a.gw) continue;
-          const int pix = gy * a.gw + gx;
-          if (need_nz2) o.nz[r] = __ldg(a.e.noise + (int64_t)k.b * a.e.noise_bstride + pix);   // scaled at use: no dependent op here
-          if (has_rgb2) {
-            o.rg[r][0] = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 0) * hw + pix);
-            o.rg[r][1] = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 1) * hw + pix);
-            o.rg[r][2] = __ldg(a.e.drgb + ((int64_t)k.b * 3 + 2) * hw + pix);
-          }
-        }
-      };
+      // per-pixel scalars of a work item (noise; skip-image gradient), fetched one work item ahead.  Plain register
+      // arrays filled by a macro: a struct handed to a lambda ended up in local memory, and the spill store then waited
+      // for the load it was meant to overlap.
+#define LFP_FETCH2(W, NZ, RG)                                                                         \
+  {                                                                                                   \
+    _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) { NZ[r_] = 0.f; RG[r_][0] = RG[r_][1] = RG[r_][2] = 0.f; } \
+    if ((W) < a.total_work) {                                                                         \
+      const Work k_ = decode(a, (W));                                                                 \
+      const int gx_ = k_.x0 + x;                                                                      \
+      _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                              \
+        const int gy_ = k_.y0 + 4 * q + r_;                                                           \
+        if (gy_ < a.gh && gx_ < a.gw) {                                                               \
+          const int pix_ = gy_ * a.gw + gx_;                                                          \
+          if (need_nz2) NZ[r_] = __ldg(a.e.noise + (int64_t)k_.b * a.e.noise_bstride + pix_);         \
+          if (has_rgb2) {                                                                             \
+            RG[r_][0] = __ldg(a.e.drgb + ((int64_t)k_.b * 3 + 0) * hw + pix_);                        \
+            RG[r_][1] = __ldg(a.e.drgb + ((int64_t)k_.b * 3 + 1) * hw + pix_);                        \
+            RG[r_][2] = __ldg(a.e.drgb + ((int64_t)k_.b * 3 + 2) * hw + pix_);                        \
+          }                                                                                           \
+        }                                                                                             \
+      }                                                                                               \
+    }                                                                                                 \
+  }
       constexpr float G = kLreluGain, GS = kLreluGain * kLreluSlope, IG = 1.f / kLreluGain, IGS = 1.f / (kLreluGain * kLreluSlope);
       const int wstep = a.nsets * gridDim.x;
       const int nchunk = a.BN >> 5;
       const int nphase = a.taps.nphase;
-      Scal nxt;
-      fetch2(eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work, nxt);
+      float nz_n[4], rg_n[4][3];
+      LFP_FETCH2(eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work, nz_n, rg_n)
       int it = eset;
       for (int w = eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work; w < a.total_work; w += wstep, it += a.nsets) {
         const Work wk = decode(a, w);
         const int as = it & (a.nacc - 1);
         const int b = wk.b, n0 = wk.n0;
         const int gx = wk.x0 + x;
-        Scal cur = nxt;
+        float cnz[4], crg[4][3];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) cur.nz[r] *= nw2;
-        fetch2(w + wstep, nxt);
+        for (int r = 0; r < 4; ++r) { cnz[r] = nw2 * nz_n[r]; crg[r][0] = rg_n[r][0]; crg[r][1] = rg_n[r][1]; crg[r][2] = rg_n[r][2]; }
+        LFP_FETCH2(w + wstep, nz_n, rg_n)
         bool valid[4];
         float* outp[4];
 #pragma unroll
@@ -517,8 +521,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                  const float o0 = lrelu(fmaf(av(r, 0), d2.x, cur.nz[r]) + b2.x);
-                  const float o1 = lrelu(fmaf(av(r, 1), d2.y, cur.nz[r]) + b2.y);
+                  const float o0 = lrelu(fmaf(av(r, 0), d2.x, cnz[r]) + b2.x);
+                  const float o1 = lrelu(fmaf(av(r, 1), d2.y, cnz[r]) + b2.y);
                   if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(o0, o1);
                   if (do_rgb2) {
                     rgbacc[r][0] = fmaf(o0, q0.x, fmaf(o1, q0.y, rgbacc[r][0]));
@@ -554,16 +558,16 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   } else {
                     float u0 = 0.f, u1 = 0.f;
                     if (has_rgb2) {
-                      u0 = fmaf(cur.rg[r][2], w2.x, fmaf(cur.rg[r][1], w1.x, cur.rg[r][0] * w0.x));
-                      u1 = fmaf(cur.rg[r][2], w2.y, fmaf(cur.rg[r][1], w1.y, cur.rg[r][0] * w0.y));
+                      u0 = fmaf(crg[r][2], w2.x, fmaf(crg[r][1], w1.x, crg[r][0] * w0.x));
+                      u1 = fmaf(crg[r][2], w2.y, fmaf(crg[r][1], w1.y, crg[r][0] * w0.y));
                     }
                     const float gt0 = fmaf(u0, s2.x, v0 * m2.x), gt1 = fmaf(u1, s2.y, v1 * m2.y);
                     const bool p0 = x2.x > 0.f, p1 = x2.y > 0.f;
                     const float gp0 = gt0 * (p0 ? G : GS), gp1 = gt1 * (p1 ? G : GS);
                     const float pre0 = x2.x * (p0 ? IG : IGS), pre1 = x2.y * (p1 ? IG : IGS);
                     if (valid[r]) {
-                      T0 = fmaf(gp0, pre0 - cur.nz[r] - b2.x, T0);
-                      T1 = fmaf(gp1, pre1 - cur.nz[r] - b2.y, T1);
+                      T0 = fmaf(gp0, pre0 - cnz[r] - b2.x, T0);
+                      T1 = fmaf(gp1, pre1 - cnz[r] - b2.y, T1);
                     }
                     R0 = fmaf(x2.x, u0, R0);
                     R1 = fmaf(x2.y, u1, R1);
@@ -893,29 +897,36 @@ int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N
   return tc::encode(reinterpret_cast<CUtensorMap*>(map_out), table, 2, dims, strides, box);
 }
 
-template <int EPI, bool MOD, bool RES, bool E2>
-static int tc_launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
+static int tc_launch4(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES, E2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES, E2, RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE)));
     attr_done = true;
   }
   const int max_ctas = num_sms();
   const dim3 grid((unsigned)(a.total_work < max_ctas ? a.total_work : max_ctas));
-  tc::conv_tc_kernel<EPI, MOD, RES, E2><<<grid, MOD ? tc::NTHREADS_MOD : tc::NTHREADS_PLAIN, dyn_smem, s>>>(tmA, tmB, tmX, a);
+  tc::conv_tc_kernel<EPI, MOD, RES, E2, RGB><<<grid, MOD ? tc::NTHREADS_MOD : tc::NTHREADS_PLAIN, dyn_smem, s>>>(tmA, tmB, tmX, a);
   LFP_LAUNCH_CHECK();
   return 0;
 }
 
+template <int EPI, bool MOD, bool RES, bool E2>
+static int tc_launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+  if (EPI == EPI_DGRAD_ACT && E2 && a.e.drgb != nullptr) return tc_launch4<EPI, MOD, RES, E2, EPI == EPI_DGRAD_ACT && E2>(tmA, tmB, tmX, a, dyn_smem, s);
+  return tc_launch4<EPI, MOD, RES, E2, false>(tmA, tmB, tmX, a, dyn_smem, s);
+}
+
+static bool tc_use_e2(int bn) {
+  // BN <= 128: 16x256b epilogue
+  static const bool e2_off = getenv("LFP_TC_E2") != nullptr && atoi(getenv("LFP_TC_E2")) == 0;
+  return !e2_off && bn <= 128;
+}
+
 template <int EPI, bool MOD, bool RES>
 static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
-  // BN <= 64: 16x256b epilogue (needs the saved-input ring for the data-gradient epilogues)
-  static const bool e2_off = getenv("LFP_TC_E2") != nullptr && atoi(getenv("LFP_TC_E2")) == 0;
-  constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
-  static const bool e2_act_off = getenv("LFP_TC_E2_ACT") != nullptr && atoi(getenv("LFP_TC_E2_ACT")) == 0;
-  const bool e2 = !e2_off && a.BN <= 128 && !(EPI == EPI_ACT && e2_act_off);
-  (void)dg;
+  const bool e2 = tc_use_e2(a.BN);
   return e2 ? tc_launch3<EPI, MOD, RES, true>(tmA, tmB, tmX, a, dyn_smem, s) : tc_launch3<EPI, MOD, RES, false>(tmA, tmB, tmX, a, dyn_smem, s);
 }
 
@@ -938,7 +949,7 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     // previous use (tile i + nsets - XS) is one it has already seen complete, i.e. nsets <= XS
     if (xs > 0 && a.nsets > xs) a.nsets = xs;
     xs_smem = (size_t)xs * (a.BN / 32) * tc::XS_CHUNK;
-    epi_smem = tc::EPI_SMEM(EPI, a.nsets, a.BN) + xs_smem;
+    epi_smem = tc::EPI_SMEM(EPI, a.nsets, a.BN, tc_use_e2(a.BN)) + xs_smem;
     const size_t budget = (size_t)tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE - 1024 - epi_smem;
     if (a.n_ntiles == 1 && b_all + 3 * (size_t)tc::A_STAGE <= budget) {
       a.b_resident = 1; a.SB = 0;
