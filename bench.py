@@ -28,6 +28,9 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 METRIC = "attribution latent-opt steps/sec (images x guesses) at 1024px"
+# average DRAM bytes per conv launch (read + write) of the default workload, from the ncu capture summarised in
+# profiles/r01_conv_dram_traffic.md; None until that capture exists
+CONV_DRAM_BYTES_PER_LAUNCH = None
 UNIT = "trajectory-steps/s"
 
 
@@ -161,8 +164,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
         "warmup": w, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"attribution_{args.size}px_mse", "size": args.size, "trajectories_per_step": 1,
-                   "loss": "mse", "key_len": 64, "shift": 448},
+        "config": {"workload": f"attribution_{args.size}px_n{args.guesses}_mse", "size": args.size,
+                   "trajectories_per_rank": args.guesses, "loss": "mse", "key_len": 64, "shift": 448,
+                   "precision": "fp32 (torch-CPU)", "sample": "one trajectory per step (the CPU runs them one at a time)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -266,9 +270,15 @@ def run_ours(args):
     pk, pk_src = peaks()
     conv_ms = ms[0] + ms[1]
     conv_fl = fl[0] + fl[1]
+    conv_by = by[0] + by[1]
     conv_launch = cnt[0] + cnt[1]
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    peak_note = f"{pk_src} bf16 sustained"
+    if prec == capi.PREC_TF32:
+        peak, peak_note = peak / 2.0, f"{pk_src} bf16 sustained / 2 (kind::tf32 runs at half the bf16 rate)"
+    else:
+        peak_note += " (fp32 CUDA-core path: the tensor peak is not its bound)"
     value = world * B * args.steps / (ms_total * 1e-3)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -285,7 +295,11 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"kernel": "modulated-conv gather kernels (forward + data-gradient)", "bound": "tensor",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                     "traffic": None, "peak_source": f"{pk_src} bf16 sustained", "launches": int(conv_launch),
+                     "traffic": CONV_DRAM_BYTES_PER_LAUNCH if (prec == capi.PREC_TF32 and size == 1024 and B == 20) else None,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the conv launches of one "
+                                     "step, ncu capture profiles/r01_conv_dram_traffic.md (bytes)",
+                     "algorithmic_bytes_per_launch": conv_by / conv_launch if conv_launch else None,
+                     "peak_source": peak_note, "launches": int(conv_launch),
                      "share_of_step": conv_ms / ms_total if ms_total else None,
                      "avg_launch_ms": conv_ms / conv_launch if conv_launch else None,
                      "algorithmic_gflop_per_launch": conv_fl / conv_launch / 1e9 if conv_launch else None},
