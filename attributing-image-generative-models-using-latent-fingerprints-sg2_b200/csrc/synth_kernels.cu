@@ -454,26 +454,37 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
   }
   float mine[3] = {0.f, 0.f, 0.f};
   const float* base = act + (int64_t)b * hw * C;
+  // groups of up to 8 pixel-iterations with all activation loads issued before the first use
+  constexpr int GRP = LPP * NCH <= 8 ? LPP : (8 / NCH >= 1 ? 8 / NCH : 1);   // <= 8 float4 in flight per lane
 #pragma unroll 1
-  for (int it = 0; it < LPP; ++it) {
-    const int pix = pix0 + it * PPW + sub;
-    float r[3] = {0.f, 0.f, 0.f};
-    if (pix < hw) {
+  for (int it0 = 0; it0 < LPP; it0 += GRP) {
+    float4 v[GRP][NCH];
+#pragma unroll
+    for (int g = 0; g < GRP; ++g) {
+      const int pix = pix0 + (it0 + g) * PPW + sub;
 #pragma unroll
       for (int q = 0; q < NCH; ++q) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + (int64_t)pix * C + (q * LPP + li) * 4));
-#pragma unroll
-        for (int o = 0; o < 3; ++o) r[o] += f4_dot(v, m[o][q]);
+        v[g][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pix < hw) v[g][q] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)pix * C + (q * LPP + li) * 4));
       }
     }
 #pragma unroll
-    for (int off = LPP / 2; off > 0; off >>= 1)
+    for (int g = 0; g < GRP; ++g) {
+      const int it = it0 + g;
+      float r[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int o = 0; o < 3; ++o) r[o] += __shfl_xor_sync(0xffffffffu, r[o], off);
+      for (int q = 0; q < NCH; ++q)
 #pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      const float v = __shfl_sync(0xffffffffu, r[o], (lane % PPW) * LPP);
-      if (lane / PPW == it) mine[o] = v;
+        for (int o = 0; o < 3; ++o) r[o] += f4_dot(v[g][q], m[o][q]);
+#pragma unroll
+      for (int off = LPP / 2; off > 0; off >>= 1)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) r[o] += __shfl_xor_sync(0xffffffffu, r[o], off);
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const float t = __shfl_sync(0xffffffffu, r[o], (lane % PPW) * LPP);
+        if (lane / PPW == it) mine[o] = t;
+      }
     }
   }
   const int pix = pix0 + lane;

@@ -20,6 +20,7 @@ import torch.distributed as dist
 
 import sharding
 from attribution import AttributionEngine
+from lfp_native import capi
 from generator import GetGen, get_noise
 
 
@@ -38,6 +39,9 @@ def parse():
     ap.add_argument("--sigma", type=float, default=1.0)
     ap.add_argument("--batch", type=int, default=0, help="trajectories per launch sequence (default: n)")
     ap.add_argument("--seed", type=int, default=1346)
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
+                    help="convolution arithmetic: tf32 = tcgen05 tensor cores (what the reference's cuDNN convs use by default), "
+                         "fp32 = CUDA-core FFMA")
     return ap.parse_args()
 
 
@@ -66,7 +70,7 @@ def main():
     noise = get_noise(opt.img_size, dev)
     plan = gen.g_ema._plan()
     eng = AttributionEngine(plan, noise, gen.pc, gen.sigma_512, gen.latent_mean, opt.key_len, opt.shift, opt.sigma,
-                            opt.sd, opt.lr)
+                            opt.sd, opt.lr, precision=capi.PREC_TF32 if opt.precision == "tf32" else capi.PREC_FP32)
     pairs = sharding.trajectory_list(opt.sample_size, opt.n)
     mine = sharding.partition(len(pairs), rank, world)
     B = opt.batch or opt.n

@@ -245,7 +245,10 @@ class Generator(nn.Module):
             self.to_rgbs.append(ToRGB(out_channel, style_dim))
             in_channel = out_channel
         self.n_latent = self.log_size * 2 - 2
-        self.precision = _capi.PREC_FP32   # convolution arithmetic of the native path
+        # convolution arithmetic of the native path: None = follow torch.backends.cudnn.allow_tf32, which is what
+        # decides it for the reference's F.conv2d / F.conv_transpose2d calls (True by default);
+        # or pin it with lfp_native.capi.PREC_FP32 / PREC_TF32
+        self.precision = None
         self._plans = {}
 
     # ---- helpers kept from the reference API (src/model.py:476-497) ---------------------------
@@ -307,5 +310,8 @@ class Generator(nn.Module):
             return latent
         plan = self._plan()
         nz = self._noise_list(noise, fixed_noise, latent.shape[0], latent.device, torch.float32)
-        image = synthesize(plan, latent, nz, self.precision)
+        prec = self.precision
+        if prec is None:
+            prec = _capi.PREC_TF32 if torch.backends.cudnn.allow_tf32 else _capi.PREC_FP32
+        image = synthesize(plan, latent, nz, prec)
         return (image, latent) if return_latents else (image, None)

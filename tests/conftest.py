@@ -12,6 +12,10 @@ for p in (ROOT, PKG, os.path.dirname(os.path.abspath(__file__))):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # fp32 parity is checked against an fp32 oracle: pin convolutions to fp32 exactly as one would for the reference
+    # (its cuDNN convs default to TF32); the tf32 tests select the tensor-core path explicitly
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
 
 
 def pytest_collection_modifyitems(config, items):

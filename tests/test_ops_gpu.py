@@ -153,3 +153,28 @@ def test_host_buffer_entry_points():
     capi.check(L.lfp_fused_bias_act_host(x.data_ptr(), b.data_ptr(), None, o2.data_ptr(), capi.F32, x.numel(),
                                          17 * 17, 3, 3, 0, 0.2, 2 ** 0.5))
     np.testing.assert_allclose(o2.numpy(), oracle.fused_leaky_relu(x, b).numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_more_than_2_pow_31_elements():
+    """64-bit indexing (the reference's kernels overflow `int` here): 2^31 + 2^20 fp16 elements through
+    fused_leaky_relu, and an upfirdn2d whose input + output exceed 2^31 elements; checked slice-wise against torch."""
+    from op import fused_leaky_relu, upfirdn2d
+    n_c, h, w = 4, 16384, 32784   # 4 * 16384 * 32784 = 2_148_532_224 > 2^31
+    x = torch.empty((1, n_c, h, w), dtype=torch.float16, device=DEV)
+    x.view(-1)[: 1 << 20].normal_()
+    x.view(-1)[1 << 20:] = x.view(-1)[: 1 << 20].repeat((x.numel() >> 20) + 1)[: x.numel() - (1 << 20)]
+    b = torch.tensor([0.5, -0.25, 0.125, 1.0], dtype=torch.float16, device=DEV)
+    y = fused_leaky_relu(x, b)
+    for c in (0, 3):
+        for rows in (slice(0, 64), slice(h - 64, h)):
+            ref = torch.nn.functional.leaky_relu(x[0, c, rows].float() + b[c].float(), 0.2) * 2 ** 0.5
+            np.testing.assert_allclose(y[0, c, rows].float().cpu().numpy(), ref.cpu().numpy(), rtol=2e-3, atol=2e-3)
+    del y
+    k = torch.tensor([[1., 3., 3., 1.]], device=DEV)
+    k = (k.t() @ k) / 64 * 4
+    xf = x[:, :2].float()     # 2 * 16384 * 32784 fp32 = 1.07e9 in, same out
+    del x
+    yf = upfirdn2d(xf, k, pad=(2, 1))
+    assert yf.shape == xf.shape
+    ref = oracle.upfirdn2d(xf[:, 1:2, h - 40:, w - 72:].cpu(), k.cpu(), pad=(2, 1))
+    np.testing.assert_allclose(yf[0, 1, h - 30:, w - 60:].cpu().numpy(), ref[0, 0, -30:, -60:].numpy(), rtol=1e-5, atol=1e-5)
