@@ -75,20 +75,28 @@ constexpr int TILE_OW = 64;
 template <int UP, int DOWN>
 struct TileGeom {
   // extent on the zero-stuffed grid covered by one output tile, then in input samples
-  static constexpr int SPAN_H = (TILE_OH - 1) * DOWN + 4;
+  static constexpr int OH = DOWN == 2 ? 16 : TILE_OH;   // output rows per tile (halved for down-2: its input tile is 4x larger)
+  static constexpr int RPT = OH / 16;                   // output rows per thread
+  static constexpr int SPAN_H = (OH - 1) * DOWN + 4;
   static constexpr int SPAN_W = (TILE_OW - 1) * DOWN + 4;
   static constexpr int IN_H = UP == 1 ? SPAN_H : SPAN_H / 2 + 1;
   static constexpr int IN_W_RAW = UP == 1 ? SPAN_W : SPAN_W / 2 + 1;
   static constexpr int IN_W = (IN_W_RAW + 3) / 4 * 4;  // 16-byte aligned rows for LDS.128
 };
 
+// One CTA owns one output tile position and walks the planes (N*C) with a register-staged pipeline: the zero-padded
+// input tile of plane p+1 is loaded (coalesced 4-byte loads - rows of 2H+1 floats rule out 16-byte alignment and TMA)
+// while plane p is filtered out of shared memory.  Per-thread source offsets, shared
+// offsets and bounds flags do not depend on the plane and are computed once.
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(256) upfirdn2d_tiled_kernel(const float* __restrict__ in,
                                                               const float* __restrict__ kernel,
                                                               float* __restrict__ out,
                                                               UpfirdnParams p) {
   using G = TileGeom<UP, DOWN>;
-  __shared__ __align__(16) float tile[G::IN_H][G::IN_W];
+  constexpr int TOT = G::IN_H * G::IN_W;
+  constexpr int NL = (TOT + 255) / 256;
+  __shared__ __align__(16) float tile[1][G::IN_H][G::IN_W];
   __shared__ float kf[4][4];  // flipped taps, zero-extended to 4x4
 
   const int tid = threadIdx.x;
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled_kernel(const float* __res
     kf[ty][tx] = v;
   }
   const int tile_ox = blockIdx.x * TILE_OW;
-  const int tile_oy = blockIdx.y * TILE_OH;
+  const int tile_oy = blockIdx.y * G::OH;
   // stuffed-grid origin of the tile and the first input sample at/after it
   const int sy0 = tile_oy * DOWN - p.pad_y0;
   const int sx0 = tile_ox * DOWN - p.pad_x0;
@@ -108,23 +116,48 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled_kernel(const float* __res
   const int64_t plane_in = (int64_t)p.in_h * p.in_w;
   const int64_t plane_out = (int64_t)p.out_h * p.out_w;
 
-  for (int64_t plane = blockIdx.z; plane < p.major; plane += gridDim.z) {
+  int goff[NL];
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int i = tid + j * 256;
+    const int r = i / G::IN_W, c = i - r * G::IN_W;
+    const int iy = iy0 + r, ix = ix0 + c;
+    const bool ok = i < TOT && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
+    goff[j] = ok ? iy * p.in_w + ix : 0;
+    okmask |= (ok ? 1u : 0u) << j;
+  }
+  // register-staged software pipeline: the next plane's tile is in flight (plain coalesced 4-byte loads: LDG issues ~4x
+  // faster than 4-byte cp.async) while the current plane is filtered out of shared memory
+  float stage[NL];
+  auto fetch = [&](int64_t plane) {
     const float* src = in + plane * plane_in;
-    __syncthreads();  // previous iteration's readers are done (also orders the kf writes)
-    for (int i = tid; i < G::IN_H * G::IN_W; i += 256) {
-      const int r = i / G::IN_W, c = i - r * G::IN_W;
-      const int iy = iy0 + r, ix = ix0 + c;
-      float v = 0.f;
-      if (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) v = __ldg(src + (int64_t)iy * p.in_w + ix);
-      tile[r][c] = v;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      stage[j] = 0.f;
+      if ((okmask >> j) & 1u) stage[j] = __ldg(src + goff[j]);
+    }
+  };
+  float* const tile_flat = &tile[0][0][0];
+
+  constexpr int RPT = G::RPT;
+  const int lx = (tid & 15) * 4;    // 4 output columns per thread
+  const int ly = (tid >> 4) * RPT;  // RPT output rows per thread
+  constexpr int buf = 0;
+  if ((int64_t)blockIdx.z < p.major) fetch(blockIdx.z);
+  for (int64_t plane = blockIdx.z; plane < p.major; plane += gridDim.z) {
+    __syncthreads();  // the previous plane's readers are done (also orders the kf writes)
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = tid + j * 256;
+      if (i < TOT) tile_flat[i] = stage[j];
     }
     __syncthreads();
-
-    const int lx = (tid & 15) * 4;  // 4 output columns per thread
-    const int ly = (tid >> 4) * 2;  // 2 output rows per thread
-    float acc[2][4] = {};
+    const int64_t next = plane + gridDim.z;
+    if (next < p.major) fetch(next);
+    float acc[RPT][4] = {};
     if (UP == 1) {
-      constexpr int WR = DOWN + 4;      // window rows:   (2-1)*DOWN + 4
+      constexpr int WR = (RPT - 1) * DOWN + 4;   // window rows
       constexpr int WC = 3 * DOWN + 4;  // window cols:   (4-1)*DOWN + 4
       constexpr int WCV = (WC + 3) / 4;
       float win[WR][WCV * 4];
@@ -132,7 +165,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled_kernel(const float* __res
       for (int r = 0; r < WR; ++r)
 #pragma unroll
         for (int v = 0; v < WCV; ++v) {
-          const float4 q = *reinterpret_cast<const float4*>(&tile[ly * DOWN + r][lx * DOWN + v * 4]);
+          const float4 q = *reinterpret_cast<const float4*>(&tile[buf][ly * DOWN + r][lx * DOWN + v * 4]);
           win[r][v * 4 + 0] = q.x; win[r][v * 4 + 1] = q.y; win[r][v * 4 + 2] = q.z; win[r][v * 4 + 3] = q.w;
         }
 #pragma unroll
@@ -141,35 +174,37 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled_kernel(const float* __res
         for (int tx = 0; tx < 4; ++tx) {
           const float k = kf[ty][tx];
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
+          for (int r = 0; r < RPT; ++r)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(win[r * DOWN + ty][c * DOWN + tx], k, acc[r][c]);
         }
     } else {
-      // UP == 2 (DOWN == 1): only taps that land on an even stuffed coordinate see a sample
+      // UP == 2 (DOWN == 1): only the taps that land on an even stuffed coordinate see a sample - two per axis, chosen
+      // by the parity of the output position (ascending tap order, as in the 16-tap form)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int r = 0; r < RPT; ++r) {
+        const int py = (sy0 + ly + r) & 1;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          const int px = (sx0 + lx + c) & 1;
           float a = 0.f;
 #pragma unroll
-          for (int ty = 0; ty < 4; ++ty) {
-            const int sy = sy0 + ly + r + ty;
-            if (sy & 1) continue;
-            const int rr = (sy >> 1) - iy0;
+          for (int jy = 0; jy < 2; ++jy) {
+            const int ty = py + 2 * jy;
+            const int rr = ((sy0 + ly + r + ty) >> 1) - iy0;
 #pragma unroll
-            for (int tx = 0; tx < 4; ++tx) {
-              const int sx = sx0 + lx + c + tx;
-              if (sx & 1) continue;
-              a = fmaf(tile[rr][(sx >> 1) - ix0], kf[ty][tx], a);
+            for (int jx = 0; jx < 2; ++jx) {
+              const int tx = px + 2 * jx;
+              a = fmaf(tile[buf][rr][((sx0 + lx + c + tx) >> 1) - ix0], kf[ty][tx], a);
             }
           }
           acc[r][c] = a;
         }
+      }
     }
     float* dst = out + plane * plane_out;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < RPT; ++r) {
       const int oy = tile_oy + ly + r;
       if (oy >= p.out_h) continue;
       const int ox = tile_ox + lx;
@@ -200,8 +235,14 @@ static int upfirdn_direct_launch(const void* in, const void* kernel, void* out, 
 template <int UP, int DOWN>
 static int upfirdn_tiled_launch(const float* in, const float* kernel, float* out, const UpfirdnParams& p,
                                 cudaStream_t s) {
-  dim3 grid((unsigned)ceil_div(p.out_w, TILE_OW), (unsigned)ceil_div(p.out_h, TILE_OH),
-            (unsigned)(p.major < 65535 ? p.major : 65535));
+  // enough CTAs for ~8 per SM; each walks several planes so that the two-stage pipeline has something to overlap
+  constexpr int OH = TileGeom<UP, DOWN>::OH;
+  const int64_t tiles = ceil_div(p.out_w, TILE_OW) * ceil_div(p.out_h, OH);
+  int64_t gz = ceil_div((int64_t)num_sms() * 8, tiles);
+  if (gz < 1) gz = 1;
+  if (gz > p.major) gz = p.major;
+  if (gz > 65535) gz = 65535;
+  dim3 grid((unsigned)ceil_div(p.out_w, TILE_OW), (unsigned)ceil_div(p.out_h, OH), (unsigned)gz);
   upfirdn2d_tiled_kernel<UP, DOWN><<<grid, 256, 0, s>>>(in, kernel, out, p);
   LFP_LAUNCH_CHECK();
   return 0;
