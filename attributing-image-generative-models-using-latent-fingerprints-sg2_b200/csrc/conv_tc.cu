@@ -899,11 +899,14 @@ int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N
 
 template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
 static int tc_launch4(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the opt-in shared-memory limit is a per-device function attribute
+  static unsigned long long attr_done_mask = 0;
+  int dev = 0;
+  LFP_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((attr_done_mask >> dev) & 1ull)) {
     LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES, E2, RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE)));
-    attr_done = true;
+    if (dev < 64) attr_done_mask |= 1ull << dev;
   }
   const int max_ctas = num_sms();
   const dim3 grid((unsigned)(a.total_work < max_ctas ? a.total_work : max_ctas));
