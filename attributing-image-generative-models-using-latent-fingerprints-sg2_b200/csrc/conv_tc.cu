@@ -17,12 +17,20 @@
 //   round-to-nearest tf32 conversion; demodulation, noise, bias and leaky-ReLU are the epilogue
 //   (src/model.py:261-263, 316, src/op/fused_act.py:110-127).
 // * Persistent CTAs (one per SM) walk the (sample, tile, n-tile) list with a stride of gridDim.x.
-//   Roles: warp 0 = TMA producer (runs ahead across tiles), warp 1 = MMA issuer (one elected thread),
-//   warps 2-5 = A transform, warps 6-9 and 10-13 = two epilogue sets that alternate tiles (TMEM ->
-//   registers -> global; warp w owns TMEM lanes 32*(w%4)..).  The accumulator has 2-4 TMEM stages, so
-//   the epilogue of tile i overlaps the MMAs of tiles i+1...  mbarrier rings: A (3-8 stages); B either streamed (4 stages) or, when the
-//   whole [taps, K, BN] weight slice fits in shared memory (the HBM-bound C <= 64 layers), loaded once
-//   and kept resident for the CTA's lifetime.
+//   Roles: warp 0 = TMA producer (runs ahead across tiles), warp 1 = MMA issuer (warp-uniform control
+//   flow, one elected lane, issue loop unrolled), warps 2-5 = A transform (a third epilogue set in the
+//   unmodulated kernels), warps 6-9 / 10-13 / 14-17 = epilogue sets that alternate tiles (TMEM ->
+//   registers -> global).  The accumulator has 2-4 TMEM stages, so the epilogue of tile i overlaps the
+//   MMAs of tiles i+1...; an epilogue set waits on mbarrier parities, which is only unambiguous while
+//   nsets <= nacc (and nsets <= XS for the saved-input ring) - see tc_launch.
+// * mbarrier rings: A (3-8 stages); B either streamed (2-4 stages) or, when the whole [taps, K, BN]
+//   weight slice fits in shared memory (the C <= 64 layers), loaded once and kept resident for the
+//   CTA's lifetime; XS = saved forward input tiles for the data-gradient epilogues (N <= 64).
+// * Epilogues: BN <= 128 read the accumulator with tcgen05.ld.16x256b (thread = 4 pixels x 8 channels,
+//   tools/tmem_layout_probe.cu), BN = 256 with 32x32b (thread = 1 pixel x 32 channels).  EPI_ACT: demod,
+//   noise, bias, lrelu (optionally the ToRGB dot product); EPI_STORE: raw, or the four sub-pixel phases
+//   of the transposed conv from four accumulators; EPI_DGRAD(_ACT): x s, style-gradient pixel sums and,
+//   fused, the backward through noise / bias / lrelu / ToRGB of the layer below.
 #include <cuda.h>
 #include <stdlib.h>
 #include <cudaTypedefs.h>
