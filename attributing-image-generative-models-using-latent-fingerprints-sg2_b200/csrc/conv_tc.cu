@@ -44,7 +44,7 @@ constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
 constexpr int A_ROWS = HALO_W * HALO_H;   // 180 rows of 128 bytes
 constexpr int A_BYTES = A_ROWS * 128;     // 23040
 constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
-constexpr int MAX_SA = 8, MAX_SB = 4;
+constexpr int MAX_SA = 8, MAX_SB = 12;
 // warp 0 TMA, warp 1 MMA, warps 2-5 transform (or a third epilogue set when there is nothing to transform),
 // warps 6-9 / 10-13 epilogue sets, warps 14-17 a third epilogue set of the modulated (forward) kernels
 constexpr int NTHREADS_MOD = 576, NTHREADS_PLAIN = 448;
@@ -966,7 +966,9 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
       a.b_resident = 1; a.SB = 0;
       a.SA = (int)((budget - b_all) / tc::A_STAGE);
     } else {
-      a.b_resident = 0; a.SB = tc::MAX_SB;
+      // enough weight slices in flight to cover the L2 latency: one slice feeds 4 MMAs of BN/2 cycles each
+      a.b_resident = 0; a.SB = a.BN >= 256 ? 4 : (a.BN >= 128 ? 8 : 12);
+      if (const char* e = getenv("LFP_TC_SB")) { const int v = atoi(e); if (v >= 2 && v <= tc::MAX_SB) a.SB = v; }
       while (a.SB > 2 && (size_t)a.SB * a.BN * 128 + 3 * (size_t)tc::A_STAGE > budget) --a.SB;
       a.SA = (int)((budget - (size_t)a.SB * a.BN * 128) / tc::A_STAGE);
     }
