@@ -501,8 +501,12 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               for (int r = 0; r < 4; ++r) {
                 const int gy = wk.y0 + 4 * q + r;
                 op[r] = nullptr;
-                if (a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1))
-                  op[r] = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
+                if (a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1)) {
+                  if (a.out_stride == 2)   // phases interleaved into the [2H+1, 2W+1] image: (2 gy + a, 2 gx + b)
+                    op[r] = a.out + (((int64_t)b * (2 * a.out_h - 1) + (2 * gy + (ph >> 1))) * (2 * a.out_w - 1) + (2 * gx + (ph & 1))) * a.N + n0;
+                  else
+                    op[r] = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
+                }
               }
             }
 #pragma unroll
@@ -736,8 +740,12 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
           float* outp = outp0;
           if (nphase > 1) {   // fused sub-pixel phases: accumulator ph -> output plane ph over its own (smaller) grid
             outp = nullptr;
-            if (a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1))
-              outp = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
+            if (a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1)) {
+              if (a.out_stride == 2)
+                outp = a.out + (((int64_t)b * (2 * a.out_h - 1) + (2 * gy + (ph >> 1))) * (2 * a.out_w - 1) + (2 * gx + (ph & 1))) * a.N + n0;
+              else
+                outp = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
+            }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j)

@@ -471,6 +471,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
         TcConv q{};
         q.in = x; q.in_planes = 1; q.in_h = q.in_w = H; q.in_bcast = x_bstride == 0; q.mod = smod; q.wmap = c.map_fwd.bytes;
         q.out = T; q.out_planes = 4; q.out_plane = 0; q.out_h = q.out_w = H + 1;
+        q.out_stride = 2;   // the four phases are written interleaved: the blur then reads an ordinary [2H+1, 2H+1] image
         q.batch = B; q.gh = q.gw = H + 1; q.K = c.cin; q.N = c.cout;
         q.taps.ngroups = 1; q.taps.group_plane[0] = 0; q.taps.group_tap0[0] = 0; q.taps.nphase = 4;
         int t = 0;
@@ -514,7 +515,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
           }
         }
       FirArgs f{};
-      f.in_planar = use_tc;
+      f.in_planar = use_tc && !fuse_phases;
       f.kx = f.ky = h->fir + 64;
       f.batch = B; f.in_h = f.in_w = 2 * H + 1; f.out_h = f.out_w = 2 * H; f.C = c.cout; f.pad = 1; f.coef = h->fir + 0;
       f.act = true; f.demod = dmod; f.noise = noise[c.noise_idx]; f.noise_bstride = nstride; f.noise_w = c.noise_w; f.bias = c.act_bias;
