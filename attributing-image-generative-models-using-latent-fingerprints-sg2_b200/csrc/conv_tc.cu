@@ -64,7 +64,7 @@ struct Args {
   int batch, gh, gw, tiles_x, tiles_y, K, N, BN;
   int n_ntiles, total_work;   // work item = (sample, tile, n-tile)
   int SA, SB, b_resident;     // A stages; B stages (streaming) or 0 with the whole weight slice resident
-  int nacc;                   // TMEM accumulator stages (2 or 4)
+  int nacc;                   // TMEM accumulator stages (1, 2 or 4)
   int epi_off;                // byte offset of the epilogue scratch in dynamic shared memory
   int XS, xs_off;             // xsave ring: stages (0 = epilogue reads xsave from global) and byte offset in dynamic smem
   int xs_bcast;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t tmem_cols = (uint32_t)(a.nacc * a.BN * a.taps.nphase);
-  const int acc_shift = a.nacc == 4 ? 2 : 1;
+  const int acc_shift = a.nacc == 4 ? 2 : (a.nacc == 2 ? 1 : 0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -957,7 +957,6 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // unambiguous when the stage's previous use (tile i + nsets - nacc) is already known to be complete, i.e.
   // nsets <= nacc (BN = 256 leaves room for two accumulator stages only)
   a.nsets = a.BN <= 128 ? 3 : 2;
-  if (const char* e = getenv("LFP_TC_NSETS")) { const int v = atoi(e); if (v == 2) a.nsets = 2; }
   constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
   // data-gradient epilogues of the HBM-bound layers (N <= 64) get their saved-input tiles through a TMA ring
   const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : 0;
@@ -983,9 +982,8 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if ((a.SA >= 3 && (a.b_resident || a.SB >= 3)) || xs <= (xs_max > 0 ? 2 : 0)) break;
   }
   if (a.SA > tc::MAX_SA) a.SA = tc::MAX_SA;
-  a.nacc = a.BN * a.taps.nphase <= 128 ? 4 : 2;
+  a.nacc = a.BN * a.taps.nphase <= 128 ? 4 : (a.BN * a.taps.nphase <= 256 ? 2 : 1);
   if (a.nsets > a.nacc) a.nsets = a.nacc;
-  if (const char* e = getenv("LFP_TC_NACC")) { const int v = atoi(e); if (v == 2 || (v == 4 && a.BN <= 128)) a.nacc = v; }
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
   // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
   a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
@@ -997,8 +995,8 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   LFP_CHECK_ARG(tc_supported(c.K, c.N, c.gh, c.gw), "conv_tc: unsupported shape K=%d N=%d grid %dx%d", c.K, c.N, c.gh, c.gw);
   LFP_CHECK_ARG(c.taps.ngroups >= 1 && c.taps.ngroups <= 4 && c.taps.group_tap0[c.taps.ngroups] <= 9, "conv_tc: bad tap table");
-  LFP_CHECK_ARG(c.taps.nphase <= 1 || (c.taps.nphase == 4 && c.epi == EPI_STORE && c.taps.ngroups == 1 && tc_block_n(c.N) * 8 <= 512),
-                "conv_tc: fused phases need EPI_STORE, one tap group and N <= 64");
+  LFP_CHECK_ARG(c.taps.nphase <= 1 || (c.taps.nphase == 4 && c.epi == EPI_STORE && c.taps.ngroups == 1 && c.N <= 128),
+                "conv_tc: fused phases need EPI_STORE, one tap group and N <= 128");
   LFP_CHECK_ARG(((uintptr_t)c.in & 15) == 0 && c.wmap != nullptr, "conv_tc: input must be 16-byte aligned");
   alignas(64) CUtensorMap tmA;
   const int nb = c.in_bcast ? 1 : c.batch;

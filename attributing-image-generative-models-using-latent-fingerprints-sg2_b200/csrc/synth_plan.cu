@@ -81,6 +81,7 @@ struct lfp_synth {
   bool finalized = false;
   int tc_min_res = 4;
   bool debug_sync = false;   // env LFP_DEBUG_SYNC=1: synchronise and log after every profiled launch
+  int fuse_phases_max_c = 128;   // env LFP_FUSE_PHASES_MAXC
   bool fuse_phases = true;   // one launch for the four sub-pixel phases of the C <= 64 transposed convs (env LFP_FUSE_PHASES=0 disables)
   bool fuse_rgb = false;     // ToRGB inside the forward conv epilogue on the tensor-core path (env LFP_FUSE_RGB=1 enables;
                              // measured slower than the separate kernel: the epilogue is the longer pole at N <= 64)
@@ -213,6 +214,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   if (blur_kernel_1d) memcpy(h->blur1d, blur_kernel_1d, 4 * sizeof(float));
   if (const char* e = getenv("LFP_DEBUG_SYNC")) h->debug_sync = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_PHASES")) h->fuse_phases = atoi(e) != 0;
+  if (const char* e = getenv("LFP_FUSE_PHASES_MAXC")) h->fuse_phases_max_c = atoi(e);
   if (const char* e = getenv("LFP_FUSE_RGB")) h->fuse_rgb = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_ACTBWD")) h->fuse_actbwd = atoi(e) != 0;
   if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 4) h->tc_min_res = v; }
@@ -464,7 +466,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
       // stride-2 transposed conv as four sub-pixel phases into [B, 2H+1, 2W+1, Cout], then blur+epilogue
       float* T = ws + L.scratchT;
       const int H = c.res_in;
-      const bool fuse_phases = use_tc && c.cout <= 64 && h->fuse_phases;
+      const bool fuse_phases = use_tc && c.cout <= h->fuse_phases_max_c && h->fuse_phases;
       if (fuse_phases) {
         // all four sub-pixel phases in one launch: the activation tile is loaded and modulated once, every tap
         // accumulates into its phase's TMEM accumulator, and the epilogue writes the four planes of [B, 4, H+1, H+1, Cout]
