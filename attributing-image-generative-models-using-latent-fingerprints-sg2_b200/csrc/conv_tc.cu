@@ -899,6 +899,16 @@ static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t
 }  // namespace tc
 
 int tc_block_n(int N) { return N >= 256 ? 256 : N; }
+// Output-channel slice of one launch: the widest slice (best MMA shape) unless that leaves SMs idle - then halve it, down
+// to 32, until there is one work item per SM (every CTA also streams 1/n of the weights, which is what the low-resolution
+// 512-channel layers and small batches are bound by).
+static int tc_pick_bn(int N, int64_t tiles_times_batch) {
+  int bn = tc_block_n(N);
+  const int sms = num_sms();
+  while (bn > 32 && tiles_times_batch * (N / bn) < sms) bn >>= 1;
+  return bn;
+}
+static int tc_bn_index(int bn) { return bn == 256 ? 0 : (bn == 128 ? 1 : (bn == 64 ? 2 : 3)); }
 int tc_tiles_per_sample(int gh, int gw) { return (int)(ceil_div(gw, tc::TILE_W) * ceil_div(gh, tc::TILE_H)); }
 bool tc_supported(int K, int N, int gh, int gw) {
   const int bn = tc_block_n(N);
@@ -906,11 +916,17 @@ bool tc_supported(int K, int N, int gh, int gw) {
   return K % 32 == 0 && K <= 512 && n_ok && gh >= 4 && gw >= 4;
 }
 
-int tc_make_weight_map(void* map_out, const float* table, int rows, int K, int N) {
+int tc_make_weight_maps(void* maps_out, const float* table, int rows, int K, int N) {
+  // four maps, box rows 256 / 128 / 64 / 32 (the ones wider than N are left unused)
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  const cuuint32_t box[2] = {32, (cuuint32_t)tc_block_n(N)};
-  return tc::encode(reinterpret_cast<CUtensorMap*>(map_out), table, 2, dims, strides, box);
+  for (int i = 0; i < 4; ++i) {
+    const int bn = 256 >> i;
+    if (bn > N || N % bn != 0) continue;
+    const cuuint32_t box[2] = {32, (cuuint32_t)bn};
+    LFP_TRY(tc::encode(reinterpret_cast<CUtensorMap*>(reinterpret_cast<unsigned char*>(maps_out) + 128 * i), table, 2, dims, strides, box));
+  }
+  return 0;
 }
 
 template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
@@ -938,9 +954,11 @@ static int tc_launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 }
 
 static bool tc_use_e2(int bn) {
-  // BN <= 128: 16x256b epilogue
+  // 16x256b epilogue for every slice width: the slice width is chosen per launch from the amount of work, and a
+  // trajectory's result must not depend on it - both epilogues add the same numbers, but in a different order
   static const bool e2_off = getenv("LFP_TC_E2") != nullptr && atoi(getenv("LFP_TC_E2")) == 0;
-  return !e2_off && bn <= 128;
+  (void)bn;
+  return !e2_off;
 }
 
 template <int EPI, bool MOD, bool RES>
@@ -1008,7 +1026,10 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   tc::Args a{};
   a.batch = c.batch; a.gh = c.gh; a.gw = c.gw;
   a.tiles_x = (int)ceil_div(c.gw, tc::TILE_W); a.tiles_y = (int)ceil_div(c.gh, tc::TILE_H);
-  a.K = c.K; a.N = c.N; a.BN = tc_block_n(c.N);
+  a.K = c.K; a.N = c.N;
+  a.BN = tc_pick_bn(c.N, (int64_t)ceil_div(c.gw, tc::TILE_W) * ceil_div(c.gh, tc::TILE_H) * c.batch);
+  if (c.taps.nphase > 1 || c.e.rgb_out != nullptr) a.BN = tc_block_n(c.N);   // fused phases / fused ToRGB keep all channels in one CTA
+  LFP_CHECK_ARG(c.e.rgb_out == nullptr || a.BN == c.N, "conv_tc: the fused ToRGB epilogue needs all %d channels in one CTA", c.N);
   a.in_bcast = c.in_bcast ? 1 : 0;
   a.taps = c.taps;
   if (a.taps.nphase <= 0) a.taps.nphase = 1;
@@ -1020,7 +1041,7 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   LFP_CHECK_ARG(total < (1ll << 31), "conv_tc: too many tiles");
   a.total_work = (int)total;
   const int ntaps = c.taps.group_tap0[c.taps.ngroups];
-  const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(c.wmap);
+  const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const unsigned char*>(c.wmap) + 128 * tc_bn_index(a.BN));
   const bool mod = c.mod != nullptr;
   if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_ACT, false>(tmA, tmB, tmA, a, ntaps, s);
   if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_STORE, false>(tmA, tmB, tmA, a, ntaps, s);

@@ -83,7 +83,7 @@ struct TcTaps {
 struct TcConv {
   const float* in; int in_planes, in_h, in_w; bool in_bcast;
   const float* mod;   // [B, K] style (forward) or null
-  const void* wmap;   // CUtensorMap of the K-major weight table [ntaps * N, K] (tc_make_weight_map)
+  const void* wmap;   // four CUtensorMaps (box rows 256/128/64/32) of the K-major weight table [ntaps * N, K] (tc_make_weight_maps)
   float* out; int out_planes, out_plane, out_h, out_w;   // out tensor [B, out_planes, out_h, out_w, N]
   int out_stride = 1, out_oy = 0, out_ox = 0;            // grid pixel (gy,gx) is written at (gy*stride+oy, gx*stride+ox)
   int batch, gh, gw, K, N;
@@ -93,7 +93,7 @@ struct TcConv {
 int launch_conv_tc(const TcConv& c, cudaStream_t s);
 bool tc_supported(int K, int N, int gh, int gw);
 int tc_tiles_per_sample(int gh, int gw);
-int tc_make_weight_map(void* map_out_128B, const float* table, int rows, int K, int N);
+int tc_make_weight_maps(void* maps_out_4x128B, const float* table, int rows, int K, int N);
 
 // 4x4 FIR on NHWC: out[b,oy,ox,c] = sum_{ty,tx} in[b, oy+ty-pad, ox+tx-pad, c] * coef[ty*4+tx]
 // optional fused epilogue (same as EPI_ACT).  coef is a device pointer to 16 floats.

@@ -33,7 +33,7 @@ static double conv_bytes(const ConvGeom& g) {
   return 4.0 * (in_px * g.K + (double)g.batch * g.gh * g.gw * g.N + (double)g.ntaps * g.K * g.N);
 }
 
-struct alignas(64) TmapBuf { unsigned char bytes[128]; };  // a CUtensorMap
+struct alignas(64) TmapBuf { unsigned char bytes[4 * 128]; };  // four CUtensorMaps (weight-slice widths 256/128/64/32)
 
 struct ConvLayer {
   std::string name;
@@ -370,8 +370,8 @@ extern "C" int lfp_synth_finalize(lfp_synth* h, void* stream) {
     LFP_TRY(launch_round_tf32(c.wg, c.wg_t, (int64_t)9 * c.cin * c.cout, s));
     c.tc_fwd = tc_supported(c.cin, c.cout, 4, 4);
     c.tc_bwd = tc_supported(c.cout, c.cin, 4, 4);
-    if (c.tc_fwd) LFP_TRY(tc_make_weight_map(c.map_fwd.bytes, c.wg_t, 9 * c.cout, c.cin, c.cout));
-    if (c.tc_bwd) LFP_TRY(tc_make_weight_map(c.map_bwd.bytes, c.wf_t, 9 * c.cin, c.cout, c.cin));
+    if (c.tc_fwd) LFP_TRY(tc_make_weight_maps(c.map_fwd.bytes, c.wg_t, 9 * c.cout, c.cin, c.cout));
+    if (c.tc_bwd) LFP_TRY(tc_make_weight_maps(c.map_bwd.bytes, c.wf_t, 9 * c.cin, c.cout, c.cin));
     LFP_TRY(launch_scale_copy(c.modw, h->A_all + (size_t)c.row0 * h->style_dim, mscale, (int64_t)c.cin * h->style_dim, s));
     LFP_TRY(launch_scale_copy(c.modb, h->b_all + c.row0, 1.f, c.cin, s));
   }
