@@ -9,9 +9,8 @@ trajectory's result is independent of what else is in its batch or on which rank
 Per step (src/main.py:58-70):
     w0 = U^T alpha + mu ; wx = w0 + sd V^T diag(sigma) sigmoid(key)      lfp_embed_forward
     est = G(wx, noise)                                                   lfp_synth_forward
-    loss = MSE(target, est) + 0.1 * alpha_bound(alpha)                   lfp_mse_loss_grad (+ bound)
-    backward to (alpha, key)                                             lfp_synth_backward, lfp_embed_backward
-    Adam(lr_i)                                                           per-element update
+    loss = MSE(target, est) + 0.1 * alpha_bound(alpha)                   lfp_mse_loss_grad, lfp_attrib_bound_loss
+    backward to (alpha, key) + Adam(lr_i)                                lfp_synth_backward, lfp_attrib_adam_update
 The perceptual (LPIPS-VGG16) loss of the reference is outside this path (SURVEY.md 8f row 1);
 ``loss="mse"`` is the reference's own alternative (src/utils.py:46-47).
 """
@@ -122,34 +121,27 @@ class AttributionEngine:
         u = u.to(self.device, torch.float32)
         return 2 * u * self.sigma_main - self.sigma_main
 
-    @staticmethod
-    def _adam(p, g, m, v, t, lr, b1=0.9, b2=0.999, eps=1e-8):
-        m.mul_(b1).add_(g, alpha=1 - b1)
-        v.mul_(b2).addcmul_(g, g, value=1 - b2)
-        denom = (v.sqrt() / math.sqrt(1 - b2 ** t)).add_(eps)
-        p.addcdiv_(m, denom, value=-(lr / (1 - b1 ** t)))
-
     def step(self, st: dict, target: torch.Tensor) -> None:
         """One Adam step of every trajectory in ``st`` (no host synchronisation)."""
         alpha, key = st["alpha"], st["key"]
         B = alpha.shape[0]
         w0, wx = self.embed(alpha, key)
         mse, d_wx, _ = self.loss_and_grad(wx, target)
-        d_alpha = torch.empty_like(alpha)
-        d_key = torch.empty_like(key)
-        capi.check(capi.lib().lfp_embed_backward(ptr(d_wx), ptr(key), ptr(self.U), ptr(self.V), ptr(self.sigma_key),
-                                                 self.sd, B, self.n_main, self.key_len, self.dim, ptr(d_alpha),
-                                                 ptr(d_key), stream_ptr(self.device)), "embed_backward")
-        over, under = alpha - self.max_alpha, self.min_alpha - alpha
-        bound = torch.relu(over).sum(1) + torch.relu(under).sum(1)          # src/utils.py:53-58
-        d_alpha += 0.1 * ((over > 0).float() - (under > 0).float())
-        st["loss"] = mse + 0.1 * bound                                      # src/main.py:65
+        L = capi.lib()
+        loss = torch.empty_like(mse)
+        capi.check(L.lfp_attrib_bound_loss(ptr(alpha), ptr(self.max_alpha), ptr(self.min_alpha), ptr(mse), B, self.n_main,
+                                           0.1, ptr(loss), stream_ptr(self.device)), "attrib_bound_loss")   # src/main.py:65
+        st["loss"] = loss
         st["w0"] = w0
         i = st["step"]
         lr = get_lr(i, self.lr0)                                            # src/main.py:67
-        if st["optimise_alpha"]:
-            self._adam(alpha, d_alpha, st["m_a"], st["v_a"], i + 1, lr)
-        self._adam(key, d_key, st["m_k"], st["v_k"], i + 1, lr)
+        t, b1, b2 = i + 1, 0.9, 0.999
+        # backward of the embed + bound sub-gradient + Adam (src/main.py:69-70) in one kernel, in place
+        capi.check(L.lfp_attrib_adam_update(ptr(d_wx), ptr(alpha), ptr(key), ptr(self.U), ptr(self.V), ptr(self.sigma_key),
+                                            ptr(self.max_alpha), ptr(self.min_alpha), self.sd, 0.1, ptr(st["m_a"]),
+                                            ptr(st["v_a"]), ptr(st["m_k"]), ptr(st["v_k"]), B, self.n_main, self.key_len,
+                                            self.dim, lr / (1 - b1 ** t), math.sqrt(1 - b2 ** t), b1, b2, 1 - b1, 1 - b2, 1e-8,
+                                            1 if st["optimise_alpha"] else 0, stream_ptr(self.device)), "attrib_adam_update")
         st["step"] = i + 1
 
     def run(self, alpha0: torch.Tensor, target: torch.Tensor, steps: int, optimise_alpha: bool = True):

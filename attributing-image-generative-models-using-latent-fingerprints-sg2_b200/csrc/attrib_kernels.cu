@@ -57,6 +57,74 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
   }
 }
 
+// loss_total[b] = mse[b] + weight * sum_i (relu(alpha - max) + relu(min - alpha))      (src/main.py:65, src/utils.py:53-58)
+// one CTA per trajectory, fixed summation order
+__global__ void __launch_bounds__(256) bound_loss_kernel(const float* __restrict__ alpha, const float* __restrict__ amax,
+                                                         const float* __restrict__ amin, const float* __restrict__ mse,
+                                                         int n_main, float weight, float* __restrict__ loss_total) {
+  __shared__ float part[8];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_main; i += 256) {
+    const float a = __ldg(alpha + (int64_t)b * n_main + i);
+    acc += fmaxf(a - __ldg(amax + i), 0.f) + fmaxf(__ldg(amin + i) - a, 0.f);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) part[w] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k];
+    loss_total[b] = __ldg(mse + b) + weight * t;
+  }
+}
+
+// Backward of the embed (as embed_bwd_kernel) + gradient of the alpha bound + one Adam step, in place
+// (src/main.py:66-70; torch.optim.Adam defaults).  One warp per (parameter element, trajectory).
+__global__ void __launch_bounds__(256) adam_update_kernel(const float* __restrict__ d_wx, float* __restrict__ alpha,
+                                                          float* __restrict__ key, const float* __restrict__ U,
+                                                          const float* __restrict__ V, const float* __restrict__ sigma,
+                                                          const float* __restrict__ amax, const float* __restrict__ amin,
+                                                          float sd, float bound_weight, float* __restrict__ m_a,
+                                                          float* __restrict__ v_a, float* __restrict__ m_k,
+                                                          float* __restrict__ v_k, int n_main, int key_len, int dim,
+                                                          float step_size, float sqrt_bc2, float beta1, float beta2,
+                                                          float omb1, float omb2, float eps, int optimise_alpha) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (row >= n_main + key_len) return;
+  if (row < n_main && !optimise_alpha) return;
+  const float* mrow = row < n_main ? U + (int64_t)row * dim : V + (int64_t)(row - n_main) * dim;
+  float acc = 0.f;
+  for (int j = lane; j < dim; j += 32) acc = fmaf(__ldg(mrow + j), __ldg(d_wx + (int64_t)b * dim + j), acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane != 0) return;
+  float g, *p, *m, *v;
+  if (row < n_main) {
+    const int64_t i = (int64_t)b * n_main + row;
+    p = alpha + i; m = m_a + i; v = v_a + i;
+    const float a = *p;
+    g = acc + bound_weight * ((a - __ldg(amax + row) > 0.f ? 1.f : 0.f) - (__ldg(amin + row) - a > 0.f ? 1.f : 0.f));
+  } else {
+    const int k = row - n_main;
+    const int64_t i = (int64_t)b * key_len + k;
+    p = key + i; m = m_k + i; v = v_k + i;
+    const float sg = sigmoidf_(*p);
+    g = sd * __ldg(sigma + k) * acc * sg * (1.f - sg);
+  }
+  // same operation order as torch.optim.Adam: m.mul_(b1).add_(g, alpha=1-b1); v.mul_(b2).addcmul_(g, g, value=1-b2);
+  // denom = v.sqrt() / sqrt(bc2) + eps; p.addcdiv_(m, denom, value=-lr/bc1)
+  const float mn = __fadd_rn(__fmul_rn(*m, beta1), __fmul_rn(omb1, g));
+  const float vn = __fadd_rn(__fmul_rn(*v, beta2), __fmul_rn(omb2, __fmul_rn(g, g)));
+  *m = mn; *v = vn;
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(vn), sqrt_bc2), eps);
+  *p = __fadd_rn(*p, __fmul_rn(-step_size, __fdiv_rn(mn, denom)));
+}
+
 // MSE: pass 1 writes d_est and per-CTA partial sums of squared error; pass 2 reduces in order
 __global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ est,
                                                           const float* __restrict__ target,
@@ -127,6 +195,32 @@ extern "C" int lfp_embed_backward(const float* d_wx, const float* key_logits, co
   LFP_CHECK_ARG(batch >= 1 && batch <= 65535, "embed_backward: bad batch");
   dim3 grid((unsigned)ceil_div(n_main + key_len, 8), (unsigned)batch);
   embed_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_wx, key_logits, U, V, sigma_key, sd, n_main, key_len, dim, d_alpha, d_key);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lfp_attrib_bound_loss(const float* alpha, const float* max_alpha, const float* min_alpha, const float* mse,
+                                     int batch, int n_main, float weight, float* loss_total, void* stream) {
+  LFP_CHECK_ARG(alpha && max_alpha && min_alpha && mse && loss_total && batch >= 1 && n_main >= 1, "attrib_bound_loss: bad argument");
+  bound_loss_kernel<<<(unsigned)batch, 256, 0, (cudaStream_t)stream>>>(alpha, max_alpha, min_alpha, mse, n_main, weight, loss_total);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int lfp_attrib_adam_update(const float* d_wx, float* alpha, float* key_logits, const float* U, const float* V,
+                                      const float* sigma_key, const float* max_alpha, const float* min_alpha, float sd,
+                                      float bound_weight, float* m_alpha, float* v_alpha, float* m_key, float* v_key,
+                                      int batch, int n_main, int key_len, int dim, float step_size, float sqrt_bc2,
+                                      float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
+                                      int optimise_alpha, void* stream) {
+  LFP_CHECK_ARG(d_wx && alpha && key_logits && U && V && sigma_key && max_alpha && min_alpha && m_alpha && v_alpha && m_key && v_key,
+                "attrib_adam_update: null argument");
+  LFP_CHECK_ARG(batch >= 1 && batch <= 65535 && n_main >= 0 && key_len >= 1 && dim >= 1, "attrib_adam_update: bad shape");
+  dim3 grid((unsigned)ceil_div(n_main + key_len, 8), (unsigned)batch);
+  adam_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_wx, alpha, key_logits, U, V, sigma_key, max_alpha, min_alpha, sd,
+                                                             bound_weight, m_alpha, v_alpha, m_key, v_key, n_main, key_len, dim,
+                                                             step_size, sqrt_bc2, beta1, beta2, one_minus_beta1, one_minus_beta2, eps,
+                                                             optimise_alpha);
   LFP_LAUNCH_CHECK();
   return 0;
 }

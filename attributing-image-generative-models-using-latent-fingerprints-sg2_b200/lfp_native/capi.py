@@ -53,6 +53,8 @@ _PROTOS = {
                                         C.POINTER(C.c_double)]),
     "lfp_embed_forward": (_i, [_vp] * 6 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_embed_backward": (_i, [_vp] * 5 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "lfp_attrib_bound_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
+    "lfp_attrib_adam_update": (_i, [_vp] * 8 + [_f, _f] + [_vp] * 4 + [_i, _i, _i, _i] + [_f] * 7 + [_i, _vp]),
     "lfp_mse_loss_grad": (_i, [_vp, _vp, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "lfp_mse_scratch_bytes": (_sz, [_i, _i64]),
 }

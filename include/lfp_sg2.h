@@ -192,6 +192,22 @@ int lfp_mse_loss_grad(const float* est, const float* target, int target_batch, i
                       size_t scratch_bytes, void* stream);
 size_t lfp_mse_scratch_bytes(int batch, int64_t numel_per);
 
+/* Step glue of the hot loop (src/main.py:65-70), batched over trajectories:
+ *   loss_total[b] = mse[b] + weight * alpha_bound(alpha[b], max_alpha, min_alpha)            (src/utils.py:53-58)
+ *   one torch.optim.Adam step (defaults beta 0.9 / 0.999, eps 1e-8) of alpha and the key logits, in place, from
+ *   d(loss)/d(wx): the embed backward (as lfp_embed_backward), the bound's sub-gradient and the Adam update in one
+ *   kernel, in torch's operation order.  step_size = lr_t / (1 - beta1^t), sqrt_bc2 = sqrt(1 - beta2^t), t = 1-based
+ *   step; one_minus_beta* are passed in (1 - 0.9 evaluated in float is not the float nearest to 0.1).
+ *   optimise_alpha = 0 freezes alpha (the key-only fixture). */
+int lfp_attrib_bound_loss(const float* alpha, const float* max_alpha, const float* min_alpha, const float* mse,
+                          int batch, int n_main, float weight, float* loss_total, void* stream);
+int lfp_attrib_adam_update(const float* d_wx, float* alpha, float* key_logits, const float* U, const float* V,
+                           const float* sigma_key, const float* max_alpha, const float* min_alpha, float sd,
+                           float bound_weight, float* m_alpha, float* v_alpha, float* m_key, float* v_key,
+                           int batch, int n_main, int key_len, int dim, float step_size, float sqrt_bc2,
+                           float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
+                           int optimise_alpha, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
