@@ -173,3 +173,34 @@ def test_fused_step_glue_matches_oracle_adam():
             oracle.adam_step(k_o[b], gk, mom[b][1][0], mom[b][1][1], t, lr)
         np.testing.assert_allclose(a_d.cpu().numpy(), torch.cat(a_o, 1).t().numpy(), rtol=0, atol=2e-5)
         np.testing.assert_allclose(k_d.cpu().numpy(), torch.cat(k_o, 1).t().numpy(), rtol=0, atol=2e-5)
+
+
+def test_config4_geometry_key_len_128():
+    """BASELINE.json configs[3]: key_len 128, sigma 1.5, shift 384 (= 512 - 128; the reference's default shift 448 cannot
+    hold 128 key axes).  Three loop steps of the engine against the oracle loop with the same geometry."""
+    from lfp_native.synthesis import SynthesisPlan
+    from attribution import AttributionEngine
+    size, seed, KL, SH, SG = 32, 17, 128, 384, 1.5
+    params = fx.make_params(size, seed)
+    noise = fx.make_noise(size, seed + 1)
+    pc, sigma, mean = fx.make_pca_basis(2)
+    sp = fx.split_basis(pc, sigma, KL, SH, SG)
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(params)
+    eng = AttributionEngine(plan, noise, pc, sigma, mean, key_len=KL, shift=SH, sigma=SG, sd=1.0, lr=0.2)
+    assert eng.n_main == 384 and eng.V.shape == (128, 512)
+    alpha_t = sp["sigma_main"] * fx.seeded((384, 1), 33)
+    key_t = (fx.seeded((KL, 1), 35) > 0).long()
+    with torch.no_grad():
+        target, _, _ = oracle.generate_with_alpha(params, size, alpha_t, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean, key_t, noise)
+    a0 = sp["sigma_main"] * fx.seeded((384, 1), 36)
+    st = eng.run(a0.t().contiguous(), target.to(DEV), steps=3)
+
+    def render(wx):
+        return oracle.generator_forward(params, [wx.reshape(1, -1)], size, input_is_latent=True, noise=noise)
+
+    l_o, a_o, k_o = oracle.attribute_one_guess(render, target, a0, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean,
+                                               sp["max_alpha"], sp["min_alpha"], steps=3, key_len=KL)
+    np.testing.assert_allclose(float(st["loss"][0]), float(l_o), rtol=1e-3)
+    np.testing.assert_allclose(st["alpha"][0].cpu().numpy(), a_o[:, 0].detach().numpy(), rtol=0, atol=5e-3)
+    np.testing.assert_allclose(st["key"][0].cpu().numpy(), k_o[:, 0].detach().numpy(), rtol=0, atol=5e-3)
