@@ -30,7 +30,7 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 METRIC = "attribution latent-opt steps/sec (images x guesses) at 1024px"
 # average DRAM bytes per conv launch (read + write) of the default workload, from the ncu capture summarised in
 # profiles/r01_conv_dram_traffic.md; None until that capture exists
-CONV_DRAM_BYTES_PER_LAUNCH = 8.953e8
+CONV_DRAM_BYTES_PER_LAUNCH = 9.346e+08
 UNIT = "trajectory-steps/s"
 
 
@@ -249,11 +249,13 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 10))
     eng.loss_and_grad_host(wx_host, target, loss_host, dwx_host)
     barrier()
-    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
     for _ in range(e2e_steps):
-        eng.loss_and_grad_host(wx_host, target, loss_host, dwx_host)
+        eng.loss_and_grad_host(wx_host, target, loss_host, dwx_host)   # H2D + fwd + bwd + D2H, synchronous
+    g1.record()
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    e2e_s = torch.tensor([g0.elapsed_time(g1) * 1e-3], device=dev)     # device clock, max over ranks below
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
 
