@@ -220,6 +220,575 @@ __global__ void __launch_bounds__(256) upfirdn2d_tiled_kernel(const float* __res
   }
 }
 
+
+// ---- warp-streaming kernels: minor == 1, fp32, kernel <= 4x4 ----------------------------------------------------------
+// One warp owns a strip of output columns and walks down the rows of a plane.  A lane loads one input column per row
+// (one coalesced 128-byte request per warp and row, no alignment requirement - rows of 2H+1 floats are fine), gets its
+// right-hand neighbours by warp shuffle, and carries the partially summed output rows in registers, so every input sample
+// is loaded once per strip and there is no shared memory and no CTA barrier.  U rows are in flight per lane (register
+// double buffer).  Taps are summed in ascending (ty, tx) order, as the 16-tap loop of the reference kernel does.
+constexpr int STREAM_U = 8;
+
+__device__ __forceinline__ void load_flipped_taps(const float* __restrict__ kernel, const UpfirdnParams& p, float (&k)[4][4]) {
+#pragma unroll
+  for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx)
+      k[ty][tx] = (ty < p.kh && tx < p.kw) ? __ldg(kernel + (p.kh - 1 - ty) * p.kw + (p.kw - 1 - tx)) : 0.f;
+}
+
+// up = down = 1: 29 output columns per warp (32 lanes minus the 3-sample halo).
+// Rows are handled in batches of U; a batch whose rows all lie inside the image (and whose outputs all exist) takes the
+// FAST instantiation, which has no per-row predicates - the kernel is otherwise bound by instruction issue, not by HBM.
+constexpr int S11_W = 29;
+#ifndef LFP_S11_MINB
+#define LFP_S11_MINB 5
+#endif
+// Two planes ride in one lane: the samples of planes (2z, 2z+1) at the same position are the halves of a 64-bit register pair
+// and every tap is one packed FFMA2 (fma.rn.f32x2), which halves the FMA issue slots per output.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// a load the compiler may not move: the streaming kernels reload a row's register right where the row was consumed, which
+// keeps U rows in flight without a second register buffer (hoisted loads would need one and spill)
+__device__ __forceinline__ float ldg_pinned(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+struct S11Ctx {
+  float k[4][4];     // flipped taps (broadcast to both halves of an FFMA2 by the instruction's scalar operand form)
+  int in_w, in_h, out_w, iy0, total;
+  int64_t in_b, out_b;  // offset of the lane's second plane (0 / unused when the pair has only one)
+  bool colok, stok, stok_b;
+};
+// rows this far below the ones being loaded are prefetched into L2: the loads then see L2 latency, and the bytes in flight
+// to DRAM no longer have to be held in registers
+constexpr int S11_PF = 24;
+template <bool FAST>
+__device__ __forceinline__ void s11_load(float (&da)[STREAM_U], float (&db)[STREAM_U], const S11Ctx& c, const float* __restrict__ col,
+                                         int jb) {
+  // col: first plane's base + row iy0 + clamped input column (32-bit row offsets from there); rows jb .. jb + U-1 of the block
+  const bool pf = false;
+#pragma unroll
+  for (int u = 0; u < STREAM_U; ++u) {
+    const int iy = c.iy0 + jb + u;
+    const float* ptr = col + (jb + u) * c.in_w;
+    if (FAST) {
+      da[u] = __ldg(ptr);
+      db[u] = __ldg(ptr + c.in_b);
+    } else {
+      const bool ok = c.colok && jb + u < c.total && iy >= 0 && iy < c.in_h;
+      da[u] = ok ? __ldg(ptr) : 0.f;
+      db[u] = ok ? __ldg(ptr + c.in_b) : 0.f;
+    }
+    if (pf) {
+      const float* pp = ptr + S11_PF * c.in_w;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + c.in_b));
+    }
+  }
+}
+template <int MODE>  // 0: every row and store predicated, 1: no predicates, 2: first batch of a block (rows 0..2 complete nothing)
+__device__ __forceinline__ void s11_rows(const float (&va)[STREAM_U], const float (&vb)[STREAM_U], const S11Ctx& c, float* __restrict__ dst,
+                                         int jb, uint64_t& a1, uint64_t& a2, uint64_t& a3) {
+  // dst: first plane's base + r0 * out_w + ox; output row of input row j is j - 3
+#pragma unroll
+  for (int u = 0; u < STREAM_U; ++u) {
+    const int j = jb + u;
+    // FAST loads keep raw values: out-of-image columns are zeroed here
+    const float xa = c.colok ? va[u] : 0.f, xb = c.colok ? vb[u] : 0.f;
+    const uint64_t v0 = pack2(xa, xb);
+    const uint64_t v1 = pack2(__shfl_down_sync(0xffffffffu, xa, 1), __shfl_down_sync(0xffffffffu, xb, 1));
+    const uint64_t v2 = pack2(__shfl_down_sync(0xffffffffu, xa, 2), __shfl_down_sync(0xffffffffu, xb, 2));
+    const uint64_t v3 = pack2(__shfl_down_sync(0xffffffffu, xa, 3), __shfl_down_sync(0xffffffffu, xb, 3));
+#define LFP_K2(ty, tx) pack2(c.k[ty][tx], c.k[ty][tx])
+    uint64_t a0 = ffma2(v0, LFP_K2(0, 0), 0ull);
+    a0 = ffma2(v1, LFP_K2(0, 1), a0); a0 = ffma2(v2, LFP_K2(0, 2), a0); a0 = ffma2(v3, LFP_K2(0, 3), a0);
+    a1 = ffma2(v0, LFP_K2(1, 0), a1); a1 = ffma2(v1, LFP_K2(1, 1), a1); a1 = ffma2(v2, LFP_K2(1, 2), a1); a1 = ffma2(v3, LFP_K2(1, 3), a1);
+    a2 = ffma2(v0, LFP_K2(2, 0), a2); a2 = ffma2(v1, LFP_K2(2, 1), a2); a2 = ffma2(v2, LFP_K2(2, 2), a2); a2 = ffma2(v3, LFP_K2(2, 3), a2);
+    a3 = ffma2(v0, LFP_K2(3, 0), a3); a3 = ffma2(v1, LFP_K2(3, 1), a3); a3 = ffma2(v2, LFP_K2(3, 2), a3); a3 = ffma2(v3, LFP_K2(3, 3), a3);
+#undef LFP_K2
+    float* ptr = dst + (j - 3) * c.out_w;
+    float ra, rb;
+    unpack2(a3, ra, rb);
+    const bool row_ok = MODE == 1 || (MODE == 2 && u >= 3) || (MODE == 0 && j >= 3 && j < c.total);
+    if (row_ok && c.stok) *ptr = ra;
+    if (row_ok && c.stok_b) ptr[c.out_b] = rb;
+    a3 = a2; a2 = a1; a1 = a0;
+  }
+}
+__global__ void __launch_bounds__(128, LFP_S11_MINB) upfirdn2d_stream11_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                                               float* __restrict__ out, UpfirdnParams p, int rh) {
+  constexpr int U = STREAM_U;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 4 + warp) * S11_W;
+  if (c0 >= p.out_w) return;
+  S11Ctx c;
+  load_flipped_taps(kernel, p, c.k);
+  const int r0 = blockIdx.y * rh;
+  const int rows = min(rh, p.out_h - r0);
+  c.total = rows + 3;  // input rows feeding this row block
+  c.in_w = p.in_w; c.in_h = p.in_h; c.out_w = p.out_w;
+  const int ix = c0 + lane - p.pad_x0;
+  c.colok = ix >= 0 && ix < p.in_w;
+  const int ixc = min(max(ix, 0), p.in_w - 1);
+  c.iy0 = r0 - p.pad_y0;
+  const int ox = c0 + lane;
+  c.stok = lane < S11_W && ox < p.out_w;
+  const int64_t plane_in = (int64_t)p.in_h * p.in_w, plane_out = (int64_t)p.out_h * p.out_w;
+  auto load_fast = [&](int jb) { return c.iy0 + jb >= 0 && c.iy0 + jb + U <= c.in_h && jb + U <= c.total; };
+  for (int64_t plane = 2 * (int64_t)blockIdx.z; plane < p.major; plane += 2 * (int64_t)gridDim.z) {
+    const bool has_b = plane + 1 < p.major;
+    c.in_b = has_b ? plane_in : 0; c.out_b = has_b ? plane_out : 0; c.stok_b = c.stok && has_b;
+    const float* col = in + plane * plane_in + (int64_t)c.iy0 * p.in_w + ixc;
+    float* dst = out + plane * plane_out + (int64_t)r0 * p.out_w + min(ox, p.out_w - 1);
+    float va[U], vb[U], na[U], nb[U];
+    uint64_t a1 = 0, a2 = 0, a3 = 0;
+    if (load_fast(0)) s11_load<true>(va, vb, c, col, 0); else s11_load<false>(va, vb, c, col, 0);
+    for (int jb = 0; jb < c.total; jb += U) {
+      if (load_fast(jb + U)) s11_load<true>(na, nb, c, col, jb + U); else s11_load<false>(na, nb, c, col, jb + U);
+      if (jb + U <= c.total) {
+        if (jb == 0) s11_rows<2>(va, vb, c, dst, jb, a1, a2, a3); else s11_rows<1>(va, vb, c, dst, jb, a1, a2, a3);
+      } else {
+        s11_rows<0>(va, vb, c, dst, jb, a1, a2, a3);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { va[u] = na[u]; vb[u] = nb[u]; }
+    }
+  }
+}
+
+// ---- row-ring kernel: up = down = 1, wide maps ---------------------------------------------------------------------------
+// The streaming kernel above holds the bytes it has in flight in registers, and at HBM latency under load (~2 us) a 4x4 FIR
+// has not enough of them to keep ~50 KB per SM in flight.  Here a producer thread streams the input rows of a 256-column
+// segment into a shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier transaction bytes): a row of 2H+1 floats
+// is not 16-byte aligned, so each copy takes the 16-byte aligned superset of the row piece and the consumers add the row's
+// skew (0..3 floats) to their shared-memory index.  Eight consumer warps walk down the rows, 32 output columns each (full,
+// aligned 128-byte stores), two planes per lane (FFMA2), partial sums in registers as in the streaming kernel.
+namespace ring {
+constexpr int CW = 256;                        // output columns per CTA
+constexpr int NCW = CW / 32;                   // consumer warps
+constexpr int G = 4;                           // input rows per ring slot (per plane)
+constexpr int D = 8;                           // ring slots
+constexpr int ROWB = ((CW + 3 + 3) * 4 + 15) / 16 * 16;  // bytes of one staged row piece (columns + halo + skew, 16-byte multiple)
+constexpr int SLOTB = G * 2 * ROWB;
+constexpr int SMEM = D * SLOTB + 2 * D * 8 + 16;
+constexpr int RB = 61;                         // output rows per CTA: RB + 3 input rows = 16 slots' worth
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+}  // namespace ring
+
+struct RingCtx {
+  float k[4][4];
+  uint32_t sbase, bars;             // ring base, barrier base (full[D], empty[D])
+  uint32_t roff[ring::G][2];        // byte offset of the lane's tap 0 inside a slot, per row of a group and plane: row r of
+                                    // every group has the same skew, since G * in_w is a multiple of 4 floats
+  int ngroups, total, jlo, jhi;     // input rows [jlo, jhi) of the band lie inside the image
+  int out_w;
+  uint32_t tokmask;                 // EDGE: bit tx set when the lane's tap tx is inside the image
+  int stok, stok_b;
+  bool any;
+};
+// One group of G input rows.  EDGE: some tap of some lane of the warp falls outside the image (per-tap predicates).
+// FULL: all G rows lie inside the image and each completes an output row of the band (no per-row predicates).
+template <bool EDGE, bool FULL>
+__device__ __forceinline__ void ring_group(const RingCtx& c, uint32_t slot_addr, int g, float*& pa, float*& pb, uint64_t& a1, uint64_t& a2,
+                                           uint64_t& a3) {
+  using namespace ring;
+#pragma unroll
+  for (int r = 0; r < G; ++r) {
+    const int j = g * G + r;
+    float xa[4], xb[4];
+    const bool rowok = FULL || (unsigned)(j - c.jlo) < (unsigned)(c.jhi - c.jlo);   // warp-uniform
+    const uint32_t ra = slot_addr + c.roff[r][0], rb = slot_addr + c.roff[r][1];
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) {
+      xa[tx] = 0.f; xb[tx] = 0.f;
+      if (rowok && (!EDGE || ((c.tokmask >> tx) & 1u))) { xa[tx] = lds(ra + tx * 4); xb[tx] = lds(rb + tx * 4); }
+    }
+    const uint64_t v0 = pack2(xa[0], xb[0]), v1 = pack2(xa[1], xb[1]), v2 = pack2(xa[2], xb[2]), v3 = pack2(xa[3], xb[3]);
+#define LFP_K2(ty, tx) pack2(c.k[ty][tx], c.k[ty][tx])
+    uint64_t a0 = ffma2(v0, LFP_K2(0, 0), 0ull);
+    a0 = ffma2(v1, LFP_K2(0, 1), a0); a0 = ffma2(v2, LFP_K2(0, 2), a0); a0 = ffma2(v3, LFP_K2(0, 3), a0);
+    a1 = ffma2(v0, LFP_K2(1, 0), a1); a1 = ffma2(v1, LFP_K2(1, 1), a1); a1 = ffma2(v2, LFP_K2(1, 2), a1); a1 = ffma2(v3, LFP_K2(1, 3), a1);
+    a2 = ffma2(v0, LFP_K2(2, 0), a2); a2 = ffma2(v1, LFP_K2(2, 1), a2); a2 = ffma2(v2, LFP_K2(2, 2), a2); a2 = ffma2(v3, LFP_K2(2, 3), a2);
+    a3 = ffma2(v0, LFP_K2(3, 0), a3); a3 = ffma2(v1, LFP_K2(3, 1), a3); a3 = ffma2(v2, LFP_K2(3, 2), a3); a3 = ffma2(v3, LFP_K2(3, 3), a3);
+#undef LFP_K2
+    float oa, ob;
+    unpack2(a3, oa, ob);
+    const bool row_st = FULL || (unsigned)(j - 3) < (unsigned)(c.total - 3);
+    if (row_st && c.stok) *pa = oa;
+    if (row_st && c.stok_b) *pb = ob;
+    pa += c.out_w; pb += c.out_w;
+    a3 = a2; a2 = a1; a1 = a0;
+  }
+}
+template <bool EDGE>
+__device__ __forceinline__ void ring_consume(const RingCtx& c, float* pa, float* pb) {
+  using namespace ring;
+  // pa / pb: output pointers of the row that input row 0 would complete (3 rows above the band), advanced by one row per input row
+  uint64_t a1 = 0, a2 = 0, a3 = 0;
+  uint32_t slot_addr = c.sbase, full_bar = c.bars, empty_bar = c.bars + D * 8, par = 0;
+  int slot = 0;
+  for (int g = 0; g < c.ngroups; ++g) {
+    if (c.any) mbar_wait(full_bar, par);
+    const int j0 = g * G;
+    if (j0 >= c.jlo && j0 + G <= c.jhi && j0 >= 3 && j0 + G <= c.total) ring_group<EDGE, true>(c, slot_addr, g, pa, pb, a1, a2, a3);
+    else ring_group<EDGE, false>(c, slot_addr, g, pa, pb, a1, a2, a3);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && c.any) mbar_arrive(empty_bar);
+    slot_addr += SLOTB; full_bar += 8; empty_bar += 8;
+    if (++slot == D) { slot = 0; slot_addr = c.sbase; full_bar = c.bars; empty_bar = c.bars + D * 8; par ^= 1u; }
+  }
+}
+
+__global__ void __launch_bounds__((ring::NCW + 1) * 32) upfirdn2d_ring11_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                                              float* __restrict__ out, UpfirdnParams p) {
+  using namespace ring;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const uint32_t sbase = smem_u32(ring_smem);
+  const uint32_t bars = sbase + D * SLOTB;  // full[D], empty[D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cx0 = blockIdx.x * CW;                         // first output column of the segment
+  const int r0 = blockIdx.y * RB;
+  const int rows = min(RB, p.out_h - r0);
+  const int total = rows + 3;                              // input rows feeding the band
+  const int ngroups = (total + G - 1) / G;
+  const int iy0 = r0 - p.pad_y0;
+  // staged input columns [cbase, cend)
+  const int cfirst = cx0 - p.pad_x0;
+  const int cbase = max(cfirst, 0), cend = min(cfirst + CW + 3, p.in_w);
+  const int ncols = cend - cbase;
+  const int64_t plane_in = (int64_t)p.in_h * p.in_w, plane_out = (int64_t)p.out_h * p.out_w;
+  const int64_t plane = 2 * (int64_t)blockIdx.z;
+  const bool has_b = plane + 1 < p.major;
+  // consumer warps that own at least one output column (the last segment of a row may be narrow); the others leave at once
+  const int nwork = min(NCW, (p.out_w - cx0 + 31) >> 5);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < D; ++i) { mbar_init(bars + i * 8, 1); mbar_init(bars + (D + i) * 8, nwork); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int jlo = max(0, -iy0), jhi = min(total, p.in_h - iy0);
+  if (warp == NCW) {
+    // ---- producer: one thread streams the rows of both planes into the ring ----
+    if (lane == 0 && ncols > 0) {
+      const float* rowa = in + plane * plane_in + (int64_t)iy0 * p.in_w + cbase;   // first staged sample of row 0
+      int ska = (int)((plane * plane_in + (int64_t)iy0 * p.in_w + cbase) & 3), skb = (int)((ska + plane_in) & 3);
+      const int iw4 = p.in_w & 3;
+      uint32_t slot_addr = sbase, full_bar = bars, empty_bar = bars + D * 8, par = 0;   // parity of the first reuse wait
+      int slot = 0;
+      for (int g = 0; g < ngroups; ++g) {
+        if (g >= D) mbar_wait(empty_bar, par);
+        // transaction bytes of the group, then the copies
+        uint32_t ba[G], bb[G], sum = 0;
+        int sa = ska, sb = skb;
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+          const int j = g * G + r;
+          const bool ok = j >= jlo && j < jhi;
+          ba[r] = ok ? (uint32_t)(((sa + ncols) * 4 + 15) & ~15) : 0u;
+          bb[r] = ok && has_b ? (uint32_t)(((sb + ncols) * 4 + 15) & ~15) : 0u;
+          sum += ba[r] + bb[r];
+          sa = (sa + iw4) & 3; sb = (sb + iw4) & 3;
+        }
+        mbar_expect_tx(full_bar, sum);
+#pragma unroll
+        for (int r = 0; r < G; ++r) {
+          const float* src = rowa + (int64_t)(g * G + r) * p.in_w;
+          if (ba[r]) bulk_g2s(slot_addr + (r * 2) * ROWB, src - ska, ba[r], full_bar);
+          if (bb[r]) bulk_g2s(slot_addr + (r * 2 + 1) * ROWB, src + plane_in - skb, bb[r], full_bar);
+          ska = (ska + iw4) & 3; skb = (skb + iw4) & 3;
+        }
+        slot_addr += SLOTB; full_bar += 8; empty_bar += 8;
+        if (++slot == D) { slot = 0; slot_addr = sbase; full_bar = bars; empty_bar = bars + D * 8; if (g >= D) par ^= 1u; }
+      }
+    }
+    return;
+  }
+  // ---- consumers ----
+  if (warp >= nwork) return;
+  RingCtx c;
+  load_flipped_taps(kernel, p, c.k);
+  const int ox = cx0 + warp * 32 + lane;
+  c.stok = ox < p.out_w; c.stok_b = c.stok && has_b;
+  // opaque to the compiler, which would otherwise recompute the flags from the thread index at every store
+  asm volatile("" : "+r"(c.stok), "+r"(c.stok_b));
+  const int ix0 = cfirst + warp * 32 + lane;               // input column of the lane's tap 0
+  c.tokmask = 0;
+#pragma unroll
+  for (int tx = 0; tx < 4; ++tx) c.tokmask |= (ix0 + tx >= 0 && ix0 + tx < p.in_w ? 1u : 0u) << tx;
+  c.sbase = sbase; c.bars = bars;
+  c.ngroups = ngroups; c.total = total; c.jlo = jlo; c.jhi = jhi; c.out_w = p.out_w; c.any = ncols > 0;
+  const int64_t ea0 = plane * plane_in + (int64_t)iy0 * p.in_w + cbase;   // element index of the first staged sample of row 0
+#pragma unroll
+  for (int r = 0; r < G; ++r) {
+    const int ska = (int)((ea0 + (int64_t)r * p.in_w) & 3), skb = (int)((ea0 + plane_in + (int64_t)r * p.in_w) & 3);
+    c.roff[r][0] = (uint32_t)((r * 2) * ROWB + (ix0 - cbase + ska) * 4);
+    c.roff[r][1] = (uint32_t)((r * 2 + 1) * ROWB + (ix0 - cbase + skb) * 4);
+  }
+  if (!c.any) { c.jlo = 0; c.jhi = 0; }
+  float* pa = out + plane * plane_out + ((int64_t)r0 - 3) * p.out_w + min(ox, p.out_w - 1);
+  float* pb = pa + (has_b ? plane_out : 0);
+  const bool wedge = __any_sync(0xffffffffu, c.tokmask != 0xfu);
+  if (wedge) ring_consume<true>(c, pa, pb); else ring_consume<false>(c, pa, pb);
+}
+
+// up = 2, down = 1: a lane owns two adjacent output columns, 60 per warp.  Only every other tap meets a sample of the
+// zero-stuffed signal: output (oy, ox) sums 2 x 2 input samples with the taps of its parity class.
+constexpr int S21_W = 60;
+struct S21Ctx {
+  float ka[2][2][2], kb[2][2][2];  // [row class f][column class e][first / second sample]; a = first contributing row, b = second
+  int in_w, in_h, out_w, iy0, total, rows, dx, dy;
+  bool colok, st0, st1, vec;
+};
+template <bool FAST>
+__device__ __forceinline__ void s21_load(float (&d)[STREAM_U], const S21Ctx& c, const float* __restrict__ col, int jb) {
+#pragma unroll
+  for (int u = 0; u < STREAM_U; ++u) {
+    const int iy = c.iy0 + jb + u;
+    const float* ptr = col + (jb + u) * c.in_w;
+    if (FAST) {
+      const float t = __ldg(ptr);
+      d[u] = c.colok ? t : 0.f;
+    } else {
+      d[u] = (c.colok && jb + u < c.total && iy >= 0 && iy < c.in_h) ? __ldg(ptr) : 0.f;
+    }
+  }
+}
+template <int MODE>  // as s11_rows
+__device__ __forceinline__ void s21_rows(const float (&v)[STREAM_U], const S21Ctx& c, float* __restrict__ dst, int jb,
+                                         float (&acc)[2][2]) {
+  // dst: plane base + r0 * out_w + ox.  Input row j completes row f of output pair t = j - (f ? dy : 0) - 1.
+#pragma unroll
+  for (int u = 0; u < STREAM_U; ++u) {
+    const int j = jb + u;
+    const float v0 = v[u];
+    const float v1 = __shfl_down_sync(0xffffffffu, v0, 1);
+    const float v2 = __shfl_down_sync(0xffffffffu, v0, 2);
+    float xa[2], xb[2];
+    xa[0] = v0; xb[0] = v1;
+    xa[1] = c.dx ? v1 : v0; xb[1] = c.dx ? v2 : v1;
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      float done[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        done[e] = fmaf(xb[e], c.kb[f][e][1], fmaf(xa[e], c.kb[f][e][0], acc[f][e]));
+        acc[f][e] = fmaf(xb[e], c.ka[f][e][1], xa[e] * c.ka[f][e][0]);
+      }
+      const int t = j - (f ? c.dy : 0) - 1;
+      const int orow = 2 * t + f;
+      float* row = dst + orow * c.out_w;
+      const bool ok = MODE == 1 || (t >= 0 && orow < c.rows && j < c.total);
+      if (c.vec) {
+        if (ok && c.st1) *reinterpret_cast<float2*>(row) = make_float2(done[0], done[1]);
+      } else {
+        if (ok && c.st0) row[0] = done[0];
+        if (ok && c.st1) row[1] = done[1];
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(128, 6) upfirdn2d_stream21_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                                 float* __restrict__ out, UpfirdnParams p, int rh) {
+  constexpr int U = STREAM_U;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 4 + warp) * S21_W;
+  if (c0 >= p.out_w) return;
+  float k[4][4];
+  load_flipped_taps(kernel, p, k);
+  S21Ctx c;
+  const int r0 = blockIdx.y * rh;
+  c.rows = min(rh, p.out_h - r0);
+  const int tp = (c.rows + 1) >> 1;  // output row pairs
+  // column classes e = 0, 1 (output column c0 + 2*lane + e) and row classes f = 0, 1 (output row r0 + 2*t + f):
+  // first contributing tap q / pr, first contributing input sample cb / rb (relative to lane / pair index)
+  int q[2], cb[2], pr[2], rb[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int bx = c0 + e - p.pad_x0;
+    q[e] = bx & 1; cb[e] = (bx + q[e]) >> 1;
+    const int by = r0 + e - p.pad_y0;
+    pr[e] = by & 1; rb[e] = (by + pr[e]) >> 1;
+  }
+  c.dx = cb[1] - cb[0]; c.dy = rb[1] - rb[0];  // 0 or 1
+#pragma unroll
+  for (int f = 0; f < 2; ++f)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        // runtime tap indices: select from the register array without dynamic indexing
+        float va = 0.f, vb = 0.f;
+#pragma unroll
+        for (int ty = 0; ty < 4; ++ty)
+#pragma unroll
+          for (int tx = 0; tx < 4; ++tx) {
+            if (ty == pr[f] && tx == q[e] + 2 * h) va = k[ty][tx];
+            if (ty == pr[f] + 2 && tx == q[e] + 2 * h) vb = k[ty][tx];
+          }
+        c.ka[f][e][h] = va; c.kb[f][e][h] = vb;
+      }
+  c.in_w = p.in_w; c.in_h = p.in_h; c.out_w = p.out_w;
+  const int ix = cb[0] + lane;
+  c.colok = ix >= 0 && ix < p.in_w;
+  const int ixc = min(max(ix, 0), p.in_w - 1);
+  c.iy0 = rb[0];
+  c.total = tp + 1 + c.dy;  // input rows feeding this row block
+  const int ox = c0 + 2 * lane;
+  const bool lane_ok = lane < S21_W / 2;
+  c.st0 = lane_ok && ox < p.out_w; c.st1 = lane_ok && ox + 1 < p.out_w;
+  c.vec = (p.out_w & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;  // c0 and ox are even
+  const int64_t plane_in = (int64_t)p.in_h * p.in_w, plane_out = (int64_t)p.out_h * p.out_w;
+  auto load_fast = [&](int jb) { return c.iy0 + jb >= 0 && c.iy0 + jb + U <= c.in_h && jb + U <= c.total; };
+  // every input row of the batch completes two existing output rows
+  auto rows_full = [&](int jb) { return jb >= 2 && jb + U <= c.total && 2 * (jb + U - 2) + 1 < c.rows; };
+  for (int64_t plane = blockIdx.z; plane < p.major; plane += gridDim.z) {
+    const float* col = in + plane * plane_in + (int64_t)c.iy0 * p.in_w + ixc;
+    float* dst = out + plane * plane_out + (int64_t)r0 * p.out_w + min(ox, p.out_w - 2 + (p.out_w & 1));
+    float v[U], nx[U];
+    float acc[2][2] = {};
+    if (load_fast(0)) s21_load<true>(v, c, col, 0); else s21_load<false>(v, c, col, 0);
+    for (int jb = 0; jb < c.total; jb += U) {
+      if (load_fast(jb + U)) s21_load<true>(nx, c, col, jb + U); else s21_load<false>(nx, c, col, jb + U);
+      if (rows_full(jb)) {
+        s21_rows<1>(v, c, dst, jb, acc);
+      } else {
+        s21_rows<0>(v, c, dst, jb, acc);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = nx[u];
+    }
+  }
+}
+
+// up = 1, down = 2: a lane owns one output column (30 per warp) and loads an aligned pair of input columns per row.
+constexpr int S12_W = 30;
+struct S12Ctx {
+  float k[4][4];
+  int in_w, in_h, out_w, iy0, total, rows, delta;
+  bool ok0, ok1, vec, stok;
+};
+template <bool FAST>
+__device__ __forceinline__ void s12_load(float2 (&d)[STREAM_U], const S12Ctx& c, const float* __restrict__ col, int jb) {
+#pragma unroll
+  for (int u = 0; u < STREAM_U; ++u) {
+    const int iy = c.iy0 + jb + u;
+    const float* ptr = col + (jb + u) * c.in_w;
+    float2 t = make_float2(0.f, 0.f);
+    if (FAST || (jb + u < c.total && iy >= 0 && iy < c.in_h)) {
+      if (c.vec) t = __ldg(reinterpret_cast<const float2*>(ptr));
+      else { if (c.ok0) t.x = __ldg(ptr); if (c.ok1) t.y = __ldg(ptr + 1); }
+    }
+    d[u] = t;
+  }
+}
+template <int MODE>  // as s11_rows
+__device__ __forceinline__ void s12_rows(const float2 (&v)[STREAM_U], const S12Ctx& c, float* __restrict__ dst, int jb, float& an,
+                                         float& ao) {
+#pragma unroll
+  for (int u = 0; u < STREAM_U; ++u) {
+    const int j = jb + u;
+    const float x0 = v[u].x, y0 = v[u].y;
+    const float x1 = __shfl_down_sync(0xffffffffu, x0, 1);
+    const float y1 = __shfl_down_sync(0xffffffffu, y0, 1);
+    const float x2 = __shfl_down_sync(0xffffffffu, x0, 2);
+    const float w0 = c.delta ? y0 : x0, w1 = c.delta ? x1 : y0, w2 = c.delta ? y1 : x1, w3 = c.delta ? x2 : y1;
+    if ((u & 1) == 0) {  // ty = 0 of the new output row, ty = 2 of the previous one
+      an = w0 * c.k[0][0]; an = fmaf(w1, c.k[0][1], an); an = fmaf(w2, c.k[0][2], an); an = fmaf(w3, c.k[0][3], an);
+      ao = fmaf(w0, c.k[2][0], ao); ao = fmaf(w1, c.k[2][1], ao); ao = fmaf(w2, c.k[2][2], ao); ao = fmaf(w3, c.k[2][3], ao);
+    } else {             // ty = 1 / ty = 3; the previous output row is complete
+      an = fmaf(w0, c.k[1][0], an); an = fmaf(w1, c.k[1][1], an); an = fmaf(w2, c.k[1][2], an); an = fmaf(w3, c.k[1][3], an);
+      ao = fmaf(w0, c.k[3][0], ao); ao = fmaf(w1, c.k[3][1], ao); ao = fmaf(w2, c.k[3][2], ao); ao = fmaf(w3, c.k[3][3], ao);
+      const int t = (j >> 1) - 1;
+      float* ptr = dst + t * c.out_w;
+      if (c.stok && (MODE == 1 || (MODE == 2 && u >= 3) || (MODE == 0 && t >= 0 && t < c.rows))) *ptr = ao;
+      ao = an;
+    }
+  }
+}
+__global__ void __launch_bounds__(128) upfirdn2d_stream12_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                                 float* __restrict__ out, UpfirdnParams p, int rh) {
+  constexpr int U = STREAM_U;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 4 + warp) * S12_W;
+  if (c0 >= p.out_w) return;
+  S12Ctx c;
+  load_flipped_taps(kernel, p, c.k);
+  const int r0 = blockIdx.y * rh;
+  c.rows = min(rh, p.out_h - r0);
+  c.total = 2 * c.rows + 2;              // input rows feeding this row block
+  const int xs = 2 * c0 - p.pad_x0;      // first input column of the warp's first output
+  const int ib = xs & ~1;                // floored to even: lanes load the pairs (ib + 2*lane, ib + 2*lane + 1)
+  c.delta = xs - ib;                     // 0 or 1
+  const int ix = ib + 2 * lane;
+  c.ok0 = ix >= 0 && ix < p.in_w; c.ok1 = ix + 1 >= 0 && ix + 1 < p.in_w;
+  // a lane whose pair straddles an image edge takes the scalar loads; its clamped pair start stays even
+  const bool even_rows = (p.in_w & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0;
+  c.vec = even_rows && c.ok0 && c.ok1;
+  const bool none = !c.ok0 && !c.ok1;
+  const int ixc = none ? 0 : ix;         // lanes with no valid column never dereference; keep their pointer in range
+  if (none) { c.vec = false; }
+  c.in_w = p.in_w; c.in_h = p.in_h; c.out_w = p.out_w;
+  c.iy0 = 2 * r0 - p.pad_y0;
+  const int ox = c0 + lane;
+  c.stok = lane < S12_W && ox < p.out_w;
+  const int64_t plane_in = (int64_t)p.in_h * p.in_w, plane_out = (int64_t)p.out_h * p.out_w;
+  auto load_fast = [&](int jb) { return c.iy0 + jb >= 0 && c.iy0 + jb + U <= c.in_h && jb + U <= c.total; };
+  for (int64_t plane = blockIdx.z; plane < p.major; plane += gridDim.z) {
+    const float* col = in + plane * plane_in + (int64_t)c.iy0 * p.in_w + ixc;
+    float* dst = out + plane * plane_out + (int64_t)r0 * p.out_w + min(ox, p.out_w - 1);
+    float2 v[U], nx[U];
+    float an = 0.f, ao = 0.f;
+    if (load_fast(0)) s12_load<true>(v, c, col, 0); else s12_load<false>(v, c, col, 0);
+    for (int jb = 0; jb < c.total; jb += U) {
+      if (load_fast(jb + U)) s12_load<true>(nx, c, col, jb + U); else s12_load<false>(nx, c, col, jb + U);
+      if (jb + U <= c.total) {
+        if (jb == 0) s12_rows<2>(v, c, dst, jb, an, ao); else s12_rows<1>(v, c, dst, jb, an, ao);
+      } else {
+        s12_rows<0>(v, c, dst, jb, an, ao);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = nx[u];
+    }
+  }
+}
+
 template <typename T>
 static int upfirdn_direct_launch(const void* in, const void* kernel, void* out, const UpfirdnParams& p,
                                  cudaStream_t s) {
@@ -248,6 +817,52 @@ static int upfirdn_tiled_launch(const float* in, const float* kernel, float* out
   return 0;
 }
 
+// rows per warp task: long enough to amortise the halo rows re-read at the top of each block, short enough that
+// there are several warps' worth of tasks per SM
+static int upfirdn_stream_launch(int up, int down, const float* in, const float* kernel, float* out, const UpfirdnParams& p,
+                                 cudaStream_t s) {
+  static const int dbg_nb = getenv("LFP_STREAM_NB") ? atoi(getenv("LFP_STREAM_NB")) : 0;
+  const int wcols = up == 2 ? S21_W : down == 2 ? S12_W : S11_W;
+  const int64_t strips = ceil_div(p.out_w, wcols);
+  const int64_t units = up == 1 && down == 1 ? (p.major + 1) / 2 : p.major;  // the 1:1 kernel pairs planes
+  const int64_t planes = units < 65535 ? units : 65535;
+  // rows per warp task (rh): the input rows feeding a block (rh + 3, rh/2 + 2, 2*rh + 2) fill whole batches of STREAM_U
+  const int halo = up == 2 ? 4 : down == 2 ? 1 : 3, unit = up == 2 ? 32 : down == 2 ? 4 : 8;
+  int nb = 128 / unit;
+  while (nb > 2 && strips * ceil_div(p.out_h, nb * unit - halo) * planes < (int64_t)num_sms() * 64) nb >>= 1;
+  if (dbg_nb) nb = dbg_nb;
+  const int rh = nb * unit - halo;
+  dim3 grid((unsigned)ceil_div(strips, 4), (unsigned)ceil_div(p.out_h, rh), (unsigned)planes);
+  if (up == 2) upfirdn2d_stream21_kernel<<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
+  else if (down == 2) upfirdn2d_stream12_kernel<<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
+  else upfirdn2d_stream11_kernel<<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int upfirdn_ring_launch(const float* in, const float* kernel, float* out, const UpfirdnParams& p, cudaStream_t s) {
+  using namespace ring;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    LFP_CUDA(cudaFuncSetAttribute(upfirdn2d_ring11_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done[dev] = true;
+  }
+  const int64_t pairs = (p.major + 1) / 2;
+  const dim3 grid0((unsigned)ceil_div(p.out_w, CW), (unsigned)ceil_div(p.out_h, RB), 1);
+  for (int64_t z0 = 0; z0 < pairs; z0 += 65534) {  // even chunks keep the chunk base 16-byte aligned
+    dim3 grid = grid0;
+    grid.z = (unsigned)(pairs - z0 < 65534 ? pairs - z0 : 65534);
+    UpfirdnParams pz = p;
+    pz.major = p.major - 2 * z0;
+    upfirdn2d_ring11_kernel<<<grid, (NCW + 1) * 32, SMEM, s>>>(in + 2 * z0 * (int64_t)p.in_h * p.in_w, kernel,
+                                                               out + 2 * z0 * (int64_t)p.out_h * p.out_w, pz);
+  }
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
 int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dtype, int64_t major,
                        int in_h, int in_w, int64_t minor, int kh, int kw, int up_x, int up_y,
                        int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
@@ -261,6 +876,17 @@ int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dty
   if (major == 0 || minor == 0 || p.out_h <= 0 || p.out_w <= 0) return 0;
   const bool small_fir = kh <= 4 && kw <= 4 && up_x == up_y && down_x == down_y;
   const bool tiny = p.out_h * (int64_t)p.out_w < 64;  // 4x4 / 8x8 maps: a tile would be mostly halo
+  static const bool use_tiled = getenv("LFP_FIR_TILED") && atoi(getenv("LFP_FIR_TILED")) != 0;
+  // the bulk copies take 16-byte aligned supersets of the rows: they stay inside the tensor when its base and its size are
+  // 16-byte multiples
+  static const bool no_ring = getenv("LFP_FIR_NO_RING") && atoi(getenv("LFP_FIR_NO_RING")) != 0;
+  if (allow_tiled && !use_tiled && !no_ring && dtype == LFP_F32 && minor == 1 && small_fir && up_x == 1 && down_x == 1 && p.out_w >= 128 &&
+      p.out_h >= 16 && (reinterpret_cast<uintptr_t>(input) & 15) == 0 && ((major * in_h * (int64_t)in_w) & 3) == 0 &&
+      (int64_t)p.out_h * p.out_w < (1ll << 31) && (int64_t)in_h * in_w < (1ll << 31))
+    return upfirdn_ring_launch((const float*)input, (const float*)kernel, (float*)out, p, s);
+  if (allow_tiled && !use_tiled && dtype == LFP_F32 && minor == 1 && small_fir && p.out_h < (1 << 30) / 2 &&
+      ((up_x == 1 && down_x == 1) || (up_x == 2 && down_x == 1) || (up_x == 1 && down_x == 2)))
+    return upfirdn_stream_launch(up_x, down_x, (const float*)input, (const float*)kernel, (float*)out, p, s);
   if (allow_tiled && dtype == LFP_F32 && minor == 1 && small_fir && !tiny) {
     if (up_x == 1 && down_x == 1) return upfirdn_tiled_launch<1, 1>((const float*)input, (const float*)kernel, (float*)out, p, s);
     if (up_x == 1 && down_x == 2) return upfirdn_tiled_launch<1, 2>((const float*)input, (const float*)kernel, (float*)out, p, s);

@@ -34,6 +34,14 @@ HOT = [  # the configurations the synthesis path hits, at sizes 
     ("down2", (2, 3, 140, 132), 1, 2, (1, 1)),
     ("blur_wide", (1, 2, 40, 300), 1, 1, (1, 1)),
     ("tiny4", (3, 4, 4, 4), 2, 1, (2, 1)),
+    # the bulk-copy row-ring kernel (wide 1:1 maps whose element count is a multiple of 4): several column segments and row
+    # bands, more row groups than ring slots, every row skew (in_w % 4), odd plane counts, crop pads
+    ("ring_odd_planes", (3, 1, 70, 300), 1, 1, (1, 1)),
+    ("ring_w517", (2, 2, 130, 517), 1, 1, (2, 2)),
+    ("ring_w258", (1, 2, 66, 258), 1, 1, (1, 1)),
+    ("ring_w259", (2, 2, 65, 259), 1, 1, (2, 1)),
+    ("ring_one_plane", (1, 1, 64, 1024), 1, 1, (1, 1)),
+    ("ring_crop", (1, 4, 96, 200), 1, 1, (-1, 4)),
 ]
 
 
