@@ -375,14 +375,12 @@ __global__ void __launch_bounds__(128, LFP_S11_MINB) upfirdn2d_stream11_kernel(c
 // skew (0..3 floats) to their shared-memory index.  Eight consumer warps walk down the rows, 32 output columns each (full,
 // aligned 128-byte stores), two planes per lane (FFMA2), partial sums in registers as in the streaming kernel.
 namespace ring {
-constexpr int CW = 256;                        // output columns per CTA
-constexpr int NCW = CW / 32;                   // consumer warps
 constexpr int G = 4;                           // input rows per ring slot (per plane)
 constexpr int D = 8;                           // ring slots
-constexpr int ROWB = ((CW + 3 + 3) * 4 + 15) / 16 * 16;  // bytes of one staged row piece (columns + halo + skew, 16-byte multiple)
-constexpr int SLOTB = G * 2 * ROWB;
-constexpr int SMEM = D * SLOTB + 2 * D * 8 + 16;
-constexpr int RB = 61;                         // output rows per CTA: RB + 3 input rows = 16 slots' worth
+// NCW consumer warps own NCW * 32 output columns; one staged row piece = columns + 3 halo + up to 3 skew floats, 16-byte multiple
+__host__ __device__ constexpr int rowb(int ncw) { return ((ncw * 32 + 3 + 3) * 4 + 15) / 16 * 16; }
+__host__ __device__ constexpr int slotb(int ncw) { return G * 2 * rowb(ncw); }
+__host__ __device__ constexpr int smem_bytes(int ncw) { return D * slotb(ncw) + 2 * D * 8 + 16; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -414,7 +412,7 @@ __device__ __forceinline__ float lds(uint32_t a) {
 
 struct RingCtx {
   float k[4][4];
-  uint32_t sbase, bars;             // ring base, barrier base (full[D], empty[D])
+  uint32_t sbase, bars, slotb;      // ring base, barrier base (full[D], empty[D]), bytes per slot
   uint32_t roff[ring::G][2];        // byte offset of the lane's tap 0 inside a slot, per row of a group and plane: row r of
                                     // every group has the same skew, since G * in_w is a multiple of 4 floats
   int ngroups, total, jlo, jhi;     // input rows [jlo, jhi) of the band lie inside the image
@@ -471,14 +469,16 @@ __device__ __forceinline__ void ring_consume(const RingCtx& c, float* pa, float*
     else ring_group<EDGE, false>(c, slot_addr, g, pa, pb, a1, a2, a3);
     __syncwarp();
     if ((threadIdx.x & 31) == 0 && c.any) mbar_arrive(empty_bar);
-    slot_addr += SLOTB; full_bar += 8; empty_bar += 8;
+    slot_addr += c.slotb; full_bar += 8; empty_bar += 8;
     if (++slot == D) { slot = 0; slot_addr = c.sbase; full_bar = c.bars; empty_bar = c.bars + D * 8; par ^= 1u; }
   }
 }
 
-__global__ void __launch_bounds__((ring::NCW + 1) * 32) upfirdn2d_ring11_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
-                                                                              float* __restrict__ out, UpfirdnParams p) {
+template <int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32) upfirdn2d_ring11_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                                        float* __restrict__ out, UpfirdnParams p, int RB) {
   using namespace ring;
+  constexpr int CW = NCW * 32, ROWB = rowb(NCW), SLOTB = slotb(NCW);
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const uint32_t sbase = smem_u32(ring_smem);
   const uint32_t bars = sbase + D * SLOTB;  // full[D], empty[D]
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__((ring::NCW + 1) * 32) upfirdn2d_ring11_kernel(
   c.tokmask = 0;
 #pragma unroll
   for (int tx = 0; tx < 4; ++tx) c.tokmask |= (ix0 + tx >= 0 && ix0 + tx < p.in_w ? 1u : 0u) << tx;
-  c.sbase = sbase; c.bars = bars;
+  c.sbase = sbase; c.bars = bars; c.slotb = SLOTB;
   c.ngroups = ngroups; c.total = total; c.jlo = jlo; c.jhi = jhi; c.out_w = p.out_w; c.any = ncols > 0;
   const int64_t ea0 = plane * plane_in + (int64_t)iy0 * p.in_w + cbase;   // element index of the first staged sample of row 0
 #pragma unroll
@@ -574,7 +574,7 @@ constexpr int S21_W = 60;
 struct S21Ctx {
   float ka[2][2][2], kb[2][2][2];  // [row class f][column class e][first / second sample]; a = first contributing row, b = second
   int in_w, in_h, out_w, iy0, total, rows, dx, dy;
-  bool colok, st0, st1, vec;
+  int colok, st0, st1;
 };
 template <bool FAST>
 __device__ __forceinline__ void s21_load(float (&d)[STREAM_U], const S21Ctx& c, const float* __restrict__ col, int jb) {
@@ -582,22 +582,19 @@ __device__ __forceinline__ void s21_load(float (&d)[STREAM_U], const S21Ctx& c, 
   for (int u = 0; u < STREAM_U; ++u) {
     const int iy = c.iy0 + jb + u;
     const float* ptr = col + (jb + u) * c.in_w;
-    if (FAST) {
-      const float t = __ldg(ptr);
-      d[u] = c.colok ? t : 0.f;
-    } else {
-      d[u] = (c.colok && jb + u < c.total && iy >= 0 && iy < c.in_h) ? __ldg(ptr) : 0.f;
-    }
+    if (FAST) d[u] = __ldg(ptr);   // out-of-image columns are zeroed where the row is consumed
+    else d[u] = (c.colok && jb + u < c.total && iy >= 0 && iy < c.in_h) ? __ldg(ptr) : 0.f;
   }
 }
-template <int MODE>  // as s11_rows
-__device__ __forceinline__ void s21_rows(const float (&v)[STREAM_U], const S21Ctx& c, float* __restrict__ dst, int jb,
-                                         float (&acc)[2][2]) {
-  // dst: plane base + r0 * out_w + ox.  Input row j completes row f of output pair t = j - (f ? dy : 0) - 1.
+// FULL: every input row of the batch completes two existing output rows (no row predicates).  VEC: float2 stores.
+template <bool FULL, bool VEC>
+__device__ __forceinline__ void s21_rows(const float (&v)[STREAM_U], const S21Ctx& c, float* (&prow)[2], int jb, float (&acc)[2][2]) {
+  // prow[f]: output row (of class f) completed by the batch's first input row, at the lane's column pair; input row j
+  // completes row f of output pair t = j - (f ? dy : 0) - 1
 #pragma unroll
   for (int u = 0; u < STREAM_U; ++u) {
     const int j = jb + u;
-    const float v0 = v[u];
+    const float v0 = c.colok ? v[u] : 0.f;
     const float v1 = __shfl_down_sync(0xffffffffu, v0, 1);
     const float v2 = __shfl_down_sync(0xffffffffu, v0, 2);
     float xa[2], xb[2];
@@ -611,27 +608,28 @@ __device__ __forceinline__ void s21_rows(const float (&v)[STREAM_U], const S21Ct
         done[e] = fmaf(xb[e], c.kb[f][e][1], fmaf(xa[e], c.kb[f][e][0], acc[f][e]));
         acc[f][e] = fmaf(xb[e], c.ka[f][e][1], xa[e] * c.ka[f][e][0]);
       }
-      const int t = j - (f ? c.dy : 0) - 1;
-      const int orow = 2 * t + f;
-      float* row = dst + orow * c.out_w;
-      const bool ok = MODE == 1 || (t >= 0 && orow < c.rows && j < c.total);
-      if (c.vec) {
-        if (ok && c.st1) *reinterpret_cast<float2*>(row) = make_float2(done[0], done[1]);
-      } else {
-        if (ok && c.st0) row[0] = done[0];
-        if (ok && c.st1) row[1] = done[1];
+      bool ok = true;
+      if (!FULL) {
+        const int t = j - (f ? c.dy : 0) - 1;
+        ok = t >= 0 && 2 * t + f < c.rows && j < c.total;
       }
+      if (VEC) {
+        if (ok && c.st1) *reinterpret_cast<float2*>(prow[f]) = make_float2(done[0], done[1]);
+      } else {
+        if (ok && c.st0) prow[f][0] = done[0];
+        if (ok && c.st1) prow[f][1] = done[1];
+      }
+      prow[f] += 2 * c.out_w;
     }
   }
 }
-__global__ void __launch_bounds__(128, 6) upfirdn2d_stream21_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
-                                                                 float* __restrict__ out, UpfirdnParams p, int rh) {
+template <bool VEC>
+__global__ void __launch_bounds__(128, 5) upfirdn2d_stream21_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                                    float* __restrict__ out, UpfirdnParams p, int rh) {
   constexpr int U = STREAM_U;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = (blockIdx.x * 4 + warp) * S21_W;
   if (c0 >= p.out_w) return;
-  float k[4][4];
-  load_flipped_taps(kernel, p, k);
   S21Ctx c;
   const int r0 = blockIdx.y * rh;
   c.rows = min(rh, p.out_h - r0);
@@ -647,22 +645,15 @@ __global__ void __launch_bounds__(128, 6) upfirdn2d_stream21_kernel(const float*
     pr[e] = by & 1; rb[e] = (by + pr[e]) >> 1;
   }
   c.dx = cb[1] - cb[0]; c.dy = rb[1] - rb[0];  // 0 or 1
+  auto tap = [&](int ty, int tx) { return (ty < p.kh && tx < p.kw) ? __ldg(kernel + (p.kh - 1 - ty) * p.kw + (p.kw - 1 - tx)) : 0.f; };
 #pragma unroll
   for (int f = 0; f < 2; ++f)
 #pragma unroll
     for (int e = 0; e < 2; ++e)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        // runtime tap indices: select from the register array without dynamic indexing
-        float va = 0.f, vb = 0.f;
-#pragma unroll
-        for (int ty = 0; ty < 4; ++ty)
-#pragma unroll
-          for (int tx = 0; tx < 4; ++tx) {
-            if (ty == pr[f] && tx == q[e] + 2 * h) va = k[ty][tx];
-            if (ty == pr[f] + 2 && tx == q[e] + 2 * h) vb = k[ty][tx];
-          }
-        c.ka[f][e][h] = va; c.kb[f][e][h] = vb;
+        c.ka[f][e][h] = tap(pr[f], q[e] + 2 * h);
+        c.kb[f][e][h] = tap(pr[f] + 2, q[e] + 2 * h);
       }
   c.in_w = p.in_w; c.in_h = p.in_h; c.out_w = p.out_w;
   const int ix = cb[0] + lane;
@@ -673,24 +664,20 @@ __global__ void __launch_bounds__(128, 6) upfirdn2d_stream21_kernel(const float*
   const int ox = c0 + 2 * lane;
   const bool lane_ok = lane < S21_W / 2;
   c.st0 = lane_ok && ox < p.out_w; c.st1 = lane_ok && ox + 1 < p.out_w;
-  c.vec = (p.out_w & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0;  // c0 and ox are even
+  asm volatile("" : "+r"(c.colok), "+r"(c.st0), "+r"(c.st1));   // keep the lane flags in registers
   const int64_t plane_in = (int64_t)p.in_h * p.in_w, plane_out = (int64_t)p.out_h * p.out_w;
   auto load_fast = [&](int jb) { return c.iy0 + jb >= 0 && c.iy0 + jb + U <= c.in_h && jb + U <= c.total; };
-  // every input row of the batch completes two existing output rows
   auto rows_full = [&](int jb) { return jb >= 2 && jb + U <= c.total && 2 * (jb + U - 2) + 1 < c.rows; };
   for (int64_t plane = blockIdx.z; plane < p.major; plane += gridDim.z) {
     const float* col = in + plane * plane_in + (int64_t)c.iy0 * p.in_w + ixc;
     float* dst = out + plane * plane_out + (int64_t)r0 * p.out_w + min(ox, p.out_w - 2 + (p.out_w & 1));
+    float* prow[2] = {dst - 2 * p.out_w, dst + (1 - 2 * (c.dy + 1)) * p.out_w};   // rows 2*(0 - d_f - 1) + f of the band
     float v[U], nx[U];
     float acc[2][2] = {};
     if (load_fast(0)) s21_load<true>(v, c, col, 0); else s21_load<false>(v, c, col, 0);
     for (int jb = 0; jb < c.total; jb += U) {
       if (load_fast(jb + U)) s21_load<true>(nx, c, col, jb + U); else s21_load<false>(nx, c, col, jb + U);
-      if (rows_full(jb)) {
-        s21_rows<1>(v, c, dst, jb, acc);
-      } else {
-        s21_rows<0>(v, c, dst, jb, acc);
-      }
+      if (rows_full(jb)) s21_rows<true, VEC>(v, c, prow, jb, acc); else s21_rows<false, VEC>(v, c, prow, jb, acc);
 #pragma unroll
       for (int u = 0; u < U; ++u) v[u] = nx[u];
     }
@@ -833,34 +820,48 @@ static int upfirdn_stream_launch(int up, int down, const float* in, const float*
   if (dbg_nb) nb = dbg_nb;
   const int rh = nb * unit - halo;
   dim3 grid((unsigned)ceil_div(strips, 4), (unsigned)ceil_div(p.out_h, rh), (unsigned)planes);
-  if (up == 2) upfirdn2d_stream21_kernel<<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
+  if (up == 2) {
+    // output column pairs start at even columns: float2 stores need even rows and an 8-byte aligned base
+    if ((p.out_w & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) upfirdn2d_stream21_kernel<true><<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
+    else upfirdn2d_stream21_kernel<false><<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
+  }
   else if (down == 2) upfirdn2d_stream12_kernel<<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
   else upfirdn2d_stream11_kernel<<<grid, 128, 0, s>>>(in, kernel, out, p, rh);
   LFP_LAUNCH_CHECK();
   return 0;
 }
 
-static int upfirdn_ring_launch(const float* in, const float* kernel, float* out, const UpfirdnParams& p, cudaStream_t s) {
+template <int NCW>
+static int upfirdn_ring_launch_t(const float* in, const float* kernel, float* out, const UpfirdnParams& p, cudaStream_t s) {
   using namespace ring;
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_done[dev]) {
-    LFP_CUDA(cudaFuncSetAttribute(upfirdn2d_ring11_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    LFP_CUDA(cudaFuncSetAttribute(upfirdn2d_ring11_kernel<NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(NCW)));
     attr_done[dev] = true;
   }
   const int64_t pairs = (p.major + 1) / 2;
-  const dim3 grid0((unsigned)ceil_div(p.out_w, CW), (unsigned)ceil_div(p.out_h, RB), 1);
+  // output rows per CTA: rb + 3 input rows fill whole groups of G; 61 (16 groups) unless the map is short or the grid small
+  int rb = 61;
+  if (p.out_h <= 125) rb = (p.out_h + 3 + G - 1) / G * G - 3;
+  const dim3 grid0((unsigned)ceil_div(p.out_w, NCW * 32), (unsigned)ceil_div(p.out_h, rb), 1);
   for (int64_t z0 = 0; z0 < pairs; z0 += 65534) {  // even chunks keep the chunk base 16-byte aligned
     dim3 grid = grid0;
     grid.z = (unsigned)(pairs - z0 < 65534 ? pairs - z0 : 65534);
     UpfirdnParams pz = p;
     pz.major = p.major - 2 * z0;
-    upfirdn2d_ring11_kernel<<<grid, (NCW + 1) * 32, SMEM, s>>>(in + 2 * z0 * (int64_t)p.in_h * p.in_w, kernel,
-                                                               out + 2 * z0 * (int64_t)p.out_h * p.out_w, pz);
+    upfirdn2d_ring11_kernel<NCW><<<grid, (NCW + 1) * 32, smem_bytes(NCW), s>>>(in + 2 * z0 * (int64_t)p.in_h * p.in_w, kernel,
+                                                                              out + 2 * z0 * (int64_t)p.out_h * p.out_w, pz, rb);
   }
   LFP_LAUNCH_CHECK();
   return 0;
+}
+static int upfirdn_ring_launch(const float* in, const float* kernel, float* out, const UpfirdnParams& p, cudaStream_t s) {
+  // segment width: the widest that does not leave most of the last segment's warps idle
+  if (p.out_w > 160) return upfirdn_ring_launch_t<8>(in, kernel, out, p, s);
+  if (p.out_w > 64) return upfirdn_ring_launch_t<4>(in, kernel, out, p, s);
+  return upfirdn_ring_launch_t<2>(in, kernel, out, p, s);
 }
 
 int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dtype, int64_t major,
@@ -880,8 +881,8 @@ int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dty
   // the bulk copies take 16-byte aligned supersets of the rows: they stay inside the tensor when its base and its size are
   // 16-byte multiples
   static const bool no_ring = getenv("LFP_FIR_NO_RING") && atoi(getenv("LFP_FIR_NO_RING")) != 0;
-  if (allow_tiled && !use_tiled && !no_ring && dtype == LFP_F32 && minor == 1 && small_fir && up_x == 1 && down_x == 1 && p.out_w >= 128 &&
-      p.out_h >= 16 && (reinterpret_cast<uintptr_t>(input) & 15) == 0 && ((major * in_h * (int64_t)in_w) & 3) == 0 &&
+  if (allow_tiled && !use_tiled && !no_ring && dtype == LFP_F32 && minor == 1 && small_fir && up_x == 1 && down_x == 1 && p.out_w >= 16 &&
+      p.out_h >= 8 && (reinterpret_cast<uintptr_t>(input) & 15) == 0 && ((major * in_h * (int64_t)in_w) & 3) == 0 &&
       (int64_t)p.out_h * p.out_w < (1ll << 31) && (int64_t)in_h * in_w < (1ll << 31))
     return upfirdn_ring_launch((const float*)input, (const float*)kernel, (float*)out, p, s);
   if (allow_tiled && !use_tiled && dtype == LFP_F32 && minor == 1 && small_fir && p.out_h < (1 << 30) / 2 &&

@@ -42,6 +42,8 @@ HOT = [  # the configurations the synthesis path hits, at sizes 
     ("ring_w259", (2, 2, 65, 259), 1, 1, (2, 1)),
     ("ring_one_plane", (1, 1, 64, 1024), 1, 1, (1, 1)),
     ("ring_crop", (1, 4, 96, 200), 1, 1, (-1, 4)),
+    ("ring_narrow", (4, 8, 17, 17), 1, 1, (1, 1)),     # 2-warp segments
+    ("ring_mid", (2, 4, 65, 100), 1, 1, (2, 2)),       # 4-warp segments, one short band
 ]
 
 
