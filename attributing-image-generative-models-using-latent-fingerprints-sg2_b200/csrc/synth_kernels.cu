@@ -375,7 +375,244 @@ __global__ void __launch_bounds__(256) fir4x4_sep_nhwc_kernel(const float* __res
   }
 }
 
+// ---- row-ring variant for the wide layers (dense NHWC input, C <= 128) -----------------------------------------------------
+// The register-streaming kernel above keeps the bytes it has in flight in registers, which at HBM latency under load is not
+// enough to saturate the memory system.  Here one producer thread streams the input rows of a pixel segment into a
+// shared-memory ring with 1-D bulk copies (cp.async.bulk + mbarrier transaction bytes; an NHWC row piece is contiguous and
+// 16-byte aligned) while eight consumer warps run the same separable passes out of shared memory: horizontal 4-tap pass per
+// input row (LDS.128, one float4 of channels per lane), vertical pass over the last four horizontal rows held in registers,
+// fused noise/bias/lrelu epilogue.  The sums are formed in the same order as in fir4x4_sep_nhwc_kernel: identical results.
+namespace nring {
+constexpr int NCW = 8;  // consumer warps
+__host__ __device__ constexpr int segp(int C, int NV) { return NCW * 32 * 4 * NV / C; }          // output pixels per CTA row
+__host__ __device__ constexpr int rowb(int C, int NV) { return (segp(C, NV) + 3) * C * 4; }      // bytes of a staged row piece
+constexpr int NZB = 128;  // bytes reserved per slot for the noise of the output row the staged input row completes (<= 32 floats)
+__host__ __device__ constexpr int slotb(int C, int NV) { return rowb(C, NV) + NZB; }
+__host__ __device__ constexpr int depth(int C, int NV) { return 49152 / slotb(C, NV) < 12 ? 49152 / slotb(C, NV) : 12; }
+__host__ __device__ constexpr int smem_bytes(int C, int NV) { return depth(C, NV) * slotb(C, NV) + 2 * depth(C, NV) * 8 + 16; }
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+}  // namespace nring
+
+template <int C, int NV, bool ACT, bool OUT_PLANAR>
+__global__ void __launch_bounds__((nring::NCW + 1) * 32, 2) fir_ring_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                            const FirArgs a, int RB) {
+  using namespace nring;
+  constexpr int SEGP = segp(C, NV), ROWB = rowb(C, NV), SLOTB = slotb(C, NV), D = depth(C, NV);
+  extern __shared__ __align__(128) uint8_t nring_smem[];
+  const uint32_t sbase = smem_u32(nring_smem);
+  const uint32_t bars = sbase + D * SLOTB;  // full[D], empty[D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int ox0 = blockIdx.x * SEGP, r0 = blockIdx.y * RB;
+  const int rows = min(RB, a.out_h - r0);
+  const int total = rows + 3;          // input rows feeding the band
+  const int iy0 = r0 - a.pad;
+  const int pfirst = ox0 - a.pad;      // input pixel of tap 0 of the segment's first output pixel
+  const int pbase = max(pfirst, 0), pend = min(pfirst + SEGP + 3, a.in_w);
+  const int npx = pend - pbase;        // staged pixels per row
+  const int jlo = max(0, -iy0), jhi = npx > 0 ? min(total, a.in_h - iy0) : 0;   // staged input rows of the band
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < D; ++i) { mbar_init(bars + i * 8, 1); mbar_init(bars + (D + i) * 8, NCW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == NCW) {
+    // ---- producer ----
+    if (lane == 0) {
+      const float* src = in + (((int64_t)b * a.in_h + iy0) * a.in_w + pbase) * C;
+      const uint32_t bytes = (uint32_t)(npx > 0 ? npx : 0) * C * 4;
+      // ACT: the noise of output row j - 3 (one value per pixel of the segment) rides in the slot of input row j
+      const float* nsrc = ACT ? a.noise + (int64_t)b * a.noise_bstride + (int64_t)(r0 - 3) * a.out_w + ox0 : nullptr;
+      const uint32_t nbytes = ACT ? (uint32_t)min(SEGP, a.out_w - ox0) * 4 : 0u;
+      uint32_t slot_addr = sbase, full_bar = bars, empty_bar = bars + D * 8, par = 0;
+      int slot = 0;
+      for (int j = 0; j < total; ++j) {
+        if (j >= D) mbar_wait(empty_bar, par);
+        const bool ok = j >= jlo && j < jhi;
+        const bool nok = ACT && j >= 3;
+        mbar_expect_tx(full_bar, (ok ? bytes : 0u) + (nok ? nbytes : 0u));
+        if (ok) bulk_g2s(slot_addr, src + (int64_t)j * a.in_w * C, bytes, full_bar);
+        if (nok) bulk_g2s(slot_addr + ROWB, nsrc + (int64_t)j * a.out_w, nbytes, full_bar);
+        slot_addr += SLOTB; full_bar += 8; empty_bar += 8;
+        if (++slot == D) { slot = 0; slot_addr = sbase; full_bar = bars; empty_bar = bars + D * 8; if (j >= D) par ^= 1u; }
+      }
+    }
+    return;
+  }
+  // ---- consumers ----
+  float kx[4], ky[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { kx[i] = __ldg(a.kx + i); ky[i] = __ldg(a.ky + i); }
+  const int t = threadIdx.x;
+  uint32_t loff[NV];          // byte offset of tap 0 in a staged row
+  uint32_t tokmask = 0;       // bit (v*4 + tx): tap inside the image
+  int stok[NV];
+  float4 d4[NV], bias4[NV];
+  uint32_t nzoff[NV];         // byte offset of the lane's noise value in a slot
+  float* op0[NV];             // output pointer of the band's first row (dense), or of the even / odd rows (phase-major)
+  float* op1[NV];
+  int64_t ostep;              // floats between consecutive rows of one output pointer
+  const int oph = (a.out_h + 1) >> 1, opw = (a.out_w + 1) >> 1;
+  ostep = OUT_PLANAR ? (int64_t)opw * C : (int64_t)a.out_w * C;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int fo = (v * NCW * 32 + t) * 4;
+    const int px = fo / C, c = fo % C;
+    const int ox = ox0 + px;
+    stok[v] = ox < a.out_w;
+    const int oxc = min(ox, a.out_w - 1);
+    loff[v] = (uint32_t)(((pfirst + px - pbase) * C + c) * 4);
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) {
+      const int ip = pfirst + px + tx;
+      tokmask |= (ip >= 0 && ip < a.in_w ? 1u : 0u) << (v * 4 + tx);
+    }
+    if (ACT) {
+      d4[v] = __ldg(reinterpret_cast<const float4*>(a.demod + (int64_t)b * C + c));
+      bias4[v] = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+      nzoff[v] = (uint32_t)(ROWB + px * 4);
+    }
+    if (OUT_PLANAR) {
+      // r0 is even: even rows of the band live in phase plane (0, ox&1), odd rows in (1, ox&1), both from row r0/2 on
+      const int64_t plane_sz = (int64_t)oph * opw;
+      op0[v] = out + (((int64_t)b * 4 + (oxc & 1)) * plane_sz + (int64_t)(r0 >> 1) * opw + (oxc >> 1)) * C + c;
+      op1[v] = out + (((int64_t)b * 4 + 2 + (oxc & 1)) * plane_sz + (int64_t)(r0 >> 1) * opw + (oxc >> 1)) * C + c;
+    } else {
+      op0[v] = out + (((int64_t)b * a.out_h + r0) * a.out_w + oxc) * C + c;
+      op1[v] = op0[v];
+    }
+  }
+  const bool edge = __any_sync(0xffffffffu, tokmask != (NV == 1 ? 0xfu : 0xffu));
+  const float nw = ACT ? __ldg(a.noise_w) : 0.f;
+  float4 h1[NV], h2[NV], h3[NV];   // horizontal passes of the previous three input rows (h3 oldest)
+#pragma unroll
+  for (int v = 0; v < NV; ++v) h1[v] = h2[v] = h3[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t slot_addr = sbase, full_bar = bars, empty_bar = bars + D * 8, par = 0;
+  int slot = 0;
+  for (int j0 = 0; j0 < total; j0 += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + u;
+      if (j < total) {
+        mbar_wait(full_bar, par);
+        const bool rowok = j >= jlo && j < jhi;   // warp-uniform
+        float4 h0[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          float4 x[4];
+#pragma unroll
+          for (int tx = 0; tx < 4; ++tx) {
+            x[tx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok && (!edge || ((tokmask >> (v * 4 + tx)) & 1u))) x[tx] = lds128(slot_addr + loff[v] + tx * C * 4);
+          }
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int tx = 0; tx < 4; ++tx) acc = f4_fma(kx[tx], x[tx], acc);
+          h0[v] = acc;
+        }
+        float nz[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) nz[v] = ACT && j >= 3 && stok[v] ? lds32(slot_addr + nzoff[v]) : 0.f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar);
+        slot_addr += SLOTB; full_bar += 8; empty_bar += 8;
+        if (++slot == D) { slot = 0; slot_addr = sbase; full_bar = bars; empty_bar = bars + D * 8; par ^= 1u; }
+        const int tr = j - 3;    // output row of the band completed by input row j
+        if (tr >= 0) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc = f4_fma(ky[0], h3[v], acc);
+            acc = f4_fma(ky[1], h2[v], acc);
+            acc = f4_fma(ky[2], h1[v], acc);
+            acc = f4_fma(ky[3], h0[v], acc);
+            if (ACT) {
+              const float nzv = nw * nz[v];
+              acc.x = lrelu_fwd(fmaf(acc.x, d4[v].x, nzv) + bias4[v].x);
+              acc.y = lrelu_fwd(fmaf(acc.y, d4[v].y, nzv) + bias4[v].y);
+              acc.z = lrelu_fwd(fmaf(acc.z, d4[v].z, nzv) + bias4[v].z);
+              acc.w = lrelu_fwd(fmaf(acc.w, d4[v].w, nzv) + bias4[v].w);
+            }
+            // j = j0 + u with j0 even: the output row tr = j - 3 is odd for u == 0 and even for u == 1
+            if (OUT_PLANAR && u == 0) {
+              if (stok[v]) *reinterpret_cast<float4*>(op1[v]) = acc;
+              op1[v] += ostep;
+            } else {
+              if (stok[v]) *reinterpret_cast<float4*>(op0[v]) = acc;
+              op0[v] += ostep;
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { h3[v] = h2[v]; h2[v] = h1[v]; h1[v] = h0[v]; }
+      }
+    }
+  }
+}
+
+template <int C, int NV, bool ACT, bool OUT_PLANAR>
+static int launch_fir_ring(const float* in, float* out, const FirArgs& a, cudaStream_t s) {
+  using namespace nring;
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    LFP_CUDA(cudaFuncSetAttribute(fir_ring_nhwc_kernel<C, NV, ACT, OUT_PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(C, NV)));
+    attr_done[dev] = true;
+  }
+  const int rb = a.out_h >= 512 ? 128 : 64;   // even: the phase-major output alternates planes by row parity
+  dim3 grid((unsigned)ceil_div(a.out_w, segp(C, NV)), (unsigned)ceil_div(a.out_h, rb), (unsigned)a.batch);
+  fir_ring_nhwc_kernel<C, NV, ACT, OUT_PLANAR><<<grid, (NCW + 1) * 32, smem_bytes(C, NV), s>>>(in, out, a, rb);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream_t s) {
+  static const bool use_ring = !(getenv("LFP_FIR_RING") && atoi(getenv("LFP_FIR_RING")) == 0);
+  const bool noise_ok = !a.act || ((a.out_w & 3) == 0 && (a.noise_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.noise) & 15) == 0);
+  if (use_ring && a.kx != nullptr && a.ky != nullptr && !a.in_planar && a.out_w >= 64 && (a.act ? !a.out_planar : true) && noise_ok &&
+      (a.C == 32 || a.C == 64 || a.C == 128) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+#define LFP_RING_CASE(CC, NVV)                                                                      \
+    if (a.C == CC) {                                                                                 \
+      if (a.act) return launch_fir_ring<CC, NVV, true, false>(in, out, a, s);                        \
+      if (a.out_planar) return launch_fir_ring<CC, NVV, false, true>(in, out, a, s);                 \
+      return launch_fir_ring<CC, NVV, false, false>(in, out, a, s);                                  \
+    }
+    LFP_RING_CASE(32, 1)
+    LFP_RING_CASE(64, 2)
+    LFP_RING_CASE(128, 2)
+#undef LFP_RING_CASE
+  }
   if (a.kx != nullptr && a.ky != nullptr && a.out_w >= 64 && a.C % 4 == 0 && a.C <= 1024) {
     const int C4 = a.C / 4;
     const int PX = 256 / C4 > 0 ? 256 / C4 : 1;
