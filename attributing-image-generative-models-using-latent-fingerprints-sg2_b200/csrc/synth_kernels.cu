@@ -590,7 +590,10 @@ static int launch_fir_ring(const float* in, float* out, const FirArgs& a, cudaSt
     LFP_CUDA(cudaFuncSetAttribute(fir_ring_nhwc_kernel<C, NV, ACT, OUT_PLANAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(C, NV)));
     attr_done[dev] = true;
   }
-  const int rb = a.out_h >= 512 ? 128 : 64;   // even: the phase-major output alternates planes by row parity
+  // output rows per CTA (even: the phase-major output alternates planes by row parity): 128 costs 2 % of halo rows; halved
+  // while the grid is shorter than ~6 waves of the 2 CTAs an SM holds
+  int rb = a.out_h >= 512 ? 128 : 64;
+  while (rb > 32 && ceil_div(a.out_w, segp(C, NV)) * ceil_div(a.out_h, rb) * a.batch < (int64_t)num_sms() * 12) rb >>= 1;
   dim3 grid((unsigned)ceil_div(a.out_w, segp(C, NV)), (unsigned)ceil_div(a.out_h, rb), (unsigned)a.batch);
   fir_ring_nhwc_kernel<C, NV, ACT, OUT_PLANAR><<<grid, (NCW + 1) * 32, smem_bytes(C, NV), s>>>(in, out, a, rb);
   LFP_LAUNCH_CHECK();
