@@ -869,7 +869,159 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdArgs a, int C4
   }
 }
 
+// ---- row-ring variant for the large maps (C <= 128): same arithmetic, inputs streamed through shared memory ------------
+// The kernel above is a one-shot CTA per 256 pixels whose loads in flight live in registers; at 117 registers two CTAs fit
+// an SM, which keeps ~35 KB in flight and the kernel at 4 TB/s.  Here a producer thread streams 2048-float chunks of the
+// activation (and of g, the per-pixel ToRGB gradients and the noise) into a shared-memory ring with bulk copies, and 256
+// consumer threads walk a 2048-pixel segment chunk by chunk.  Each thread still sums its pixels in ascending order.
+namespace aring {
+constexpr int CHF = 2048;            // floats of activation per chunk
+constexpr int SEG = 2048;            // pixels per CTA
+constexpr int AUXB = 4 * 512;        // three ToRGB-gradient planes + noise, <= 128 floats each
+__host__ __device__ constexpr int slotb(bool gin) { return CHF * 4 * (gin ? 2 : 1) + AUXB; }
+constexpr int D = 5;
+__host__ __device__ constexpr int smem_bytes(bool gin) { return D * slotb(gin) + 2 * D * 8 + 16 + 2 * 1024 * 4; }
+}  // namespace aring
+
+template <int C, bool GIN, bool RGB>
+__global__ void __launch_bounds__(288) act_bwd_ring_kernel(const ActBwdArgs a) {
+  using namespace nring;
+  constexpr int CHF = aring::CHF, CHP = CHF / C, SLOTB = aring::slotb(GIN), D = aring::D, NCHUNK = aring::SEG / CHP;
+  constexpr int C4 = C / 4, PXT = 256 / C4;
+  extern __shared__ __align__(128) uint8_t aring_smem[];
+  const uint32_t sbase = smem_u32(aring_smem);
+  const uint32_t bars = sbase + D * SLOTB;
+  float* redT = reinterpret_cast<float*>(aring_smem + D * SLOTB + 2 * D * 8 + 16);
+  float* redR = redT + 1024;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int segs_per = a.hw / aring::SEG;
+  const int seg = blockIdx.x;
+  const int b = seg / segs_per;
+  const int pix0 = (seg - b * segs_per) * aring::SEG;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < D; ++i) { mbar_init(bars + i * 8, 1); mbar_init(bars + (D + i) * 8, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 8) {
+    if (lane == 0) {
+      const float* asrc = a.act + ((int64_t)b * a.hw + pix0) * C;
+      const float* gsrc = a.g + ((int64_t)b * a.hw + pix0) * C;
+      const float* nsrc = a.noise + (int64_t)b * a.noise_bstride + pix0;
+      const uint32_t bytes = CHF * 4 * (GIN ? 2 : 1) + CHP * 4 * (RGB ? 4 : 1);
+      for (int k = 0; k < NCHUNK; ++k) {
+        const int slot = k % D;
+        const uint32_t sa = sbase + slot * SLOTB, fb = bars + slot * 8;
+        if (k >= D) mbar_wait(bars + (D + slot) * 8, ((k / D) - 1) & 1);
+        mbar_expect_tx(fb, bytes);
+        bulk_g2s(sa, asrc + (int64_t)k * CHF, CHF * 4, fb);
+        if (GIN) bulk_g2s(sa + CHF * 4, gsrc + (int64_t)k * CHF, CHF * 4, fb);
+        const uint32_t aux = sa + CHF * 4 * (GIN ? 2 : 1);
+        bulk_g2s(aux, nsrc + k * CHP, CHP * 4, fb);
+        if (RGB) {
+#pragma unroll
+          for (int o = 0; o < 3; ++o)
+            bulk_g2s(aux + (1 + o) * 512, a.drgb + ((int64_t)b * 3 + o) * a.hw + pix0 + k * CHP, CHP * 4, fb);
+        }
+      }
+    }
+  } else {
+    const int t = threadIdx.x;
+    const int c4 = t % C4, py = t / C4;
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(a.demod + (int64_t)b * C + c4 * 4));
+    const float4 bias4 = __ldg(reinterpret_cast<const float4*>(a.bias + c4 * 4));
+    const float nw = __ldg(a.noise_w);
+    float4 T4 = make_float4(0.f, 0.f, 0.f, 0.f), R4 = T4;
+    float4 s4 = T4, w0 = T4, w1 = T4, w2 = T4;
+    if (RGB) {
+      s4 = __ldg(reinterpret_cast<const float4*>(a.s_rgb + (int64_t)b * C + c4 * 4));
+      w0 = __ldg(reinterpret_cast<const float4*>(a.wrgb + 0 * C + c4 * 4));
+      w1 = __ldg(reinterpret_cast<const float4*>(a.wrgb + 1 * C + c4 * 4));
+      w2 = __ldg(reinterpret_cast<const float4*>(a.wrgb + 2 * C + c4 * 4));
+    }
+    const float inv_pos = 1.f / kLreluGain, inv_neg = 1.f / (kLreluGain * kLreluSlope);
+    float* gout = a.g + ((int64_t)b * a.hw + pix0) * C;
+    constexpr int NV = CHF / 1024;   // float4 per thread and chunk
+    for (int k = 0; k < NCHUNK; ++k) {
+      const int slot = k % D;
+      const uint32_t sa = sbase + slot * SLOTB;
+      mbar_wait(bars + slot * 8, (k / D) & 1);
+      float4 act_v[NV], g_v[NV];
+      float r0v[NV], r1v[NV], r2v[NV], nzv[NV];
+      const uint32_t aux = sa + CHF * 4 * (GIN ? 2 : 1);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int f = (v * 256 + t) * 4, px = f / C;
+        act_v[v] = lds128(sa + f * 4);
+        g_v[v] = GIN ? lds128(sa + CHF * 4 + f * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nzv[v] = nw * lds32(aux + px * 4);
+        r0v[v] = r1v[v] = r2v[v] = 0.f;
+        if (RGB) { r0v[v] = lds32(aux + 512 + px * 4); r1v[v] = lds32(aux + 1024 + px * 4); r2v[v] = lds32(aux + 1536 + px * 4); }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + (D + slot) * 8);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int f = (v * 256 + t) * 4;
+        const float4 act4 = act_v[v];
+        float4 g4 = g_v[v];
+        if (RGB) {
+          const float r0 = r0v[v], r1 = r1v[v], r2 = r2v[v];
+          float4 q4 = make_float4(r0 * w0.x, r0 * w0.y, r0 * w0.z, r0 * w0.w);
+          q4 = f4_fma(r1, w1, q4);
+          q4 = f4_fma(r2, w2, q4);
+          g4 = f4_fma4(q4, s4, g4);
+          R4 = f4_fma4(act4, q4, R4);
+        }
+        const float nz = nzv[v];
+        float4 o4;
+#define LFP_ACTB(comp)                                                          \
+  {                                                                             \
+    const bool pos = act4.comp > 0.f;                                           \
+    const float gpre = g4.comp * (pos ? kLreluGain : kLreluGain * kLreluSlope); \
+    const float pre = act4.comp * (pos ? inv_pos : inv_neg);                    \
+    T4.comp = fmaf(gpre, pre - nz - bias4.comp, T4.comp);                       \
+    o4.comp = gpre * d4.comp;                                                   \
+  }
+        LFP_ACTB(x) LFP_ACTB(y) LFP_ACTB(z) LFP_ACTB(w)
+#undef LFP_ACTB
+        *reinterpret_cast<float4*>(gout + (int64_t)k * CHF + f) = o4;
+      }
+    }
+    *reinterpret_cast<float4*>(&redT[py * C + c4 * 4]) = T4;
+    *reinterpret_cast<float4*>(&redR[py * C + c4 * 4]) = R4;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 288) {
+    float tt = 0.f, r = 0.f;
+    for (int q = 0; q < PXT; ++q) { tt += redT[q * C + c]; r += redR[q * C + c]; }
+    a.pT[(int64_t)seg * C + c] = tt;
+    if (RGB) a.pR[(int64_t)seg * C + c] = r;
+  }
+}
+
+static bool actbwd_ring_ok(int hw, int C) {
+  static const bool use_ring = !(getenv("LFP_ACTBWD_RING") && atoi(getenv("LFP_ACTBWD_RING")) == 0);
+  return use_ring && (C == 32 || C == 64 || C == 128) && hw >= 65536 && hw % aring::SEG == 0;
+}
+
+template <int C, bool GIN, bool RGB>
+static int launch_act_bwd_ring(const ActBwdArgs& a, cudaStream_t s) {
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_done[dev]) {
+    LFP_CUDA(cudaFuncSetAttribute(act_bwd_ring_kernel<C, GIN, RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, aring::smem_bytes(GIN)));
+    attr_done[dev] = true;
+  }
+  const int64_t nseg = (int64_t)a.batch * (a.hw / aring::SEG);
+  act_bwd_ring_kernel<C, GIN, RGB><<<(unsigned)nseg, 288, aring::smem_bytes(GIN), s>>>(a);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
 int actbwd_seglen(int hw, int C) {
+  if (actbwd_ring_ok(hw, C)) return aring::SEG;
   const int PX = 1024 / C;  // pixels per CTA pass
   int seg = PX * 8;
   if (seg < 256) seg = 256;
@@ -879,6 +1031,19 @@ int actbwd_seglen(int hw, int C) {
 
 int launch_act_bwd(const ActBwdArgs& a, cudaStream_t s) {
   LFP_CHECK_ARG(a.C % 4 == 0 && a.C <= 1024 && 1024 % a.C == 0, "act_bwd: unsupported C=%d", a.C);
+  const bool aligned = (reinterpret_cast<uintptr_t>(a.act) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.g) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.noise) & 15) == 0 && (a.noise_bstride & 3) == 0 &&
+                       (a.drgb == nullptr || (reinterpret_cast<uintptr_t>(a.drgb) & 15) == 0);
+  if (actbwd_ring_ok(a.hw, a.C)) {
+    LFP_CHECK_ARG(aligned, "act_bwd: the ring kernel needs 16-byte aligned tensors");
+#define LFP_AR(CC)                                                                                         \
+    if (a.C == CC) {                                                                                        \
+      if (a.g_has_input) return a.drgb ? launch_act_bwd_ring<CC, true, true>(a, s) : launch_act_bwd_ring<CC, true, false>(a, s); \
+      return a.drgb ? launch_act_bwd_ring<CC, false, true>(a, s) : launch_act_bwd_ring<CC, false, false>(a, s);                \
+    }
+    LFP_AR(32) LFP_AR(64) LFP_AR(128)
+#undef LFP_AR
+  }
   const int C4 = a.C / 4, PX = 256 / C4;
   const int seglen = actbwd_seglen(a.hw, a.C);
   LFP_CHECK_ARG(a.hw % seglen == 0, "act_bwd: hw=%d not divisible by segment %d", a.hw, seglen);
