@@ -649,20 +649,20 @@ int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream
 // =============================================================================================
 __device__ __forceinline__ float up2_sample(const float* __restrict__ sp, int h2, int w2,
                                             const float* __restrict__ kup, int oy, int ox) {
-  // Upsample: upfirdn2d(up=2, pad=(2,1)) (src/model.py:33-51); flipped tap (ty,tx) = kup[3-ty][3-tx]
+  // Upsample: upfirdn2d(up=2, pad=(2,1)) (src/model.py:33-51); flipped tap (ty,tx) = kup[3-ty][3-tx].  Only the taps whose
+  // zero-stuffed coordinate oy + ty - 2 is even meet a sample: ty = (oy & 1) + {0, 2}, likewise tx; ascending tap order.
   float acc = 0.f;
+  const int py = oy & 1, px = ox & 1;
 #pragma unroll
-  for (int ty = 0; ty < 4; ++ty) {
-    const int sy = oy + ty - 2;
-    if (sy < 0 || (sy & 1)) continue;
-    const int iy = sy >> 1;
-    if (iy >= h2) continue;
+  for (int jy = 0; jy < 2; ++jy) {
+    const int ty = py + 2 * jy;
+    const int iy = (oy + ty - 2) >> 1;
+    if (iy < 0 || iy >= h2) continue;
 #pragma unroll
-    for (int tx = 0; tx < 4; ++tx) {
-      const int sx = ox + tx - 2;
-      if (sx < 0 || (sx & 1)) continue;
-      const int ix = sx >> 1;
-      if (ix >= w2) continue;
+    for (int jx = 0; jx < 2; ++jx) {
+      const int tx = px + 2 * jx;
+      const int ix = (ox + tx - 2) >> 1;
+      if (ix < 0 || ix >= w2) continue;
       acc = fmaf(__ldg(sp + (int64_t)iy * w2 + ix), __ldg(kup + (3 - ty) * 4 + (3 - tx)), acc);
     }
   }
