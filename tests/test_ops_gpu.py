@@ -72,6 +72,19 @@ def test_upfirdn2d_many_planes_and_dtypes():
     x = fx.seeded((70000, 1, 6, 6), 9)  # N*C > 65535: beyond one grid dimension
     y = op.upfirdn2d(x.to(DEV), k.to(DEV), pad=(1, 1))
     np.testing.assert_allclose(y.cpu().numpy(), oracle.upfirdn2d(x, k, pad=(1, 1)).numpy(), rtol=1e-5, atol=1e-6)
+    # plane counts beyond one grid dimension in the specialised kernels: the ring kernel launches in chunks of 65534 plane
+    # pairs, the streaming kernels loop over planes; checked on the planes around the boundaries
+    big = torch.randn(140000, 1, 17, 17, generator=torch.Generator().manual_seed(5))
+    yb = op.upfirdn2d(big.to(DEV), k.to(DEV), pad=(1, 1)).cpu()
+    for lo in (0, 65530, 131060, 139990):
+        ref = oracle.upfirdn2d(big[lo:lo + 10], k, pad=(1, 1))
+        np.testing.assert_allclose(yb[lo:lo + 10].numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
+    small = torch.randn(70000, 1, 8, 8, generator=torch.Generator().manual_seed(6))
+    yu = op.upfirdn2d(small.to(DEV), k.to(DEV), up=2, pad=(2, 1)).cpu()
+    yd = op.upfirdn2d(small.to(DEV), k.to(DEV), down=2, pad=(1, 1)).cpu()
+    for lo in (0, 65530, 69990):
+        np.testing.assert_allclose(yu[lo:lo + 10].numpy(), oracle.upfirdn2d(small[lo:lo + 10], k, up=2, pad=(2, 1)).numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(yd[lo:lo + 10].numpy(), oracle.upfirdn2d(small[lo:lo + 10], k, down=2, pad=(1, 1)).numpy(), rtol=1e-5, atol=1e-6)
     x = fx.seeded((2, 3, 33, 31), 10)
     for dt, tol in ((torch.float64, 1e-12), (torch.float16, 2e-3)):
         ref = oracle.upfirdn2d(x.double(), k.double(), up=2, pad=(2, 1))
