@@ -6,12 +6,13 @@
 // with S the zero-stuffed input (S[j] = in[j/up] when up | j and 0 <= j/up < in, else 0) and
 // kflip[ty][tx] = kernel[kh-1-ty][kw-1-tx].
 //
-// B200 design: the op is HBM-bound (4 B in + 4 B out per sample at up=down=1).  The hot
-// configurations in the synthesis path all have minor == 1 and a <=4x4 kernel, so they go to a
-// shared-memory tiled kernel: one CTA stages a zero-padded input tile once (coalesced 4-byte
-// loads; rows of 2H+1 floats rule out 16-byte global alignment) and every thread produces a
-// 2x4 micro-tile from 128-bit shared loads, i.e. 10 LDS.128 per 128 FMAs at up=down=1.
-// Everything else (minor > 1, big kernels, odd up/down, fp16/fp64) takes the direct kernel.
+// B200 design: the op is HBM-bound (4 B in + 4 B out per sample at up=down=1), and at the memory latency a loaded HBM system
+// has (~2 us) the bound is only reached with >= 50 KB of reads in flight per SM.  The hot configurations of the synthesis
+// path (minor == 1, taps <= 4x4, fp32) therefore go to
+//   * up = down = 1 (Blur and its adjoint): a shared-memory row ring filled by 1-D bulk copies (cp.async.bulk + mbarrier),
+//     consumed by warps that keep the partially summed output rows in registers - upfirdn2d_ring11_kernel;
+//   * up = 2 / down = 2: warp-streaming kernels without shared memory (a lane owns an output column, neighbours by shuffle);
+// everything else (minor > 1, big kernels, odd up/down, fp16/fp64) takes the direct kernel.
 // All indexing is 64-bit (the reference overflows at 2^31 elements).
 #include "common.cuh"
 
@@ -68,159 +69,6 @@ __global__ void __launch_bounds__(256) upfirdn2d_direct_kernel(const T* __restri
   }
 }
 
-// ---- tiled kernel: minor == 1, fp32, kernel <= 4x4, (UP,DOWN) in {(1,1),(1,2),(2,1)} ----------
-constexpr int TILE_OH = 32;
-constexpr int TILE_OW = 64;
-
-template <int UP, int DOWN>
-struct TileGeom {
-  // extent on the zero-stuffed grid covered by one output tile, then in input samples
-  static constexpr int OH = DOWN == 2 ? 16 : TILE_OH;   // output rows per tile (halved for down-2: its input tile is 4x larger)
-  static constexpr int RPT = OH / 16;                   // output rows per thread
-  static constexpr int SPAN_H = (OH - 1) * DOWN + 4;
-  static constexpr int SPAN_W = (TILE_OW - 1) * DOWN + 4;
-  static constexpr int IN_H = UP == 1 ? SPAN_H : SPAN_H / 2 + 1;
-  static constexpr int IN_W_RAW = UP == 1 ? SPAN_W : SPAN_W / 2 + 1;
-  static constexpr int IN_W = (IN_W_RAW + 3) / 4 * 4;  // 16-byte aligned rows for LDS.128
-};
-
-// One CTA owns one output tile position and walks the planes (N*C) with a register-staged pipeline: the zero-padded
-// input tile of plane p+1 is loaded (coalesced 4-byte loads - rows of 2H+1 floats rule out 16-byte alignment and TMA)
-// while plane p is filtered out of shared memory.  Per-thread source offsets, shared
-// offsets and bounds flags do not depend on the plane and are computed once.
-template <int UP, int DOWN>
-__global__ void __launch_bounds__(256) upfirdn2d_tiled_kernel(const float* __restrict__ in,
-                                                              const float* __restrict__ kernel,
-                                                              float* __restrict__ out,
-                                                              UpfirdnParams p) {
-  using G = TileGeom<UP, DOWN>;
-  constexpr int TOT = G::IN_H * G::IN_W;
-  constexpr int NL = (TOT + 255) / 256;
-  __shared__ __align__(16) float tile[1][G::IN_H][G::IN_W];
-  __shared__ float kf[4][4];  // flipped taps, zero-extended to 4x4
-
-  const int tid = threadIdx.x;
-  if (tid < 16) {
-    const int ty = tid >> 2, tx = tid & 3;
-    float v = 0.f;
-    if (ty < p.kh && tx < p.kw) v = kernel[(p.kh - 1 - ty) * p.kw + (p.kw - 1 - tx)];
-    kf[ty][tx] = v;
-  }
-  const int tile_ox = blockIdx.x * TILE_OW;
-  const int tile_oy = blockIdx.y * G::OH;
-  // stuffed-grid origin of the tile and the first input sample at/after it
-  const int sy0 = tile_oy * DOWN - p.pad_y0;
-  const int sx0 = tile_ox * DOWN - p.pad_x0;
-  const int iy0 = UP == 1 ? sy0 : floor_div_i(sy0 + 1, 2);
-  const int ix0 = UP == 1 ? sx0 : floor_div_i(sx0 + 1, 2);
-  const int64_t plane_in = (int64_t)p.in_h * p.in_w;
-  const int64_t plane_out = (int64_t)p.out_h * p.out_w;
-
-  int goff[NL];
-  uint32_t okmask = 0;
-#pragma unroll
-  for (int j = 0; j < NL; ++j) {
-    const int i = tid + j * 256;
-    const int r = i / G::IN_W, c = i - r * G::IN_W;
-    const int iy = iy0 + r, ix = ix0 + c;
-    const bool ok = i < TOT && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
-    goff[j] = ok ? iy * p.in_w + ix : 0;
-    okmask |= (ok ? 1u : 0u) << j;
-  }
-  // register-staged software pipeline: the next plane's tile is in flight (plain coalesced 4-byte loads: LDG issues ~4x
-  // faster than 4-byte cp.async) while the current plane is filtered out of shared memory
-  float stage[NL];
-  auto fetch = [&](int64_t plane) {
-    const float* src = in + plane * plane_in;
-#pragma unroll
-    for (int j = 0; j < NL; ++j) {
-      stage[j] = 0.f;
-      if ((okmask >> j) & 1u) stage[j] = __ldg(src + goff[j]);
-    }
-  };
-  float* const tile_flat = &tile[0][0][0];
-
-  constexpr int RPT = G::RPT;
-  const int lx = (tid & 15) * 4;    // 4 output columns per thread
-  const int ly = (tid >> 4) * RPT;  // RPT output rows per thread
-  constexpr int buf = 0;
-  if ((int64_t)blockIdx.z < p.major) fetch(blockIdx.z);
-  for (int64_t plane = blockIdx.z; plane < p.major; plane += gridDim.z) {
-    __syncthreads();  // the previous plane's readers are done (also orders the kf writes)
-#pragma unroll
-    for (int j = 0; j < NL; ++j) {
-      const int i = tid + j * 256;
-      if (i < TOT) tile_flat[i] = stage[j];
-    }
-    __syncthreads();
-    const int64_t next = plane + gridDim.z;
-    if (next < p.major) fetch(next);
-    float acc[RPT][4] = {};
-    if (UP == 1) {
-      constexpr int WR = (RPT - 1) * DOWN + 4;   // window rows
-      constexpr int WC = 3 * DOWN + 4;  // window cols:   (4-1)*DOWN + 4
-      constexpr int WCV = (WC + 3) / 4;
-      float win[WR][WCV * 4];
-#pragma unroll
-      for (int r = 0; r < WR; ++r)
-#pragma unroll
-        for (int v = 0; v < WCV; ++v) {
-          const float4 q = *reinterpret_cast<const float4*>(&tile[buf][ly * DOWN + r][lx * DOWN + v * 4]);
-          win[r][v * 4 + 0] = q.x; win[r][v * 4 + 1] = q.y; win[r][v * 4 + 2] = q.z; win[r][v * 4 + 3] = q.w;
-        }
-#pragma unroll
-      for (int ty = 0; ty < 4; ++ty)
-#pragma unroll
-        for (int tx = 0; tx < 4; ++tx) {
-          const float k = kf[ty][tx];
-#pragma unroll
-          for (int r = 0; r < RPT; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(win[r * DOWN + ty][c * DOWN + tx], k, acc[r][c]);
-        }
-    } else {
-      // UP == 2 (DOWN == 1): only the taps that land on an even stuffed coordinate see a sample - two per axis, chosen
-      // by the parity of the output position (ascending tap order, as in the 16-tap form)
-#pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        const int py = (sy0 + ly + r) & 1;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int px = (sx0 + lx + c) & 1;
-          float a = 0.f;
-#pragma unroll
-          for (int jy = 0; jy < 2; ++jy) {
-            const int ty = py + 2 * jy;
-            const int rr = ((sy0 + ly + r + ty) >> 1) - iy0;
-#pragma unroll
-            for (int jx = 0; jx < 2; ++jx) {
-              const int tx = px + 2 * jx;
-              a = fmaf(tile[buf][rr][((sx0 + lx + c + tx) >> 1) - ix0], kf[ty][tx], a);
-            }
-          }
-          acc[r][c] = a;
-        }
-      }
-    }
-    float* dst = out + plane * plane_out;
-#pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int oy = tile_oy + ly + r;
-      if (oy >= p.out_h) continue;
-      const int ox = tile_ox + lx;
-      float* row = dst + (int64_t)oy * p.out_w + ox;
-      if (ox + 3 < p.out_w && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
-        *reinterpret_cast<float4*>(row) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (ox + c < p.out_w) row[c] = acc[r][c];
-      }
-    }
-  }
-}
-
-
 // ---- warp-streaming kernels: minor == 1, fp32, kernel <= 4x4 ----------------------------------------------------------
 // One warp owns a strip of output columns and walks down the rows of a plane.  A lane loads one input column per row
 // (one coalesced 128-byte request per warp and row, no alignment requirement - rows of 2H+1 floats are fine), gets its
@@ -252,13 +100,6 @@ __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   return r;
 }
 __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-// a load the compiler may not move: the streaming kernels reload a row's register right where the row was consumed, which
-// keeps U rows in flight without a second register buffer (hoisted loads would need one and spill)
-__device__ __forceinline__ float ldg_pinned(const float* p) {
-  float v;
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t r;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -270,14 +111,10 @@ struct S11Ctx {
   int64_t in_b, out_b;  // offset of the lane's second plane (0 / unused when the pair has only one)
   bool colok, stok, stok_b;
 };
-// rows this far below the ones being loaded are prefetched into L2: the loads then see L2 latency, and the bytes in flight
-// to DRAM no longer have to be held in registers
-constexpr int S11_PF = 24;
 template <bool FAST>
 __device__ __forceinline__ void s11_load(float (&da)[STREAM_U], float (&db)[STREAM_U], const S11Ctx& c, const float* __restrict__ col,
                                          int jb) {
   // col: first plane's base + row iy0 + clamped input column (32-bit row offsets from there); rows jb .. jb + U-1 of the block
-  const bool pf = false;
 #pragma unroll
   for (int u = 0; u < STREAM_U; ++u) {
     const int iy = c.iy0 + jb + u;
@@ -289,11 +126,6 @@ __device__ __forceinline__ void s11_load(float (&da)[STREAM_U], float (&db)[STRE
       const bool ok = c.colok && jb + u < c.total && iy >= 0 && iy < c.in_h;
       da[u] = ok ? __ldg(ptr) : 0.f;
       db[u] = ok ? __ldg(ptr + c.in_b) : 0.f;
-    }
-    if (pf) {
-      const float* pp = ptr + S11_PF * c.in_w;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + c.in_b));
     }
   }
 }
@@ -788,27 +620,10 @@ static int upfirdn_direct_launch(const void* in, const void* kernel, void* out, 
   return 0;
 }
 
-template <int UP, int DOWN>
-static int upfirdn_tiled_launch(const float* in, const float* kernel, float* out, const UpfirdnParams& p,
-                                cudaStream_t s) {
-  // enough CTAs for ~8 per SM; each walks several planes so that the two-stage pipeline has something to overlap
-  constexpr int OH = TileGeom<UP, DOWN>::OH;
-  const int64_t tiles = ceil_div(p.out_w, TILE_OW) * ceil_div(p.out_h, OH);
-  int64_t gz = ceil_div((int64_t)num_sms() * 8, tiles);
-  if (gz < 1) gz = 1;
-  if (gz > p.major) gz = p.major;
-  if (gz > 65535) gz = 65535;
-  dim3 grid((unsigned)ceil_div(p.out_w, TILE_OW), (unsigned)ceil_div(p.out_h, OH), (unsigned)gz);
-  upfirdn2d_tiled_kernel<UP, DOWN><<<grid, 256, 0, s>>>(in, kernel, out, p);
-  LFP_LAUNCH_CHECK();
-  return 0;
-}
-
 // rows per warp task: long enough to amortise the halo rows re-read at the top of each block, short enough that
 // there are several warps' worth of tasks per SM
 static int upfirdn_stream_launch(int up, int down, const float* in, const float* kernel, float* out, const UpfirdnParams& p,
                                  cudaStream_t s) {
-  static const int dbg_nb = getenv("LFP_STREAM_NB") ? atoi(getenv("LFP_STREAM_NB")) : 0;
   const int wcols = up == 2 ? S21_W : down == 2 ? S12_W : S11_W;
   const int64_t strips = ceil_div(p.out_w, wcols);
   const int64_t units = up == 1 && down == 1 ? (p.major + 1) / 2 : p.major;  // the 1:1 kernel pairs planes
@@ -817,7 +632,6 @@ static int upfirdn_stream_launch(int up, int down, const float* in, const float*
   const int halo = up == 2 ? 4 : down == 2 ? 1 : 3, unit = up == 2 ? 32 : down == 2 ? 4 : 8;
   int nb = 128 / unit;
   while (nb > 2 && strips * ceil_div(p.out_h, nb * unit - halo) * planes < (int64_t)num_sms() * 64) nb >>= 1;
-  if (dbg_nb) nb = dbg_nb;
   const int rh = nb * unit - halo;
   dim3 grid((unsigned)ceil_div(strips, 4), (unsigned)ceil_div(p.out_h, rh), (unsigned)planes);
   if (up == 2) {
@@ -876,23 +690,15 @@ int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dty
                                  pad_y0, pad_y1, &p.out_h, &p.out_w));
   if (major == 0 || minor == 0 || p.out_h <= 0 || p.out_w <= 0) return 0;
   const bool small_fir = kh <= 4 && kw <= 4 && up_x == up_y && down_x == down_y;
-  const bool tiny = p.out_h * (int64_t)p.out_w < 64;  // 4x4 / 8x8 maps: a tile would be mostly halo
-  static const bool use_tiled = getenv("LFP_FIR_TILED") && atoi(getenv("LFP_FIR_TILED")) != 0;
   // the bulk copies take 16-byte aligned supersets of the rows: they stay inside the tensor when its base and its size are
   // 16-byte multiples
   static const bool no_ring = getenv("LFP_FIR_NO_RING") && atoi(getenv("LFP_FIR_NO_RING")) != 0;
-  if (allow_tiled && !use_tiled && !no_ring && dtype == LFP_F32 && minor == 1 && small_fir && up_x == 1 && down_x == 1 && p.out_w >= 16 &&
-      p.out_h >= 8 && (reinterpret_cast<uintptr_t>(input) & 15) == 0 && ((major * in_h * (int64_t)in_w) & 3) == 0 &&
-      (int64_t)p.out_h * p.out_w < (1ll << 31) && (int64_t)in_h * in_w < (1ll << 31))
+  const bool fast = allow_tiled && dtype == LFP_F32 && minor == 1 && small_fir && p.out_h < (1 << 30) / 2;
+  if (fast && !no_ring && up_x == 1 && down_x == 1 && p.out_w >= 16 && p.out_h >= 8 && (reinterpret_cast<uintptr_t>(input) & 15) == 0 &&
+      ((major * in_h * (int64_t)in_w) & 3) == 0 && (int64_t)p.out_h * p.out_w < (1ll << 31) && (int64_t)in_h * in_w < (1ll << 31))
     return upfirdn_ring_launch((const float*)input, (const float*)kernel, (float*)out, p, s);
-  if (allow_tiled && !use_tiled && dtype == LFP_F32 && minor == 1 && small_fir && p.out_h < (1 << 30) / 2 &&
-      ((up_x == 1 && down_x == 1) || (up_x == 2 && down_x == 1) || (up_x == 1 && down_x == 2)))
+  if (fast && ((up_x == 1 && down_x == 1) || (up_x == 2 && down_x == 1) || (up_x == 1 && down_x == 2)))
     return upfirdn_stream_launch(up_x, down_x, (const float*)input, (const float*)kernel, (float*)out, p, s);
-  if (allow_tiled && dtype == LFP_F32 && minor == 1 && small_fir && !tiny) {
-    if (up_x == 1 && down_x == 1) return upfirdn_tiled_launch<1, 1>((const float*)input, (const float*)kernel, (float*)out, p, s);
-    if (up_x == 1 && down_x == 2) return upfirdn_tiled_launch<1, 2>((const float*)input, (const float*)kernel, (float*)out, p, s);
-    if (up_x == 2 && down_x == 1) return upfirdn_tiled_launch<2, 1>((const float*)input, (const float*)kernel, (float*)out, p, s);
-  }
   switch (dtype) {
     case LFP_F32: return upfirdn_direct_launch<float>(input, kernel, out, p, s);
     case LFP_F64: return upfirdn_direct_launch<double>(input, kernel, out, p, s);
