@@ -604,7 +604,7 @@ int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream
   static const bool use_ring = !(getenv("LFP_FIR_RING") && atoi(getenv("LFP_FIR_RING")) == 0);
   const bool noise_ok = !a.act || ((a.out_w & 3) == 0 && (a.noise_bstride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.noise) & 15) == 0);
   if (use_ring && a.kx != nullptr && a.ky != nullptr && !a.in_planar && a.out_w >= 64 && (a.act ? !a.out_planar : true) && noise_ok &&
-      (a.C == 32 || a.C == 64 || a.C == 128) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+      (a.C == 32 || a.C == 64 || a.C == 128 || a.C == 256) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
 #define LFP_RING_CASE(CC, NVV)                                                                      \
     if (a.C == CC) {                                                                                 \
       if (a.act) return launch_fir_ring<CC, NVV, true, false>(in, out, a, s);                        \
@@ -612,8 +612,9 @@ int launch_fir4x4_nhwc(const float* in, float* out, const FirArgs& a, cudaStream
       return launch_fir_ring<CC, NVV, false, false>(in, out, a, s);                                  \
     }
     LFP_RING_CASE(32, 1)
-    LFP_RING_CASE(64, 2)
-    LFP_RING_CASE(128, 2)
+    LFP_RING_CASE(64, 1)
+    LFP_RING_CASE(128, 1)
+    LFP_RING_CASE(256, 1)
 #undef LFP_RING_CASE
   }
   if (a.kx != nullptr && a.ky != nullptr && a.out_w >= 64 && a.C % 4 == 0 && a.C <= 1024) {
