@@ -694,19 +694,31 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
     for (int o = 0; o < 3; ++o) m[o][q] = f4_mul(sv, __ldg(reinterpret_cast<const float4*>(wrgb + o * C + c)));
   }
   float mine[3] = {0.f, 0.f, 0.f};
-  const float* base = act + (int64_t)b * hw * C;
+  // C = 4 * LPP * NCH is fixed by the instantiation: one 64-bit pointer per lane, every other address a compile-time
+  // offset from it (the kernel is bound by instruction issue, not by bytes)
+  constexpr int CT = 4 * LPP * NCH;
+  const float* lane_base = act + ((int64_t)b * hw + pix0 + sub) * CT + li * 4;
+  const bool whole = pix0 + 32 <= hw;   // warp-uniform: all 32 pixels of the group exist
   // groups of up to 8 pixel-iterations with all activation loads issued before the first use
   constexpr int GRP = LPP * NCH <= 8 ? LPP : (8 / NCH >= 1 ? 8 / NCH : 1);   // <= 8 float4 in flight per lane
 #pragma unroll 1
   for (int it0 = 0; it0 < LPP; it0 += GRP) {
     float4 v[GRP][NCH];
+    const float* gp = lane_base + (int64_t)it0 * PPW * CT;
+    if (whole) {
 #pragma unroll
-    for (int g = 0; g < GRP; ++g) {
-      const int pix = pix0 + (it0 + g) * PPW + sub;
+      for (int g = 0; g < GRP; ++g)
 #pragma unroll
-      for (int q = 0; q < NCH; ++q) {
-        v[g][q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pix < hw) v[g][q] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)pix * C + (q * LPP + li) * 4));
+        for (int q = 0; q < NCH; ++q) v[g][q] = __ldg(reinterpret_cast<const float4*>(gp + g * PPW * CT + q * LPP * 4));
+    } else {
+#pragma unroll
+      for (int g = 0; g < GRP; ++g) {
+        const int pix = pix0 + (it0 + g) * PPW + sub;
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+          v[g][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pix < hw) v[g][q] = __ldg(reinterpret_cast<const float4*>(gp + g * PPW * CT + q * LPP * 4));
+        }
       }
     }
 #pragma unroll
