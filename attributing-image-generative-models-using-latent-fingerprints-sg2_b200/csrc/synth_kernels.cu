@@ -721,26 +721,43 @@ __global__ void __launch_bounds__(256) torgb_fwd_kernel(const float* __restrict_
         }
       }
     }
+    float r[GRP][3];
 #pragma unroll
     for (int g = 0; g < GRP; ++g) {
-      const int it = it0 + g;
-      float r[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int o = 0; o < 3; ++o) r[g][o] = 0.f;
 #pragma unroll
       for (int q = 0; q < NCH; ++q)
 #pragma unroll
-        for (int o = 0; o < 3; ++o) r[o] += f4_dot(v[g][q], m[o][q]);
+        for (int o = 0; o < 3; ++o) r[g][o] += f4_dot(v[g][q], m[o][q]);
+    }
+    // Reduce over the LPP lanes of a pixel by recursive halving: at each step a lane keeps half of the passes it still holds
+    // and hands the other half to its partner, so GRP passes cost 3*(GRP-1) shuffles instead of 3*GRP*log2(LPP).  Afterwards
+    // the lanes whose low bits are j hold pass it0 + j; the fixed exchange pattern keeps the sums independent of the batch.
 #pragma unroll
-      for (int off = LPP / 2; off > 0; off >>= 1)
+    for (int bit = GRP / 2; bit >= 1; bit >>= 1) {
+      const bool upper = (li & bit) != 0;
 #pragma unroll
-        for (int o = 0; o < 3; ++o) r[o] += __shfl_xor_sync(0xffffffffu, r[o], off);
+      for (int g = 0; g < bit; ++g)
 #pragma unroll
-      for (int o = 0; o < 3; ++o) {
-        const float t = __shfl_sync(0xffffffffu, r[o], (lane % PPW) * LPP);
-        if (lane / PPW == it) mine[o] = t;
-      }
+        for (int o = 0; o < 3; ++o) {
+          const float send = upper ? r[g][o] : r[g + bit][o];
+          const float keep = upper ? r[g + bit][o] : r[g][o];
+          r[g][o] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+#pragma unroll
+    for (int off = GRP; off < LPP; off <<= 1)
+#pragma unroll
+      for (int o = 0; o < 3; ++o) r[0][o] += __shfl_xor_sync(0xffffffffu, r[0][o], off);
+    // lane li keeps pass `li`: it is computed in the batch with it0 == (li rounded down to GRP)
+    if ((li & ~(GRP - 1)) == it0) {
+#pragma unroll
+      for (int o = 0; o < 3; ++o) mine[o] = r[0][o];
     }
   }
-  const int pix = pix0 + lane;
+  // lane (sub, li) owns the pixel of pass li: pix0 + li * PPW + sub
+  const int pix = pix0 + li * PPW + sub;
   if (pix < hw) {
     const int y = pix / w, x = pix - y * w;
 #pragma unroll
