@@ -30,7 +30,7 @@ for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
 METRIC = "attribution latent-opt steps/sec (images x guesses) at 1024px"
 # average DRAM bytes per conv launch (read + write) of the default workload, from the ncu capture summarised in
 # profiles/r01_conv_dram_traffic.md; None until that capture exists
-CONV_DRAM_BYTES_PER_LAUNCH = 9.365e+08
+CONV_DRAM_BYTES_PER_LAUNCH = 9.327e+08
 UNIT = "trajectory-steps/s"
 
 
