@@ -1152,7 +1152,10 @@ int launch_style_affine(const float* latent, const float* A, const float* bias, 
   return 0;
 }
 
-__global__ void __launch_bounds__(128) style_affine_bwd_kernel(const float* __restrict__ ds,
+// d_latent[b, slot, j] = sum over the rows r of the slot of ds[b, r] * A[r, j].  A CTA owns 32 columns; its eight warps walk
+// interleaved rows (r0 + w, r0 + w + 8, ...: a row of A is one 128-byte request per warp) with four independent
+// accumulators each, and the partial sums are added in a fixed order.
+__global__ void __launch_bounds__(256) style_affine_bwd_kernel(const float* __restrict__ ds,
                                                                const float* __restrict__ A,
                                                                const int* __restrict__ row_begin,
                                                                const int* __restrict__ row_end,
@@ -1160,24 +1163,40 @@ __global__ void __launch_bounds__(128) style_affine_bwd_kernel(const float* __re
                                                                const int* __restrict__ row_cin,
                                                                float* __restrict__ d_latent, int batch,
                                                                int n_latent, int dim) {
-  const int j = blockIdx.x * 128 + threadIdx.x;
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   const int slot = blockIdx.y, b = blockIdx.z;
-  if (j >= dim) return;
   const int r0 = row_begin[slot], r1 = row_end[slot];
-  float acc = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const int base = row_base[r];
-    acc = fmaf(__ldg(ds + (int64_t)batch * base + (int64_t)b * row_cin[r] + (r - base)), __ldg(A + (int64_t)r * dim + j), acc);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (j < dim) {
+    for (int rr = r0 + w; rr < r1; rr += 32) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rr + u * 8;
+        if (r < r1) {
+          const int base = row_base[r];
+          acc[u] = fmaf(__ldg(ds + (int64_t)batch * base + (int64_t)b * row_cin[r] + (r - base)), __ldg(A + (int64_t)r * dim + j), acc[u]);
+        }
+      }
+    }
   }
-  d_latent[((int64_t)b * n_latent + slot) * dim + j] = acc;
+  part[w][lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (w == 0 && j < dim) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    d_latent[((int64_t)b * n_latent + slot) * dim + j] = t;
+  }
 }
 
 int launch_style_affine_bwd(const float* ds, const float* A, const int* slot_row_begin,
                             const int* slot_row_end, const int* row_base, const int* row_cin,
                             float* d_latent, int batch, int rows, int n_latent, int dim,
                             cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(dim, 128), (unsigned)n_latent, (unsigned)batch);
-  style_affine_bwd_kernel<<<grid, 128, 0, st>>>(ds, A, slot_row_begin, slot_row_end, row_base, row_cin, d_latent, batch, n_latent, dim);
+  dim3 grid((unsigned)ceil_div(dim, 32), (unsigned)n_latent, (unsigned)batch);
+  style_affine_bwd_kernel<<<grid, 256, 0, st>>>(ds, A, slot_row_begin, slot_row_end, row_base, row_cin, d_latent, batch, n_latent, dim);
   LFP_LAUNCH_CHECK();
   return 0;
 }
