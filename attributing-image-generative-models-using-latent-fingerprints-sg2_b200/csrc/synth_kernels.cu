@@ -1083,25 +1083,34 @@ int launch_act_bwd(const ActBwdArgs& a, cudaStream_t s) {
   return 0;
 }
 
-// out[b, c] = sum_q partial[b*Q + q, c], fixed order (8 contiguous q-ranges, then 8 sums)
-__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ partial,
-                                                             float* __restrict__ out, int Q, int C,
-                                                             int64_t out_bstride) {
-  __shared__ float sm[8][32];
+// out[b, c] = sum_q partial[b*Q + q, c], fixed order: NR contiguous q-ranges (four independent accumulators each, combined
+// in a fixed tree), then the NR range sums in ascending order.  NR = 32 for the long reductions of the high-resolution
+// layers (Q up to 8192 tiles per sample), 8 otherwise.
+template <int NR>
+__global__ void __launch_bounds__(NR * 32) partial_reduce_kernel(const float* __restrict__ partial,
+                                                                 float* __restrict__ out, int Q, int C,
+                                                                 int64_t out_bstride) {
+  __shared__ float sm[NR][32];
   const int cx = threadIdx.x & 31, qy = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const int b = blockIdx.y;
-  const int per = (Q + 7) / 8;
+  const int per = (Q + NR - 1) / NR;
   const int q0 = qy * per, q1 = min(Q, q0 + per);
-  float acc = 0.f;
-  if (c < C)
-    for (int q = q0; q < q1; ++q) acc += __ldg(partial + ((int64_t)b * Q + q) * C + c);
-  sm[qy][cx] = acc;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < C) {
+    const float* p = partial + ((int64_t)b * Q + q0) * C + c;
+    int q = q0;
+    for (; q + 4 <= q1; q += 4, p += 4 * (int64_t)C) {
+      a0 += __ldg(p); a1 += __ldg(p + C); a2 += __ldg(p + 2 * (int64_t)C); a3 += __ldg(p + 3 * (int64_t)C);
+    }
+    for (; q < q1; ++q, p += C) a0 += __ldg(p);
+  }
+  sm[qy][cx] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (qy == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    for (int k = 0; k < NR; ++k) t += sm[k][cx];
     out[(int64_t)b * out_bstride + c] = t;
   }
 }
@@ -1109,7 +1118,8 @@ __global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __rest
 int launch_partial_reduce(const float* partial, float* out, int batch, int Q, int C, int64_t out_bstride,
                           cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)batch);
-  partial_reduce_kernel<<<grid, 256, 0, s>>>(partial, out, Q, C, out_bstride);
+  if (Q >= 256) partial_reduce_kernel<32><<<grid, 1024, 0, s>>>(partial, out, Q, C, out_bstride);
+  else partial_reduce_kernel<8><<<grid, 256, 0, s>>>(partial, out, Q, C, out_bstride);
   LFP_LAUNCH_CHECK();
   return 0;
 }
