@@ -144,6 +144,33 @@ class AttributionEngine:
                                             1 if st["optimise_alpha"] else 0, stream_ptr(self.device)), "attrib_adam_update")
         st["step"] = i + 1
 
+    STATE_KEYS = ("alpha", "key", "m_a", "v_a", "m_k", "v_k")
+
+    def host_state(self, st: dict) -> dict:
+        """Pinned host copy of a trajectory state (what a host-side caller of the step owns)."""
+        hs = {k: st[k].detach().cpu().pin_memory() for k in self.STATE_KEYS}
+        hs["loss"] = torch.zeros(st["alpha"].shape[0]).pin_memory()
+        hs["step"], hs["optimise_alpha"] = st["step"], st["optimise_alpha"]
+        return hs
+
+    def step_host(self, hs: dict, target: torch.Tensor, st: Optional[dict] = None) -> dict:
+        """One full Adam step with the trajectory state in HOST (pinned) buffers: H2D of alpha, key logits and the Adam
+        moments, embed -> synthesis forward -> loss -> synthesis backward -> Adam on the device, D2H of the updated
+        state and the per-trajectory loss; synchronous.  ``st`` (device buffers of the same shapes) is reused when
+        given.  This is the end-to-end call bench.py times as ``e2e``."""
+        if st is None:
+            st = {k: torch.empty(hs[k].shape, device=self.device) for k in self.STATE_KEYS}
+        for k in self.STATE_KEYS:
+            st[k].copy_(hs[k], non_blocking=True)
+        st["step"], st["optimise_alpha"] = hs["step"], hs["optimise_alpha"]
+        self.step(st, target)
+        for k in self.STATE_KEYS:
+            hs[k].copy_(st[k], non_blocking=True)
+        hs["loss"].copy_(st["loss"], non_blocking=True)
+        hs["step"] = st["step"]
+        torch.cuda.current_stream(self.device).synchronize()
+        return st
+
     def run(self, alpha0: torch.Tensor, target: torch.Tensor, steps: int, optimise_alpha: bool = True):
         st = self.init_state(alpha0, optimise_alpha)
         for _ in range(steps):

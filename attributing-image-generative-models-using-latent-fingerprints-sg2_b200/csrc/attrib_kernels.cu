@@ -162,10 +162,12 @@ __global__ void mse_final_kernel(const float* __restrict__ partial, float* __res
   loss[b] = acc * inv_n;
 }
 
+// Chunk count of the two-pass reduction.  It depends on numel_per ONLY (fixed chunk length of 16384 elements, at most
+// 2048 chunks): the summation order of a trajectory's loss must not change with the batch it runs in, otherwise near-tied
+// guesses could flip the per-image arg-min between differently sharded runs.  grid.y = batch supplies the parallelism.
 static int mse_chunks(int batch, int64_t numel_per) {
-  int64_t c = ceil_div((int64_t)num_sms() * 8, batch);
-  const int64_t maxc = ceil_div(numel_per, 4096);
-  if (c > maxc) c = maxc;
+  (void)batch;
+  int64_t c = ceil_div(numel_per, 16384);
   if (c < 1) c = 1;
   if (c > 2048) c = 2048;
   return (int)c;

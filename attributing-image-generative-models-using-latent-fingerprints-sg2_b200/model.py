@@ -15,6 +15,7 @@ Only CUDA tensors are accepted: there is no CPU fallback.
 """
 import math
 
+import numpy as np
 import torch
 from torch import nn
 from torch.nn import functional as F
@@ -219,6 +220,10 @@ class Generator(nn.Module):
 
     def __init__(self, size, style_dim, n_mlp, channel_multiplier=2, blur_kernel=[1, 3, 3, 1], lr_mlp=0.01):
         super().__init__()
+        # the reference reseeds the GLOBAL numpy RNG here (src/model.py:404); utils.get_noise() (src/utils.py:128-138)
+        # draws every noise map after the 4x4 from that global stream, so callers that build their noise the reference
+        # way get the reference's maps only if the constructor does the same
+        np.random.seed(2022)
         self.size, self.style_dim = size, style_dim
         self.channel_multiplier, self.blur_kernel = channel_multiplier, list(blur_kernel)
         self.style = nn.Sequential(PixelNorm(), *[

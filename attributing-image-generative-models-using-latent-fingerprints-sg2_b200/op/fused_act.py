@@ -44,8 +44,11 @@ def _native(x: torch.Tensor, bias, ref, act: int, grad: int, alpha: float, scale
 
 def _grad_bias(grad_input: torch.Tensor) -> torch.Tensor:
     """Sum over every dim but 1 (src/op/fused_act.py:34-40); deterministic native reduction in fp32."""
-    if grad_input.dtype != torch.float32 or grad_input.ndim < 2:
-        dims = [0] + list(range(2, grad_input.ndim))
+    dims = [0] + list(range(2, grad_input.ndim))
+    # the native reduction covers fp32, non-empty tensors and up to 65535 channels (its grid.y); everything else
+    # takes the reference's own expression, grad_input.sum(dim)
+    if (grad_input.dtype != torch.float32 or grad_input.ndim < 2 or grad_input.numel() == 0
+            or grad_input.shape[1] > 65535):
         return grad_input.sum(dims)
     outer, size_b = grad_input.shape[0], grad_input.shape[1]
     step_b = grad_input.numel() // max(outer * size_b, 1)

@@ -37,11 +37,12 @@ def build_generator(size, seed, cm=2):
 KINK_TOL = 5e-3   # free-running gradient tolerance (see module docstring)
 
 
-def grad_parity(size, seed, lat, noise, cm=2, precision=None, img_tol=1e-4, grad_tol=5e-5, flip_band=1e-4):
+def grad_parity(size, seed, lat, noise, cm=2, precision=None, img_tol=1e-4, grad_tol=5e-5, flip_band=1e-4, act_tol=None):
     """Plan-level forward/backward against the oracle with the CUDA path's lrelu branches imposed."""
     from lfp_native import capi
     from lfp_native.synthesis import SynthesisPlan
     precision = capi.PREC_FP32 if precision is None else precision
+    act_tol = img_tol if act_tol is None else act_tol
     params = fx.make_params(size, seed, cm)
     plan = SynthesisPlan(size, channel_multiplier=cm, device=DEV)
     plan.load(params)
@@ -57,12 +58,16 @@ def grad_parity(size, seed, lat, noise, cm=2, precision=None, img_tol=1e-4, grad
         ref = oracle.synthesis(params, lat, noise, activations=ref_acts)
     img_close(img.cpu().numpy(), ref.numpy(), img_tol)
     flips = 0
-    for a, r in zip(acts, ref_acts):
-        assert a.shape == r.shape
+    for li, (a, r) in enumerate(zip(acts, ref_acts)):
+        # per-layer comparison: a failure names the StyledConv (0 = conv1, 1 + i = convs.i) that first went wrong
+        assert a.shape == r.shape, f"conv {li}: shape {tuple(a.shape)} vs {tuple(r.shape)}"
+        scale = max(1.0, float(r.abs().max()))
+        err = float((a - r).abs().max())
+        assert err <= act_tol * scale, f"StyledConv {li} ({r.shape[1]} ch @ {r.shape[2]} px): max-abs {err:.3e} vs scale {scale:.3e}"
         diff = (a > 0) != (r > 0)
         flips += int(diff.sum())
         if diff.any():   # branches may differ only where the activation is numerically zero
-            assert float(r[diff].abs().max()) < flip_band * max(1.0, float(r.abs().max()))
+            assert float(r[diff].abs().max()) < flip_band * scale, f"StyledConv {li}: lrelu branch differs away from 0"
     # oracle with the CUDA path's branch pattern: arithmetic parity of the gradient
     lr = lat.clone().requires_grad_(True)
     refm = oracle.synthesis(params, lr, noise, sign_masks=[a > 0 for a in acts])
@@ -235,30 +240,50 @@ def test_tf32_batch_independence_is_bitwise_and_default_follows_cudnn_flag():
     img_close(img_tf.cpu().numpy(), img_fp.cpu().numpy(), 5e-3)
 
 
-def test_full_size_1024_tf32_against_fp32_path():
-    """BASELINE.json size (1024 px): the oracle is too slow here, so the tensor-core path is checked against the
-    fp32 CUDA-core path of the same library (itself oracle-checked up to 256 px) - image and per-slot latent gradient."""
+@pytest.mark.parametrize("size", [512, 1024])
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_full_size_oracle_parity(size, prec):
+    """The benchmarked sizes (BASELINE.json: 1024 px attribution, 512 px config 4) against the CPU oracle on both
+    arithmetic paths: image, every saved StyledConv activation (named per layer), leaky-ReLU branch pattern, and
+    the per-slot latent gradient with the CUDA path's branches imposed on the oracle.  These are the only
+    tests that reach the resident-weight C <= 64 tcgen05 instantiations, the NHWC ring FIR kernels, the ring
+    act_bwd kernel and the C = 64 / 32 ToRGB kernels (src/model.py:499-572 at full size).
+    Tolerances as stated in DESIGN.md section 2: fp32 1e-4 image / 5e-5 gradient; tf32 5e-3 / 1e-2."""
+    from lfp_native import capi
+    seed = 300 + size
+    noise = fx.make_noise(size, seed + 1)
+    lat = fx.seeded((1, oracle.n_latent(size), 512), seed + 2)
+    if prec == "fp32":
+        rel, flips = grad_parity(size, seed, lat, noise, cm=2, precision=capi.PREC_FP32)
+    else:
+        rel, flips = grad_parity(size, seed, lat, noise, cm=2, precision=capi.PREC_TF32, img_tol=5e-3, grad_tol=1e-2,
+                                 flip_band=2e-2)
+    print(f"{prec} size {size}: gradient rel err {rel:.2e}, {flips} branch flips")
+
+
+def test_full_size_1024_batched_equals_single_bitwise():
+    """B = 20 (the bench's batch) picks different slice widths / work distributions than B = 1 at the low
+    resolutions; the per-trajectory result must not depend on it (tensor-core path, 1024 px)."""
     from lfp_native import capi
     from lfp_native.synthesis import SynthesisPlan
-    size, seed, B = 1024, 77, 2
+    size, seed, B = 1024, 77, 3
     params = fx.make_params(size, seed)
     plan = SynthesisPlan(size, device=DEV)
     plan.load(params)
     noise = [n.to(DEV) for n in fx.make_noise(size, seed + 1)]
     lat = fx.seeded((B, plan.n_latent, 512), seed + 2).to(DEV)
     ct = fx.seeded((B, 3, size, size), seed + 3).to(DEV)
-    out = {}
-    for name, prec in (("fp32", capi.PREC_FP32), ("tf32", capi.PREC_TF32)):
-        ws = plan.new_workspace(B)
-        img = plan.forward(lat, noise, ws, prec).clone()
-        dl = plan.backward(ct, B, ws, prec).clone()
-        out[name] = (img, dl)
-        del ws
-    img_close(out["tf32"][0].cpu().numpy(), out["fp32"][0].cpu().numpy(), 5e-3)
-    g0, g1 = out["fp32"][1], out["tf32"][1]
-    rel = ((g0 - g1).flatten(2).norm(dim=2) / g0.flatten(2).norm(dim=2)).max()
-    assert float(rel) <= 8e-2, float(rel)   # free-running (kink flips included); imposed-branch bar is 1e-2 above
-    assert torch.isfinite(g1).all()
+    ws = plan.new_workspace(B)
+    img = plan.forward(lat, noise, ws, capi.PREC_TF32).clone()
+    dl = plan.backward(ct, B, ws, capi.PREC_TF32).clone()
+    del ws
+    ws1 = plan.new_workspace(1)
+    for b in (0, B - 1):
+        img1 = plan.forward(lat[b:b + 1].contiguous(), noise, ws1, capi.PREC_TF32)
+        assert torch.equal(img1[0], img[b])
+        dl1 = plan.backward(ct[b:b + 1].contiguous(), 1, ws1, capi.PREC_TF32)
+        assert torch.equal(dl1[0], dl[b])
+    assert torch.isfinite(dl).all()
 
 
 def test_interleaved_forwards_keep_backward_correct():
