@@ -11,8 +11,9 @@ Per step (src/main.py:58-70):
     est = G(wx, noise)                                                   lfp_synth_forward
     loss = MSE(target, est) + 0.1 * alpha_bound(alpha)                   lfp_mse_loss_grad, lfp_attrib_bound_loss
     backward to (alpha, key) + Adam(lr_i)                                lfp_synth_backward, lfp_attrib_adam_update
-The perceptual (LPIPS-VGG16) loss of the reference is outside this path (SURVEY.md 8f row 1);
-``loss="mse"`` is the reference's own alternative (src/utils.py:46-47).
+Losses (src/utils.py:44-50): ``loss="mse"`` is the reference's own MSE alternative (:46-47); ``loss="lpips"`` is its
+default perceptual loss, LPIPS v0.1 / VGG16, on the native kernels (lfp_lpips_*: target features cached per image,
+forward + backward to the image; backbone weights are whatever ``lpips_params`` holds - no pretrained VGG offline).
 """
 from __future__ import annotations
 
@@ -34,8 +35,18 @@ def get_lr(step: int, lr0: float = 0.2) -> float:
 class AttributionEngine:
     def __init__(self, plan: SynthesisPlan, noise: Sequence[torch.Tensor], pc: torch.Tensor,
                  sigma_512: torch.Tensor, latent_mean: torch.Tensor, key_len: int = 64, shift: int = 448,
-                 sigma: float = 1.0, sd: float = 1.0, lr: float = 0.2, precision: int = capi.PREC_FP32):
+                 sigma: float = 1.0, sd: float = 1.0, lr: float = 0.2, precision: int = capi.PREC_FP32,
+                 loss: str = "mse", lpips_params: Optional[dict] = None):
         self.plan, self.device = plan, plan.device
+        if loss not in ("mse", "lpips"):
+            raise ValueError(f"loss must be 'mse' or 'lpips', got {loss!r}")
+        self.loss_kind, self.lpips, self._lpips_target = loss, None, None
+        if loss == "lpips":
+            if lpips_params is None:
+                raise ValueError("loss='lpips' needs lpips_params (PNetLin state_dict: VGG16 convs + linear heads)")
+            from lfp_native.lpips import LpipsPlan
+            self.lpips = LpipsPlan(plan.size, plan.size, device=plan.device)
+            self.lpips.load(lpips_params)
         dev, f32 = self.device, torch.float32
         dim = pc.shape[0]
         self.dim, self.key_len, self.n_main = dim, key_len, dim - key_len
@@ -74,7 +85,7 @@ class AttributionEngine:
         """generate_image (src/generator.py:170-174) for B latents, no gradient kept."""
         B = wx.shape[0]
         latent = wx[:, None, :].expand(B, self.plan.n_latent, self.dim).contiguous()
-        return self.plan.forward(latent, self.noise, self.plan.shared_workspace(B), self.precision)
+        return self.plan.generate(latent, self.noise, self.precision)
 
     def loss_and_grad(self, wx: torch.Tensor, target: torch.Tensor):
         """MSE(target, G(wx)) per trajectory and its gradient w.r.t. wx.  target [1 or B, 3, S, S]."""
@@ -85,17 +96,29 @@ class AttributionEngine:
             self._ws = self.plan.new_workspace(B)
         latent = wx[:, None, :].expand(B, self.plan.n_latent, self.dim).contiguous()
         img = self.plan.forward(latent, self.noise, self._ws, self.precision)
-        numel = img[0].numel()
-        nb = L.lfp_mse_scratch_bytes(B, numel)
-        if self._mse_scratch is None or self._mse_scratch.numel() < nb:
-            self._mse_scratch = torch.empty(max(nb, 4), dtype=torch.uint8, device=self.device)
-        loss = torch.empty(B, device=self.device)
-        d_img = torch.empty_like(img)
-        capi.check(L.lfp_mse_loss_grad(ptr(img), ptr(target), target.shape[0], B, numel, ptr(loss), ptr(d_img),
-                                       ptr(self._mse_scratch), self._mse_scratch.numel(), stream_ptr(self.device)),
-                   "mse_loss_grad")
+        if self.loss_kind == "lpips":
+            key = (target.data_ptr(), target._version, tuple(target.shape), self.precision)
+            if key != self._lpips_target:      # the target's VGG features are computed once per image (and arithmetic)
+                self.lpips.set_target(target, self.precision)
+                self._lpips_target = key
+            loss, d_img = self.lpips.loss_grad(img, self.precision)
+        else:
+            numel = img[0].numel()
+            nb = L.lfp_mse_scratch_bytes(B, numel)
+            if self._mse_scratch is None or self._mse_scratch.numel() < nb:
+                self._mse_scratch = torch.empty(max(nb, 4), dtype=torch.uint8, device=self.device)
+            loss = torch.empty(B, device=self.device)
+            d_img = torch.empty_like(img)
+            capi.check(L.lfp_mse_loss_grad(ptr(img), ptr(target), target.shape[0], B, numel, ptr(loss), ptr(d_img),
+                                           ptr(self._mse_scratch), self._mse_scratch.numel(), stream_ptr(self.device)),
+                       "mse_loss_grad")
         d_latent = self.plan.backward(d_img, B, self._ws, self.precision)
-        return loss, d_latent.sum(1), img
+        # backward of the repeat over the latent slots (src/model.py:531-535): ascending-slot sum, the order the native
+        # step (slot_sum_kernel) uses, so that both drivers give the same bits
+        d_wx = d_latent[:, 0].clone()
+        for slot in range(1, d_latent.shape[1]):
+            d_wx += d_latent[:, slot]
+        return loss, d_wx, img
 
     def loss_and_grad_host(self, wx_host: torch.Tensor, target: torch.Tensor, loss_host: torch.Tensor,
                            dwx_host: torch.Tensor) -> None:
@@ -153,17 +176,21 @@ class AttributionEngine:
         hs["step"], hs["optimise_alpha"] = st["step"], st["optimise_alpha"]
         return hs
 
-    def step_host(self, hs: dict, target: torch.Tensor, st: Optional[dict] = None) -> dict:
+    def step_host(self, hs: dict, target: torch.Tensor, st: Optional[dict] = None, stepper=None) -> dict:
         """One full Adam step with the trajectory state in HOST (pinned) buffers: H2D of alpha, key logits and the Adam
         moments, embed -> synthesis forward -> loss -> synthesis backward -> Adam on the device, D2H of the updated
         state and the per-trajectory loss; synchronous.  ``st`` (device buffers of the same shapes) is reused when
-        given.  This is the end-to-end call bench.py times as ``e2e``."""
+        given; ``stepper`` (a NativeStepper bound to ``st``) runs the step as one graph launch.  This is the
+        end-to-end call bench.py times as ``e2e``."""
         if st is None:
             st = {k: torch.empty(hs[k].shape, device=self.device) for k in self.STATE_KEYS}
         for k in self.STATE_KEYS:
             st[k].copy_(hs[k], non_blocking=True)
         st["step"], st["optimise_alpha"] = hs["step"], hs["optimise_alpha"]
-        self.step(st, target)
+        if stepper is not None:      # ``st`` must be the state the stepper is bound to
+            stepper.run(1)
+        else:
+            self.step(st, target)
         for k in self.STATE_KEYS:
             hs[k].copy_(st[k], non_blocking=True)
         hs["loss"].copy_(st["loss"], non_blocking=True)
@@ -171,8 +198,19 @@ class AttributionEngine:
         torch.cuda.current_stream(self.device).synchronize()
         return st
 
-    def run(self, alpha0: torch.Tensor, target: torch.Tensor, steps: int, optimise_alpha: bool = True):
+    def native_stepper(self, st: dict, target: torch.Tensor, max_steps: int = 4096) -> "NativeStepper":
+        """Bind ``st`` and ``target`` to the native whole-step (lfp_attrib_*, CUDA-graph replay)."""
+        return NativeStepper(self, st, target, max_steps)
+
+    def run(self, alpha0: torch.Tensor, target: torch.Tensor, steps: int, optimise_alpha: bool = True,
+            native: bool = True):
+        """``steps`` Adam steps from ``alpha0`` (src/main.py:51-81 for every trajectory of the batch).  ``native``: the
+        whole step is one captured CUDA graph replayed per step; otherwise every step is driven from Python through the
+        same kernels (bit-identical results, tests/test_attribution_gpu.py)."""
         st = self.init_state(alpha0, optimise_alpha)
+        if native and steps > 0 and self.loss_kind == "mse":   # the captured step covers the MSE loss
+            self.native_stepper(st, target, max_steps=max(steps, 1)).run(steps)
+            return st
         for _ in range(steps):
             self.step(st, target)
         return st
@@ -181,3 +219,61 @@ class AttributionEngine:
     def decode(key_logits: torch.Tensor) -> torch.Tensor:
         """``round(sigmoid(key))`` (src/main.py:72)."""
         return torch.round(torch.sigmoid(key_logits))
+
+
+class NativeStepper:
+    """One trajectory batch bound to the native whole-step (include/lfp_sg2.h group 6).  ``run(n)`` enqueues ``n`` Adam
+    steps: the first eagerly, the rest as replays of one captured CUDA graph, on a private stream that is ordered after
+    and before the caller's current stream.  ``st`` is updated in place (``alpha``, ``key``, moments, ``loss``, ``step``)."""
+
+    def __init__(self, eng: AttributionEngine, st: dict, target: torch.Tensor, max_steps: int = 4096):
+        import ctypes as C
+        self.eng, self.st, self.device = eng, st, eng.device
+        L = capi.lib()
+        B = st["alpha"].shape[0]
+        self.B = B
+        self.target = target.to(self.device, torch.float32).contiguous()
+        self.loss = torch.zeros(B, device=self.device)
+        self._h = C.c_void_p()
+        self.max_steps = max_steps + st["step"]
+        with torch.cuda.device(self.device):
+            capi.check(L.lfp_attrib_create(C.byref(self._h), eng.plan._h, eng.plan.size, B, eng.n_main, eng.key_len, eng.dim,
+                                           ptr(eng.U), ptr(eng.V), ptr(eng.sigma_key), ptr(eng.mu), ptr(eng.max_alpha),
+                                           ptr(eng.min_alpha), eng.sd, 0.1, eng.lr0, self.max_steps, eng.precision), "attrib_create")
+            nbytes = int(L.lfp_attrib_workspace_bytes(self._h))
+            self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self.ws.data_ptr() + 255) // 256 * 256
+            nz = eng.noise
+            self._nptr = (C.c_void_p * len(nz))(*[n.data_ptr() for n in nz])
+            self._nb = (C.c_int * len(nz))(*[n.shape[0] for n in nz])
+            capi.check(L.lfp_attrib_bind(self._h, self._nptr, self._nb, ptr(self.target), self.target.shape[0], ptr(st["alpha"]),
+                                         ptr(st["key"]), ptr(st["m_a"]), ptr(st["v_a"]), ptr(st["m_k"]), ptr(st["v_k"]),
+                                         ptr(self.loss), 1 if st["optimise_alpha"] else 0, base,
+                                         self.ws.data_ptr() + self.ws.numel() - base), "attrib_bind")
+            self.stream = torch.cuda.Stream(self.device)
+            self._dev_step = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                torch.cuda.synchronize(self.device)
+                capi.lib().lfp_attrib_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def run(self, steps: int, graph: bool = True) -> None:
+        L = capi.lib()
+        st = self.st
+        if st["step"] + steps > self.max_steps:
+            raise RuntimeError(f"stepper was created for {self.max_steps} steps; asked to run to {st['step'] + steps}")
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.device(self.device):
+            if self._dev_step != st["step"]:     # the host-side step index was changed behind the stepper (e.g. step_host)
+                capi.check(L.lfp_attrib_set_step(self._h, st["step"], self.stream.cuda_stream), "attrib_set_step")
+            capi.check(L.lfp_attrib_run(self._h, steps, 1 if graph else 0, self.stream.cuda_stream), "attrib_run")
+        cur.wait_stream(self.stream)
+        st["step"] += steps
+        self._dev_step = st["step"]
+        st["loss"] = self.loss

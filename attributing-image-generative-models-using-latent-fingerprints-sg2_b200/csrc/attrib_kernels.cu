@@ -91,12 +91,17 @@ __global__ void __launch_bounds__(256) adam_update_kernel(const float* __restric
                                                           float* __restrict__ v_a, float* __restrict__ m_k,
                                                           float* __restrict__ v_k, int n_main, int key_len, int dim,
                                                           float step_size, float sqrt_bc2, float beta1, float beta2,
-                                                          float omb1, float omb2, float eps, int optimise_alpha) {
+                                                          float omb1, float omb2, float eps, int optimise_alpha,
+                                                          const float2* __restrict__ hyper, const int* __restrict__ step_ptr) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int b = blockIdx.y;
   if (row >= n_main + key_len) return;
   if (row < n_main && !optimise_alpha) return;
+  if (hyper != nullptr) {   // graph-replayed step: the schedule scalars of step *step_ptr come from a device table
+    const float2 hp = hyper[*step_ptr];
+    step_size = hp.x; sqrt_bc2 = hp.y;
+  }
   const float* mrow = row < n_main ? U + (int64_t)row * dim : V + (int64_t)(row - n_main) * dim;
   float acc = 0.f;
   for (int j = lane; j < dim; j += 32) acc = fmaf(__ldg(mrow + j), __ldg(d_wx + (int64_t)b * dim + j), acc);
@@ -222,10 +227,26 @@ extern "C" int lfp_attrib_adam_update(const float* d_wx, float* alpha, float* ke
   adam_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_wx, alpha, key_logits, U, V, sigma_key, max_alpha, min_alpha, sd,
                                                              bound_weight, m_alpha, v_alpha, m_key, v_key, n_main, key_len, dim,
                                                              step_size, sqrt_bc2, beta1, beta2, one_minus_beta1, one_minus_beta2, eps,
-                                                             optimise_alpha);
+                                                             optimise_alpha, nullptr, nullptr);
   LFP_LAUNCH_CHECK();
   return 0;
 }
+
+namespace lfp {
+// same kernel with step_size / sqrt_bc2 read from hyper[*step_ptr] (device memory): what a captured CUDA graph replays
+int launch_adam_update_dev(const float* d_wx, float* alpha, float* key_logits, const float* U, const float* V, const float* sigma_key,
+                           const float* max_alpha, const float* min_alpha, float sd, float bound_weight, float* m_alpha, float* v_alpha,
+                           float* m_key, float* v_key, int batch, int n_main, int key_len, int dim, const float2* hyper,
+                           const int* step_ptr, float beta1, float beta2, float omb1, float omb2, float eps, int optimise_alpha,
+                           cudaStream_t s) {
+  dim3 grid((unsigned)ceil_div(n_main + key_len, 8), (unsigned)batch);
+  adam_update_kernel<<<grid, 256, 0, s>>>(d_wx, alpha, key_logits, U, V, sigma_key, max_alpha, min_alpha, sd, bound_weight, m_alpha,
+                                          v_alpha, m_key, v_key, n_main, key_len, dim, 0.f, 1.f, beta1, beta2, omb1, omb2, eps,
+                                          optimise_alpha, hyper, step_ptr);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace lfp
 
 extern "C" size_t lfp_mse_scratch_bytes(int batch, int64_t numel_per) {
   if (batch <= 0 || numel_per <= 0) return 0;

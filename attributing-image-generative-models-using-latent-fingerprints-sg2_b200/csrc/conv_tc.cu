@@ -46,8 +46,9 @@ constexpr int A_BYTES = A_ROWS * 128;     // 23040
 constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
 constexpr int MAX_SA = 8, MAX_SB = 12;
 // warp 0 TMA, warp 1 MMA, warps 2-5 transform (or a third epilogue set when there is nothing to transform),
-// warps 6-9 / 10-13 epilogue sets, warps 14-17 a third epilogue set of the modulated (forward) kernels
-constexpr int NTHREADS_MOD = 576, NTHREADS_PLAIN = 448;
+// warps 6-9 / 10-13 epilogue sets; warps 14-15 of the modulated (forward) kernels only pad the block to 512 threads
+constexpr int NTHREADS_MOD = 512, NTHREADS_PLAIN = 480;   // both are charged as 512 threads: 128 registers
+constexpr int MMA2_WARP = 14;                              // second MMA issuer (tiles alternate between warps 1 and 14)
 constexpr int MAX_ACC = 4;                // TMEM accumulator stages
 constexpr int MAX_XS = 4;                 // stages of the saved-input (xsave) tile ring of the data-gradient epilogues
 constexpr int XS_CHUNK = 128 * 128;       // one 128-pixel x 32-channel tile
@@ -69,6 +70,7 @@ struct Args {
   int XS, xs_off;             // xsave ring: stages (0 = epilogue reads xsave from global) and byte offset in dynamic smem
   int xs_bcast;
   int nsets;                  // epilogue warp sets (2, or 3 when the transform warps are free and smem allows)
+  int nissue;                 // MMA-issuing warps (1 or 2): tile i of a CTA is issued by warp i % nissue
   int in_bcast;
   TcTaps taps;
   float* out;
@@ -171,13 +173,20 @@ __device__ __forceinline__ Work decode(const Args& a, int w) {
 // Persistent: CTA c processes work items c, c + gridDim.x, ...  (consecutive CTAs work on neighbouring
 // tiles at the same time, so halo rows and weight slices are L2 hits).
 template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
+// Register budget: the register file is handed out to a CTA in units of four warps, so a 576-thread block is charged as
+// 640 threads and gets 96 registers per thread.  At 96 the epilogues spilled to local memory - and with (almost) all of
+// the SM's memory carved out as shared memory there is no L1 behind a spill: every STL / LDL was an L2 round trip (ncu:
+// 30 % of the epilogue warps' stall samples on the 32 -> 32 layer at 1024 px were long-scoreboard waits on them, and
+// the spill store of a prefetched noise value waited for the very load it was meant to overlap).  Both layouts therefore
+// stay at <= 512 threads = 128 registers: the modulated kernels run two epilogue sets instead of three.
 __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmX, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[NBARS];
   __shared__ uint32_t tmem_base_s;
-  constexpr bool DG = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
+  constexpr bool DG = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;     // style-gradient reductions
+  constexpr bool DGX = DG || EPI == EPI_DGRAD_RELU;                  // epilogue reads the layer's saved forward input
   constexpr int NRED = EPI == EPI_DGRAD_ACT ? 3 : 1;   // column reductions per tile
 
 
@@ -235,26 +244,38 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
           for (int kc = 0; kc < kchunks; ++kc)
             tma_load_2d(b_base + (uint32_t)(t * kchunks + kc) * b_slice_bytes, &tmB, bar_b_all, kc * 32, (int)a.taps.widx[t] * a.N);
       }
-      int sa = 0, sb = 0, sx = 0;
-      uint32_t pa = 0, pb = 0, px = 0;
-      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+      // With two MMA issuers the A (and B) stages form two rings, one per issuer: tile i of the CTA uses ring i & 1.  A
+      // parity wait is only meaningful within one phase of its barrier, so an issuer must be the only consumer of the
+      // slots it waits on (an issuer skipping over the other's stages of a shared ring would see an earlier phase of the
+      // same parity as "its" data).
+      // (scalars with selects, not arrays indexed by `ring`: a dynamically indexed array lives in local memory)
+      int sa_0 = 0, sa_1 = 0, sb_0 = 0, sb_1 = 0, sx = 0;
+      uint32_t pa_0 = 0, pa_1 = 0, pb_0 = 0, pb_1 = 0, px = 0;
+      const int SAr = SA / a.nissue, SBr = RES ? 0 : SB / a.nissue;
+      int it = 0;
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++it) {
         const Work wk = decode(a, w);
         const int bin = a.in_bcast ? 0 : wk.b;
+        const int ring = a.nissue == 2 ? (it & 1) : 0;
+        int sa = ring ? sa_1 : sa_0, sb = ring ? sb_1 : sb_0;
+        uint32_t pa = ring ? pa_1 : pa_0, pb = ring ? pb_1 : pb_0;
+        const int a0 = ring * SAr, b0 = ring * SBr;
         for (int kc = 0; kc < kchunks; ++kc)
           for (int g = 0; g < ngroups; ++g) {
-            mbar_wait(bar_a_empty(sa), pa ^ 1u);
-            mbar_expect_tx(bar_a_full(sa), A_BYTES);
-            tma_load_5d(a_base + sa * A_STAGE, &tmA, bar_a_full(sa), kc * 32, wk.x0 - 1, wk.y0 - 1, a.taps.group_plane[g], bin);
+            mbar_wait(bar_a_empty(a0 + sa), pa ^ 1u);
+            mbar_expect_tx(bar_a_full(a0 + sa), A_BYTES);
+            tma_load_5d(a_base + (a0 + sa) * A_STAGE, &tmA, bar_a_full(a0 + sa), kc * 32, wk.x0 - 1, wk.y0 - 1, a.taps.group_plane[g], bin);
             if (!RES)
               for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
-                mbar_wait(bar_b_empty(sb), pb ^ 1u);
-                mbar_expect_tx(bar_b_full(sb), b_slice_bytes);
-                tma_load_2d(b_base + sb * b_slice_bytes, &tmB, bar_b_full(sb), kc * 32, (int)a.taps.widx[t] * a.N + wk.n0);
-                if (++sb == SB) { sb = 0; pb ^= 1u; }
+                mbar_wait(bar_b_empty(b0 + sb), pb ^ 1u);
+                mbar_expect_tx(bar_b_full(b0 + sb), b_slice_bytes);
+                tma_load_2d(b_base + (b0 + sb) * b_slice_bytes, &tmB, bar_b_full(b0 + sb), kc * 32, (int)a.taps.widx[t] * a.N + wk.n0);
+                if (++sb == SBr) { sb = 0; pb ^= 1u; }
               }
-            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            if (++sa == SAr) { sa = 0; pa ^= 1u; }
           }
-        if (DG && a.XS > 0) {
+        if (ring) { sa_1 = sa; sb_1 = sb; pa_1 = pa; pb_1 = pb; } else { sa_0 = sa; sb_0 = sb; pa_0 = pa; pb_0 = pb; }
+        if (DGX && a.XS > 0) {
           // saved forward input of this tile for the epilogue (128 px x BN channels, one 16 KB box per 32 channels)
           const int nch = a.BN >> 5;
           mbar_wait(bar_xs_empty(sx), px ^ 1u);
@@ -266,8 +287,12 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 1 || warp == MMA2_WARP) {
+    // ---------------- MMA issuer(s) ----------------
+    // Two issuing warps take alternate tiles of the CTA: the per-tile serial part of one (barrier waits, descriptor set-up,
+    // the commit) overlaps the other's issue, so the tensor pipe's queue does not drain between tiles.  A tile's MMAs all
+    // come from one thread (in order, into its own accumulator stage); its A / B stages are the contiguous range of the
+    // producer's sequence that belongs to it.
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / commit.
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -275,8 +300,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     const uint32_t b_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_lo0 = (a_base >> 4) | 0x10000u, b_lo0 = (b_base >> 4) | 0x10000u;
     const uint32_t b_slice16 = b_slice_bytes >> 4;
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
+    const int issuer = warp == 1 ? 0 : 1;
     // per-tap descriptor offsets (16-byte units), kept in registers: the issue loop below is fully unrolled
     uint32_t tap_a[9], tap_b[9], tap_p[9];
     const int nphase = a.taps.nphase;
@@ -288,9 +312,14 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       tap_b[t] = b_lo0 + (uint32_t)(tt * kchunks) * b_slice16;
       tap_p[t] = nphase > 1 ? (uint32_t)a.taps.acc[tt] : 0u;
     }
-    if (RES) mbar_wait(bar_b_all, 0);
-    int it = 0;
-    for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++it) {
+    if (RES && issuer < a.nissue) mbar_wait(bar_b_all, 0);
+    // this issuer's own rings (see the producer): slots [a0, a0 + SAr) and [b0, b0 + SBr), consumed in order
+    const int SAr = SA / a.nissue, SBr = RES ? 0 : SB / a.nissue;
+    const int a0 = issuer * SAr, b0 = issuer * SBr;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int it = issuer;
+    for (int w = issuer < a.nissue ? blockIdx.x + issuer * gridDim.x : a.total_work; w < a.total_work; w += a.nissue * gridDim.x, it += a.nissue) {
       const int as = it & (a.nacc - 1);
       mbar_wait(bar_acc_empty(as), (((uint32_t)it >> acc_shift) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -298,9 +327,9 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       uint32_t started = 0;   // bit p: accumulator p of this tile has received its first MMA
       for (int kc = 0; kc < kchunks; ++kc)
         for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(MOD ? bar_a_ready(sa) : bar_a_full(sa), pa);
+          mbar_wait(MOD ? bar_a_ready(a0 + sa) : bar_a_full(a0 + sa), pa);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_stage_lo = a_lo0 + (uint32_t)sa * (A_STAGE >> 4);
+          const uint32_t a_stage_lo = a_lo0 + (uint32_t)(a0 + sa) * (A_STAGE >> 4);
           const int t0 = a.taps.group_tap0[g], t1 = a.taps.group_tap0[g + 1];
           if (RES) {
             // weights resident: every MMA of this activation stage is issued in one elected region
@@ -317,7 +346,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
                   started |= 1u << tap_p[t];
                 }
-              umma_commit(bar_a_empty(sa));
+              umma_commit(bar_a_empty(a0 + sa));
             }
             __syncwarp();
             started = (1u << nphase) - 1u;   // every accumulator has taps in every activation stage
@@ -325,9 +354,9 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
 #pragma unroll
             for (int t = 0; t < 9; ++t)
               if (t >= t0 && t < t1) {
-                mbar_wait(bar_b_full(sb), pb);
+                mbar_wait(bar_b_full(b0 + sb), pb);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)sb * b_slice16;
+                const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)(b0 + sb) * b_slice16;
                 const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
                 const uint32_t accumulate = (started >> tap_p[t]) & 1u;
                 if (elect_one()) {
@@ -335,16 +364,16 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
-                  umma_commit(bar_b_empty(sb));
+                  umma_commit(bar_b_empty(b0 + sb));
                 }
                 __syncwarp();
                 started |= 1u << tap_p[t];
-                if (++sb == SB) { sb = 0; pb ^= 1u; }
+                if (++sb == SBr) { sb = 0; pb ^= 1u; }
               }
-            if (elect_one()) umma_commit(bar_a_empty(sa));
+            if (elect_one()) umma_commit(bar_a_empty(a0 + sa));
             __syncwarp();
           }
-          if (++sa == SA) { sa = 0; pa ^= 1u; }
+          if (++sa == SAr) { sa = 0; pa ^= 1u; }
         }
       if (elect_one()) umma_commit(bar_acc_full(as));
       __syncwarp();
@@ -353,11 +382,16 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     if (MOD) {
       // ---------------- A transform: x * s[b, k], rounded to tf32 ----------------
       const int et = tid - 64;  // 0..127
-      int sa = 0;
-      uint32_t pa = 0;
-      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x) {
+      int sa_0 = 0, sa_1 = 0;
+      uint32_t pa_0 = 0, pa_1 = 0;
+      const int SAr = SA / a.nissue;
+      int it = 0;
+      for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++it) {
         const Work wk = decode(a, w);
         const float* sm = a.mod + (int64_t)wk.b * a.K;
+        const int ring = a.nissue == 2 ? (it & 1) : 0;   // the producer's ring of this tile
+        int sa_rel = ring ? sa_1 : sa_0, sa = ring * SAr + sa_rel;
+        uint32_t pa = ring ? pa_1 : pa_0;
         for (int kc = 0; kc < kchunks; ++kc)
           for (int g = 0; g < ngroups; ++g) {
             mbar_wait(bar_a_full(sa), pa);
@@ -382,10 +416,14 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_a_ready(sa));
-            if (++sa == SA) { sa = 0; pa ^= 1u; }
+            ++sa;
+            if (++sa_rel == SAr) { sa_rel = 0; sa = ring * SAr; pa ^= 1u; }
           }
+        if (ring) { sa_1 = sa_rel; pa_1 = pa; } else { sa_0 = sa_rel; pa_0 = pa; }
       }
     }
+  } else if (warp >= MMA2_WARP) {
+    // padding warp of the 512-thread modulated layout: nothing to do
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     // two sets of four warps alternate tiles, so one tile's operand-load / store latency overlaps the next tile
@@ -458,7 +496,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             outp[r] = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
                                (gx * a.out_stride + a.out_ox)) * a.N + n0;
         }
-        const bool xs_smem2 = DG && a.XS > 0;
+        const bool xs_smem2 = DGX && a.XS > 0;
         const int sx = xs_smem2 ? it % a.XS : 0;
         // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x
         const uint8_t* xbase = smem_al + a.xs_off + (size_t)sx * nchunk * XS_CHUNK + (32 * q + x) * 128 + (cq & 1) * 8;
@@ -467,7 +505,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           xg[r] = nullptr;
-          if (DG && !xs_smem2 && valid[r])
+          if (DGX && !xs_smem2 && valid[r])
             xg[r] = a.e.xsave + (int64_t)b * a.e.xsave_bstride + ((int64_t)(wk.y0 + 4 * q + r) * a.gw + gx) * a.N + n0;
         }
         float rgbacc[4][3];
@@ -541,6 +579,20 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                     rgbacc[r][1] = fmaf(o0, q1.x, fmaf(o1, q1.y, rgbacc[r][1]));
                     rgbacc[r][2] = fmaf(o0, q2.x, fmaf(o1, q2.y, rgbacc[r][2]));
                   }
+                }
+              } else if (EPI == EPI_RELU) {
+                const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + n0 + ch));
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(fmaxf(av(r, 0) + b2.x, 0.f), fmaxf(av(r, 1) + b2.y, 0.f));
+              } else if (EPI == EPI_DGRAD_RELU) {
+                const int j16 = (c * 8 + 2 * k + (cq >> 1));
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  float2 x2 = make_float2(0.f, 0.f);
+                  if (xs_smem2) x2 = *reinterpret_cast<const float2*>(xbase + (size_t)c * XS_CHUNK + r * 8 * 128 + (((j16 & 7) ^ x) << 4));
+                  else if (xg[r]) x2 = __ldg(reinterpret_cast<const float2*>(xg[r] + ch));
+                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(x2.x > 0.f ? av(r, 0) : 0.f, x2.y > 0.f ? av(r, 1) : 0.f);
                 }
               } else {
                 const float2 m2 = __ldg(reinterpret_cast<const float2*>(a.e.mod_out + bn));
@@ -661,7 +713,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     const int wstep = a.nsets * gridDim.x;
     float nz_n, rg0_n, rg1_n, rg2_n;
     fetch(blockIdx.x + eset * gridDim.x, nz_n, rg0_n, rg1_n, rg2_n);
-    const bool xs_smem = DG && a.XS > 0;
+    const bool xs_smem = DGX && a.XS > 0;
     const int nchunk = a.BN >> 5;
     int it = eset;
     for (int w = eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work; w < a.total_work; w += wstep, it += a.nsets) {
@@ -679,7 +731,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                         (gx * a.out_stride + a.out_ox)) * a.N + n0;
       float* const outp = outp0;
       const float* xs = nullptr;
-      if (DG && valid && !xs_smem) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
+      if (DGX && valid && !xs_smem) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
       // saved-input tile in shared memory (TMA, SWIZZLE_128B): pixel m is row m, channel quad j at position j ^ (m & 7)
       const int sx = xs_smem ? it % a.XS : 0;
       const uint8_t* xrow = smem_al + a.xs_off + (size_t)sx * nchunk * XS_CHUNK + m * 128;
@@ -753,6 +805,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               *reinterpret_cast<float4*>(outp + c * 32 + j * 4) =
                   make_float4(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
                               __uint_as_float(r[j * 4 + 3]));
+        } else if (EPI == EPI_RELU || EPI == EPI_DGRAD_RELU) {
+          // the VGG epilogues exist in the 16x256b form only (tc_launch2 refuses them when LFP_TC_E2=0)
         } else if (EPI == EPI_DGRAD) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -964,6 +1018,7 @@ static bool tc_use_e2(int bn) {
 template <int EPI, bool MOD, bool RES>
 static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
   const bool e2 = tc_use_e2(a.BN);
+  LFP_CHECK_ARG(e2 || (EPI != EPI_RELU && EPI != EPI_DGRAD_RELU), "conv_tc: the ReLU epilogues need the 16x256b epilogue (LFP_TC_E2=0 is set)");
   return e2 ? tc_launch3<EPI, MOD, RES, true>(tmA, tmB, tmX, a, dyn_smem, s) : tc_launch3<EPI, MOD, RES, false>(tmA, tmB, tmX, a, dyn_smem, s);
 }
 
@@ -974,19 +1029,45 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // an epilogue set that finished tile i waits next for tile i + nsets; the parity wait on that TMEM stage is only
   // unambiguous when the stage's previous use (tile i + nsets - nacc) is already known to be complete, i.e.
   // nsets <= nacc (BN = 256 leaves room for two accumulator stages only)
-  a.nsets = a.BN <= 128 ? 3 : 2;
-  constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT;
+  a.nsets = (a.BN <= 128 && !MOD) ? 3 : 2;   // the modulated kernels have two epilogue sets (512-thread layout)
+  constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT || EPI == EPI_DGRAD_RELU;
   // data-gradient epilogues of the HBM-bound layers (N <= 64) get their saved-input tiles through a TMA ring
   const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : 0;
   size_t xs_smem = 0, epi_smem = 0;
-  for (int xs = xs_max;; --xs) {
+  // LFP_TC_SMEM_CAP (bytes): cap the shared memory a launch asks for, which leaves the rest of the 228 KB to the L1
+  static const size_t smem_cap = getenv("LFP_TC_SMEM_CAP") ? (size_t)atol(getenv("LFP_TC_SMEM_CAP")) : (size_t)tc::SMEM_OPTIN;
+  const size_t optin = smem_cap < (size_t)tc::SMEM_OPTIN && smem_cap >= 98304 ? smem_cap : (size_t)tc::SMEM_OPTIN;
+  const int nsets0 = a.nsets;
+  // LFP_TC_PREFER_RES=1: make the whole weight slice resident first, giving up saved-input ring stages (down to none: the
+  // epilogue then reads the saved input from global memory) for it.  Measured on the N <= 64 data-gradient layers at
+  // 512 / 1024 px: no gain - 64 -> 64 at 512 px takes 1.43 ms either way (with the ring the weights stream, 147 KB per
+  // tile; without it ncu shows 43 % of all stall samples on the epilogue's global loads of the saved input), and the
+  // stride-2 32 -> 64 layer loses 6 % with a two-stage ring.  So the round-1 order (ring first) stays the default.
+  static const bool prefer_res = getenv("LFP_TC_PREFER_RES") && atoi(getenv("LFP_TC_PREFER_RES")) != 0;
+  bool planned = false;
+  if (prefer_res && a.n_ntiles == 1)
+    for (int xs = xs_max; xs >= 0 && !planned; --xs) {
+      if (xs == 1) continue;                       // a one-stage ring serialises the epilogue sets
+      int nsets = nsets0;
+      if (xs > 0 && nsets > xs) nsets = xs;
+      const size_t xsm = (size_t)xs * (a.BN / 32) * tc::XS_CHUNK;
+      const size_t epi = tc::EPI_SMEM(EPI, nsets, a.BN, tc_use_e2(a.BN)) + xsm;
+      if (optin < tc::STATIC_SMEM_RESERVE + 1024 + epi) continue;
+      const size_t budget = optin - tc::STATIC_SMEM_RESERVE - 1024 - epi;
+      if (b_all + 3 * (size_t)tc::A_STAGE <= budget) {
+        a.XS = xs; a.nsets = nsets; xs_smem = xsm; epi_smem = epi;
+        a.b_resident = 1; a.SB = 0; a.SA = (int)((budget - b_all) / tc::A_STAGE);
+        planned = true;
+      }
+    }
+  for (int xs = xs_max; !planned; --xs) {
     a.XS = xs;
     // same parity argument for the saved-input ring: a set may only wait on stage (i + nsets) % XS when the stage's
     // previous use (tile i + nsets - XS) is one it has already seen complete, i.e. nsets <= XS
     if (xs > 0 && a.nsets > xs) a.nsets = xs;
     xs_smem = (size_t)xs * (a.BN / 32) * tc::XS_CHUNK;
     epi_smem = tc::EPI_SMEM(EPI, a.nsets, a.BN, tc_use_e2(a.BN)) + xs_smem;
-    const size_t budget = (size_t)tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE - 1024 - epi_smem;
+    const size_t budget = optin - tc::STATIC_SMEM_RESERVE - 1024 - epi_smem;
     if (a.n_ntiles == 1 && b_all + 3 * (size_t)tc::A_STAGE <= budget) {
       a.b_resident = 1; a.SB = 0;
       a.SA = (int)((budget - b_all) / tc::A_STAGE);
@@ -1000,8 +1081,22 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     if ((a.SA >= 3 && (a.b_resident || a.SB >= 3)) || xs <= (xs_max > 0 ? 2 : 0)) break;
   }
   if (a.SA > tc::MAX_SA) a.SA = tc::MAX_SA;
+  // resident-weight launches: more than five activation stages buy nothing, while keeping the request under the 196 KB
+  // carve-out leaves 32 KB of L1 for the per-pixel noise / skip-gradient rows every tile re-reads (32 -> 32 at 1024 px:
+  // 1649 -> 1396 us with six stages instead of eight)
+  if (a.b_resident && smem_cap >= (size_t)tc::SMEM_OPTIN) {
+    const size_t fixed = (size_t)b_all + epi_smem + 1024 + tc::STATIC_SMEM_RESERVE;
+    while (a.SA > 5 && fixed + (size_t)a.SA * tc::A_STAGE > 196u * 1024u) --a.SA;
+  }
+  if (const char* e = getenv("LFP_TC_SA_MAX")) { const int v = atoi(e); if (v >= 2 && a.SA > v) a.SA = v; }
   a.nacc = a.BN * a.taps.nphase <= 128 ? 4 : (a.BN * a.taps.nphase <= 256 ? 2 : 1);
   if (a.nsets > a.nacc) a.nsets = a.nacc;
+  // LFP_TC_ISSUE=2 turns the second MMA-issuing warp on (needs two accumulator stages and two stages per ring).  Measured
+  // on the 1024 px step, B = 20, same box: forward convolutions 7.6 -> 8.6 ms, data gradients unchanged - each issuer gets
+  // half of the activation stages, and the shallower prefetch costs more than the overlapped per-tile issue overhead
+  // gains - so the default stays one issuer.
+  static const int issue_env = getenv("LFP_TC_ISSUE") ? atoi(getenv("LFP_TC_ISSUE")) : 1;
+  a.nissue = (a.nacc >= 2 && issue_env >= 2 && a.SA >= 4 && (a.b_resident || a.SB >= 4)) ? 2 : 1;   // >= 2 stages per ring
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
   // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
   a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
@@ -1045,7 +1140,8 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   const bool mod = c.mod != nullptr;
   if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_ACT, false>(tmA, tmB, tmA, a, ntaps, s);
   if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_STORE, false>(tmA, tmB, tmA, a, ntaps, s);
-  LFP_CHECK_ARG(!mod, "conv_tc: the data-gradient kernel takes an unmodulated input");
+  LFP_CHECK_ARG(!mod, "conv_tc: this epilogue takes an unmodulated input");
+  if (c.epi == EPI_RELU) return tc_launch<EPI_RELU, false>(tmA, tmB, tmA, a, ntaps, s);
   // saved forward input [B or 1, gh, gw, N]: 128-pixel x 32-channel boxes for the epilogue
   alignas(64) CUtensorMap tmX;
   a.xs_bcast = c.e.xsave_bstride == 0 ? 1 : 0;
@@ -1057,6 +1153,7 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
     LFP_TRY(tc::encode(&tmX, c.e.xsave, 5, xd, xst, xbox));
   }
   if (c.epi == EPI_DGRAD_ACT) return tc_launch<EPI_DGRAD_ACT, false>(tmA, tmB, tmX, a, ntaps, s);
+  if (c.epi == EPI_DGRAD_RELU) return tc_launch<EPI_DGRAD_RELU, false>(tmA, tmB, tmX, a, ntaps, s);
   return tc_launch<EPI_DGRAD, false>(tmA, tmB, tmX, a, ntaps, s);
 }
 

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvKArgs a) {
     bias4 = __ldg(reinterpret_cast<const float4*>(a.e.bias + n));
     nw = __ldg(a.e.noise_w);
   }
+  if (EPI == EPI_RELU && n_ok) bias4 = __ldg(reinterpret_cast<const float4*>(a.e.bias + n));
 #pragma unroll
   for (int r = 0; r < TMR; ++r) {
     const int64_t p = tile0 + tm * TMR + r;
@@ -156,6 +157,11 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvKArgs a) {
       const float4 xs = __ldg(reinterpret_cast<const float4*>(a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)rem * N + n));
       red = f4_fma4(xs, v, red);
       v = f4_mul(v, __ldg(reinterpret_cast<const float4*>(a.e.mod_out + (int64_t)b * N + n)));
+    } else if (EPI == EPI_RELU) {
+      v.x = fmaxf(v.x + bias4.x, 0.f); v.y = fmaxf(v.y + bias4.y, 0.f); v.z = fmaxf(v.z + bias4.z, 0.f); v.w = fmaxf(v.w + bias4.w, 0.f);
+    } else if (EPI == EPI_DGRAD_RELU) {
+      const float4 xs = __ldg(reinterpret_cast<const float4*>(a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)rem * N + n));
+      v.x = xs.x > 0.f ? v.x : 0.f; v.y = xs.y > 0.f ? v.y : 0.f; v.z = xs.z > 0.f ? v.z : 0.f; v.w = xs.w > 0.f ? v.w : 0.f;
     }
     if (a.out != nullptr) {
       const int oy = gy * g.out_stride + g.out_oy, ox = gx * g.out_stride + g.out_ox;
@@ -208,13 +214,19 @@ int launch_conv_simt(const float* in, const float* mod, const float* wtab, float
   const int TN = g.N >= 64 ? 64 : 32;
   dim3 grid((unsigned)ceil_div(total_pix, 128), (unsigned)ceil_div(g.N, TN));
   const bool m = mod != nullptr;
+  LFP_CHECK_ARG(epi == EPI_STORE || epi == EPI_ACT || epi == EPI_DGRAD || epi == EPI_RELU || epi == EPI_DGRAD_RELU,
+                "conv: epilogue %d is not available on the CUDA-core kernel", epi);
   if (TN == 64) {
     if (epi == EPI_STORE) return conv_simt_launch2<64, EPI_STORE>(ka, m, grid, s);
     if (epi == EPI_ACT) return conv_simt_launch2<64, EPI_ACT>(ka, m, grid, s);
+    if (epi == EPI_RELU) return conv_simt_launch2<64, EPI_RELU>(ka, m, grid, s);
+    if (epi == EPI_DGRAD_RELU) return conv_simt_launch2<64, EPI_DGRAD_RELU>(ka, m, grid, s);
     return conv_simt_launch2<64, EPI_DGRAD>(ka, m, grid, s);
   }
   if (epi == EPI_STORE) return conv_simt_launch2<32, EPI_STORE>(ka, m, grid, s);
   if (epi == EPI_ACT) return conv_simt_launch2<32, EPI_ACT>(ka, m, grid, s);
+  if (epi == EPI_RELU) return conv_simt_launch2<32, EPI_RELU>(ka, m, grid, s);
+  if (epi == EPI_DGRAD_RELU) return conv_simt_launch2<32, EPI_DGRAD_RELU>(ka, m, grid, s);
   return conv_simt_launch2<32, EPI_DGRAD>(ka, m, grid, s);
 }
 
@@ -1162,42 +1174,48 @@ int launch_style_affine(const float* latent, const float* A, const float* bias, 
   return 0;
 }
 
-// d_latent[b, slot, j] = sum over the rows r of the slot of ds[b, r] * A[r, j].  A CTA owns 32 columns; its eight warps walk
-// interleaved rows (r0 + w, r0 + w + 8, ...: a row of A is one 128-byte request per warp) with four independent
-// accumulators each, and the partial sums are added in a fixed order.
-__global__ void __launch_bounds__(256) style_affine_bwd_kernel(const float* __restrict__ ds,
-                                                               const float* __restrict__ A,
-                                                               const int* __restrict__ row_begin,
-                                                               const int* __restrict__ row_end,
-                                                               const int* __restrict__ row_base,
-                                                               const int* __restrict__ row_cin,
-                                                               float* __restrict__ d_latent, int batch,
-                                                               int n_latent, int dim) {
-  __shared__ float part[8][32];
+// d_latent[b, slot, j] = sum over the rows r of the slot of ds[b, r] * A[r, j], eight samples per CTA: a row of A is read
+// once for the eight (it was read once per sample: 20 x 12 MB through L2 per step).  Same per-sample summation order as
+// style_affine_bwd_kernel: warp w walks rows r0 + w + 8u (u < 4) + 32i with one accumulator per u.
+__global__ void __launch_bounds__(256) style_affine_bwd8_kernel(const float* __restrict__ ds, const float* __restrict__ A,
+                                                                const int* __restrict__ row_begin, const int* __restrict__ row_end,
+                                                                const int* __restrict__ row_base, const int* __restrict__ row_cin,
+                                                                float* __restrict__ d_latent, int batch, int n_latent, int dim) {
+  __shared__ float part[8][8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
-  const int slot = blockIdx.y, b = blockIdx.z;
+  const int slot = blockIdx.y, b0 = blockIdx.z * 8;
+  const int nb = min(8, batch - b0);
   const int r0 = row_begin[slot], r1 = row_end[slot];
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[8][4];
+#pragma unroll
+  for (int bb = 0; bb < 8; ++bb)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[bb][u] = 0.f;
   if (j < dim) {
     for (int rr = r0 + w; rr < r1; rr += 32) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int r = rr + u * 8;
         if (r < r1) {
-          const int base = row_base[r];
-          acc[u] = fmaf(__ldg(ds + (int64_t)batch * base + (int64_t)b * row_cin[r] + (r - base)), __ldg(A + (int64_t)r * dim + j), acc[u]);
+          const int base = row_base[r], cin = row_cin[r];
+          const float av = __ldg(A + (int64_t)r * dim + j);
+          const float* dsr = ds + (int64_t)batch * base + (int64_t)b0 * cin + (r - base);
+#pragma unroll
+          for (int bb = 0; bb < 8; ++bb)
+            if (bb < nb) acc[bb][u] = fmaf(__ldg(dsr + (int64_t)bb * cin), av, acc[bb][u]);
         }
       }
     }
   }
-  part[w][lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+  for (int bb = 0; bb < 8; ++bb) part[bb][w][lane] = (acc[bb][0] + acc[bb][1]) + (acc[bb][2] + acc[bb][3]);
   __syncthreads();
-  if (w == 0 && j < dim) {
+  if (w < nb && j < dim) {   // warp w finishes sample b0 + w
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][lane];
-    d_latent[((int64_t)b * n_latent + slot) * dim + j] = t;
+    for (int k = 0; k < 8; ++k) t += part[w][k][lane];
+    d_latent[((int64_t)(b0 + w) * n_latent + slot) * dim + j] = t;
   }
 }
 
@@ -1205,8 +1223,8 @@ int launch_style_affine_bwd(const float* ds, const float* A, const int* slot_row
                             const int* slot_row_end, const int* row_base, const int* row_cin,
                             float* d_latent, int batch, int rows, int n_latent, int dim,
                             cudaStream_t st) {
-  dim3 grid((unsigned)ceil_div(dim, 32), (unsigned)n_latent, (unsigned)batch);
-  style_affine_bwd_kernel<<<grid, 256, 0, st>>>(ds, A, slot_row_begin, slot_row_end, row_base, row_cin, d_latent, batch, n_latent, dim);
+  dim3 grid((unsigned)ceil_div(dim, 32), (unsigned)n_latent, (unsigned)ceil_div(batch, 8));
+  style_affine_bwd8_kernel<<<grid, 256, 0, st>>>(ds, A, slot_row_begin, slot_row_end, row_base, row_cin, d_latent, batch, n_latent, dim);
   LFP_LAUNCH_CHECK();
   return 0;
 }
@@ -1271,6 +1289,110 @@ int launch_style_grad(const float* r1, const float* s, int64_t s_bstride, const 
                       int cin, int cout, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(cin, 32), (unsigned)batch);
   style_grad_kernel<<<grid, 256, 0, st>>>(r1, s, s_bstride, T, d, d_bstride, wsq, ds, cin, cout);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =============================================================================================
+// Batched forms: every reduction / style-gradient / demodulation of a pass in ONE launch each.
+// Items live in device memory and address the workspace by float offsets, so a table depends on the
+// plan, the batch and the kernel choices only (built once per configuration by the plan).
+// The per-(sample, channel) summation orders are exactly those of the single-layer kernels above.
+// =============================================================================================
+__global__ void __launch_bounds__(1024) batched_partial_reduce_kernel(const ReduceItem* __restrict__ items,
+                                                                      const int2* __restrict__ blocks,
+                                                                      float* __restrict__ ws) {
+  __shared__ float sm[32][32];
+  const int2 blk = blocks[blockIdx.x];
+  const ReduceItem it = items[blk.x];
+  const int NR = it.Q >= 256 ? 32 : 8;
+  const int cx = threadIdx.x & 31, qy = threadIdx.x >> 5;
+  const int c = blk.y * 32 + cx;
+  const int b = blockIdx.y;
+  const int Q = it.Q, C = it.C;
+  const int per = (Q + NR - 1) / NR;
+  const int q0 = qy * per, q1 = min(Q, q0 + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < C && qy < NR) {
+    const float* p = ws + it.src_off + ((int64_t)b * Q + q0) * C + c;
+    int q = q0;
+    for (; q + 4 <= q1; q += 4, p += 4 * (int64_t)C) {
+      a0 += __ldg(p); a1 += __ldg(p + C); a2 += __ldg(p + 2 * (int64_t)C); a3 += __ldg(p + 3 * (int64_t)C);
+    }
+    for (; q < q1; ++q, p += C) a0 += __ldg(p);
+  }
+  sm[qy][cx] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (qy == 0 && c < C) {
+    float t = 0.f;
+    for (int k = 0; k < NR; ++k) t += sm[k][cx];
+    ws[it.dst_off + (int64_t)b * C + c] = t;
+  }
+}
+
+int launch_batched_partial_reduce(const ReduceItem* items, const int2* blocks, int nblocks, float* ws, int batch, cudaStream_t s) {
+  if (nblocks == 0) return 0;
+  batched_partial_reduce_kernel<<<dim3((unsigned)nblocks, (unsigned)batch), 1024, 0, s>>>(items, blocks, ws);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) batched_style_grad_kernel(const GradItem* __restrict__ items, const int2* __restrict__ blocks,
+                                                                 float* __restrict__ ws) {
+  __shared__ float part[8][32];
+  const int2 blk = blocks[blockIdx.x];
+  const GradItem it = items[blk.x];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ci = blk.y * 32 + lane;
+  const int b = blockIdx.y;
+  const float* T = ws + it.T_off + (int64_t)b * it.cout;
+  const float* d = ws + it.d_off + (int64_t)b * it.cout;
+  float acc = 0.f;
+  if (ci < it.cin)
+    for (int co = w; co < it.cout; co += 8) {
+      const float dv = d[co];
+      acc = fmaf(T[co] * dv * dv, __ldg(it.wsq + (int64_t)co * it.cin + ci), acc);
+    }
+  part[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && ci < it.cin) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    const int64_t i = (int64_t)b * it.cin + ci;
+    ws[it.ds_off + i] = ws[it.r1_off + i] - ws[it.s_off + i] * t;
+  }
+}
+
+int launch_batched_style_grad(const GradItem* items, const int2* blocks, int nblocks, float* ws, int batch, cudaStream_t s) {
+  if (nblocks == 0) return 0;
+  batched_style_grad_kernel<<<dim3((unsigned)nblocks, (unsigned)batch), 256, 0, s>>>(items, blocks, ws);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) batched_demod_kernel(const DemodItem* __restrict__ items, const int2* __restrict__ blocks,
+                                                            float* __restrict__ ws) {
+  const int2 blk = blocks[blockIdx.x];
+  const DemodItem it = items[blk.x];
+  const int lane = threadIdx.x & 31;
+  const int co = blk.y * 8 + (threadIdx.x >> 5);
+  const int b = blockIdx.y;
+  if (co >= it.cout) return;
+  const float* s = ws + it.s_off + (int64_t)b * it.cin;
+  float acc = 0.f;
+  for (int ci = lane; ci < it.cin; ci += 32) {
+    const float sv = s[ci];
+    acc = fmaf(sv * sv, __ldg(it.wsq + (int64_t)co * it.cin + ci), acc);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) ws[it.d_off + (int64_t)b * it.cout + co] = rsqrtf(acc + 1e-8f);
+}
+
+int launch_batched_demod(const DemodItem* items, const int2* blocks, int nblocks, float* ws, int batch, cudaStream_t s) {
+  if (nblocks == 0) return 0;
+  batched_demod_kernel<<<dim3((unsigned)nblocks, (unsigned)batch), 256, 0, s>>>(items, blocks, ws);
   LFP_LAUNCH_CHECK();
   return 0;
 }

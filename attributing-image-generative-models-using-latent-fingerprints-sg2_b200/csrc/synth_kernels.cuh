@@ -34,6 +34,9 @@ enum ConvEpilogue {
   // that produced xsave (what act_bwd_kernel does as a separate pass): out = gpre*demod, partial_T, partial_R.
   // Tensor-core kernel only.
   EPI_DGRAD_ACT = 3,
+  // plain (unmodulated) convolution layers of the perceptual loss's VGG16 backbone (src/custom_lpips/pretrained_networks.py:97-135):
+  EPI_RELU = 4,        // max(acc + bias[n], 0)
+  EPI_DGRAD_RELU = 5,  // acc * (xsave > 0): data gradient through the ReLU that produced this layer's input
 };
 
 struct ConvEpiArgs {
@@ -142,6 +145,15 @@ int launch_act_bwd(const ActBwdArgs& a, cudaStream_t s);
 // out[b, c] = sum_{q<Q} partial[b*Q+q, c]   (fixed order -> deterministic)
 int launch_partial_reduce(const float* partial, float* out, int batch, int Q, int C, int64_t out_bstride,
                           cudaStream_t s);
+
+// Batched forms (one launch per pass): items address the workspace `ws` by float offsets.
+struct ReduceItem { int64_t src_off, dst_off; int Q, C; };                     // dst[b, c] = sum_q src[b*Q + q, c]
+struct GradItem { int64_t r1_off, s_off, T_off, d_off, ds_off; const float* wsq; int cin, cout; };   // launch_style_grad
+struct DemodItem { int64_t s_off, d_off; const float* wsq; int cin, cout; };   // launch_demod
+// blocks[i] = (item, 32-channel block (reduce, style-grad) or 8-channel block (demod)); grid = (nblocks, batch)
+int launch_batched_partial_reduce(const ReduceItem* items, const int2* blocks, int nblocks, float* ws, int batch, cudaStream_t s);
+int launch_batched_style_grad(const GradItem* items, const int2* blocks, int nblocks, float* ws, int batch, cudaStream_t s);
+int launch_batched_demod(const DemodItem* items, const int2* blocks, int nblocks, float* ws, int batch, cudaStream_t s);
 
 // s[b, r] = sum_j latent[b, slot[r], j] * A[r, j] + bias[r]      (src/model.py:151-161, 258)
 // s is stored per modulation unit as compact [B, cin] blocks: element (b, r) lives at

@@ -6,6 +6,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -47,19 +49,36 @@ struct ConvLayer {
   bool tc_fwd = false, tc_bwd = false;
   int row0 = 0;       // first row in the stacked modulation matrix
   int demod_off = 0;  // offset into the demod table (units of cout, times batch at run time)
-  size_t act_off = 0; // workspace offset (floats) of the saved output activation
 };
 struct RgbLayer {
   std::string name;
   int cin = 0, res = 0, slot = 0;
   float *W = nullptr, *modw = nullptr, *modb = nullptr, *bias = nullptr, *wrgb = nullptr;
   int row0 = 0;
-  size_t skip_off = 0;
 };
 
+// Workspace layout for one batch size (float offsets).  Full layout: every StyledConv output is kept for the backward,
+// and every layer owns its partial-sum regions so that all reductions of a backward pass can run in one launch at its end.
+// Forward-only layout (generation, no backward): activations and skip images ping-pong between two buffers.
 struct Layout {
-  size_t s_all, d_all, scratchT, bufA, bufB, dskipA, dskipB, pT, pR, pX, T_all, R1_all, ds_all, total;
+  size_t s_all = 0, d_all = 0, scratchT = 0, bufA = 0, bufB = 0, dskipA = 0, dskipB = 0, T_all = 0, R1_all = 0, ds_all = 0, total = 0;
+  std::vector<size_t> act_off, skip_off;      // per conv layer / per ToRGB layer
+  std::vector<size_t> pX_off, pT_off, pR_off; // per conv layer: dgrad style partials, act-backward partials (T and ToRGB R)
 };
+
+// what one backward pass does per conv layer for a given precision (decided once, used by the launch loop and by the
+// builder of the batched-reduction tables)
+struct BwdStep { bool use_tc = false, fuse = false; int Qx = 0, QT = 0; };
+
+// device tables of the batched kernels for one (batch, precision)
+struct Tables {
+  ReduceItem* ritems = nullptr; int2* rblocks = nullptr; int nrblocks = 0;
+  GradItem* gitems = nullptr; int2* gblocks = nullptr; int ngblocks = 0;
+  DemodItem* ditems = nullptr; int2* dblocks = nullptr; int ndblocks = 0;
+};
+
+// forward bookkeeping per workspace: the backward validates against the workspace it is given
+struct FwdRec { int batch = -1, precision = -1; bool fwd_only = false; std::vector<const float*> noise; std::vector<int> noise_batch; };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -86,10 +105,12 @@ struct lfp_synth {
   bool fuse_rgb = false;     // ToRGB inside the forward conv epilogue on the tensor-core path (env LFP_FUSE_RGB=1 enables;
                              // measured slower than the separate kernel: the epilogue is the longer pole at N <= 64)
   bool fuse_actbwd = true;   // run act_bwd inside the upstream dgrad epilogue on the tensor-core path (env LFP_FUSE_ACTBWD=0 disables)   // smallest output grid the tensor-core kernel is used for (env LFP_TC_MIN_RES)
-  int fwd_batch = -1;
-  std::vector<const float*> fwd_noise;
-  std::vector<int> fwd_noise_batch;
+  std::mutex mu;                              // guards the caches below (a plan may be shared by host threads)
+  std::map<const void*, FwdRec> fwd_recs;     // last forward per workspace
+  std::map<long long, Tables> tables;         // key = batch * 8 + precision * 2 + forward-only
   std::vector<void*> owned;
+  // grow-only device buffers of the host-pointer entry point (no allocation per call)
+  struct HostBufs { void* p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; size_t cap[5] = {0, 0, 0, 0, 0}; std::vector<void*> noise; std::vector<size_t> noise_cap; } hb;
 
   // optional per-kernel-class timing with CUDA events on the launching stream
   bool prof_on = false;
@@ -105,6 +126,8 @@ struct lfp_synth {
 
   ~lfp_synth() {
     for (void* p : owned) cudaFree(p);
+    for (int i = 0; i < 5; ++i) if (hb.p[i]) cudaFree(hb.p[i]);
+    for (void* p : hb.noise) if (p) cudaFree(p);
     for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   }
   bool prof_begin(int kind, double flops, double bytes, cudaStream_t s) {
@@ -147,53 +170,130 @@ struct lfp_synth {
     }
     return 0;
   }
-  Layout layout(int B) const;
+  Layout layout(int B, bool fwd_only = false) const;
+  std::vector<BwdStep> bwd_steps(int precision) const;
+  int get_tables(int B, int precision, const Layout& L, const std::vector<BwdStep>& st, const Tables** out);
 };
 
-Layout lfp_synth::layout(int B) const {
-  Layout L{};
+Layout lfp_synth::layout(int B, bool fwd_only) const {
+  Layout L;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off = align_up(off + n, 64); return o; };
   L.s_all = take((size_t)B * rows);
   L.d_all = take((size_t)B * demod_total);
-  size_t max_act = 0, max_T = 0, max_pT = 0, max_pX = 0;
+  size_t max_act = 0, max_T = 0;
   for (const ConvLayer& c : convs) {
     const size_t n = (size_t)B * c.res_out * c.res_out * c.cout;
-    const_cast<ConvLayer&>(c).act_off = take(n);
     if (n > max_act) max_act = n;
     const size_t nin = (size_t)B * c.res_in * c.res_in * c.cin;
     if (nin > max_act) max_act = nin;
     if (c.up) {
-      // interleaved [2H+1, 2H+1] (fp32 path) or phase-major [4, H+1, H+1] (tensor-core path)
+      // interleaved [2H+1, 2H+1] (fp32 path, fused phases) or phase-major [4, H+1, H+1] (tensor-core path)
       const size_t t = (size_t)B * (c.res_out + 2) * (c.res_out + 2) * c.cout;
       if (t > max_T) max_T = t;
     }
-    const int hw = c.res_out * c.res_out;
-    const size_t pt = (size_t)B * (hw / actbwd_seglen(hw, c.cout)) * c.cout;
-    if (pt > max_pT) max_pT = pt;
-    const int hwi = c.res_in * c.res_in;
-    size_t px = (size_t)B * (hwi / (hwi < 128 ? hwi : 128)) * c.cin;
-    const size_t px_tc = (size_t)B * tc_tiles_per_sample(c.res_in, c.res_in) * c.cin;
-    if (px_tc > px) px = px_tc;
-    if (px > max_pX) max_pX = px;
   }
-  for (size_t i = 0; i < rgbs.size(); ++i)
-    const_cast<RgbLayer&>(rgbs[i]).skip_off = take((size_t)B * 3 * rgbs[i].res * rgbs[i].res);
   L.scratchT = take(max_T);
   L.bufA = take(max_act);
   L.bufB = take(max_act);
+  L.act_off.resize(convs.size());
+  L.skip_off.resize(rgbs.size());
+  if (fwd_only) {
+    // layer li reads the output of li - 1 and writes its own: two buffers; the skip image likewise
+    for (size_t li = 0; li < convs.size(); ++li) L.act_off[li] = (li & 1) ? L.bufB : L.bufA;
+    const size_t full = (size_t)B * 3 * size * size;
+    const size_t s0 = take(full), s1 = take(full);
+    for (size_t ri = 0; ri < rgbs.size(); ++ri) L.skip_off[ri] = (ri & 1) ? s1 : s0;
+    L.total = off;
+    return L;
+  }
+  for (size_t li = 0; li < convs.size(); ++li)
+    L.act_off[li] = take((size_t)B * convs[li].res_out * convs[li].res_out * convs[li].cout);
+  for (size_t ri = 0; ri < rgbs.size(); ++ri) L.skip_off[ri] = take((size_t)B * 3 * rgbs[ri].res * rgbs[ri].res);
   const size_t half = (size_t)B * 3 * (size / 2) * (size / 2);
   L.dskipA = take(half);
   L.dskipB = take(half);
-  if (max_pX > max_pT) max_pT = max_pX;
-  L.pT = take(max_pT);
-  L.pR = take(max_pT);
-  L.pX = take(max_pX);
+  L.pX_off.resize(convs.size()); L.pT_off.resize(convs.size()); L.pR_off.resize(convs.size());
+  for (size_t li = 0; li < convs.size(); ++li) {
+    const ConvLayer& c = convs[li];
+    const int hw = c.res_out * c.res_out, hwi = c.res_in * c.res_in;
+    // rows per sample: the larger of what the CUDA-core and the tensor-core kernels write
+    int qx = hwi / (hwi < 128 ? hwi : 128);
+    const int qx_tc = tc_tiles_per_sample(c.res_in, c.res_in);
+    if (qx_tc > qx) qx = qx_tc;
+    int qt = hw / actbwd_seglen(hw, c.cout);
+    const int qt_tc = tc_tiles_per_sample(c.res_out, c.res_out);
+    if (qt_tc > qt) qt = qt_tc;
+    L.pX_off[li] = take((size_t)B * qx * c.cin);
+    L.pT_off[li] = take((size_t)B * qt * c.cout);
+    L.pR_off[li] = (li == 0 || (li % 2) == 0) ? take((size_t)B * qt * c.cout) : 0;
+  }
   L.T_all = take((size_t)B * demod_total);
   L.R1_all = take((size_t)B * rows);
   L.ds_all = take((size_t)B * rows);
   L.total = off;
   return L;
+}
+
+std::vector<BwdStep> lfp_synth::bwd_steps(int precision) const {
+  std::vector<BwdStep> st(convs.size());
+  for (size_t li = 0; li < convs.size(); ++li) {
+    const ConvLayer& c = convs[li];
+    const int hwi = c.res_in * c.res_in;
+    st[li].use_tc = precision == LFP_PREC_TF32 && c.tc_bwd && c.res_in >= tc_min_res;
+    st[li].fuse = st[li].use_tc && li >= 1 && fuse_actbwd;
+    st[li].Qx = st[li].use_tc ? tc_tiles_per_sample(c.res_in, c.res_in) : hwi / (hwi < 128 ? hwi : 128);
+  }
+  for (size_t li = 0; li < convs.size(); ++li) {
+    const ConvLayer& c = convs[li];
+    const int hw = c.res_out * c.res_out;
+    const bool from_above = li + 1 < convs.size() && st[li + 1].fuse;   // the dgrad of the layer above ran this layer's act backward
+    st[li].QT = from_above ? st[li + 1].Qx : hw / actbwd_seglen(hw, c.cout);
+  }
+  return st;
+}
+
+template <class T>
+static int upload(std::vector<void*>& owned, const std::vector<T>& v, T** out) {
+  *out = nullptr;
+  if (v.empty()) return 0;
+  LFP_CUDA(cudaMalloc((void**)out, v.size() * sizeof(T)));
+  owned.push_back(*out);
+  LFP_CUDA(cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int lfp_synth::get_tables(int B, int precision, const Layout& L, const std::vector<BwdStep>& st, const Tables** out) {
+  std::lock_guard<std::mutex> lock(mu);
+  const long long key = (long long)B * 8 + precision * 2 + (L.pX_off.empty() ? 1 : 0);
+  auto it = tables.find(key);
+  if (it != tables.end()) { *out = &it->second; return 0; }
+  std::vector<ReduceItem> ri; std::vector<int2> rb;
+  std::vector<GradItem> gi; std::vector<int2> gb;
+  std::vector<DemodItem> di; std::vector<int2> db;
+  auto add_reduce = [&](size_t src, size_t dst, int Q, int C) {
+    ri.push_back(ReduceItem{(int64_t)src, (int64_t)dst, Q, C});
+    for (int cb = 0; cb < (C + 31) / 32; ++cb) rb.push_back(make_int2((int)ri.size() - 1, cb));
+  };
+  for (size_t li = 0; li < convs.size(); ++li) {
+    const ConvLayer& c = convs[li];
+    di.push_back(DemodItem{(int64_t)(L.s_all + (size_t)B * c.row0), (int64_t)(L.d_all + (size_t)B * c.demod_off), c.wsq, c.cin, c.cout});
+    for (int cb = 0; cb < (c.cout + 7) / 8; ++cb) db.push_back(make_int2((int)di.size() - 1, cb));
+    if (L.pX_off.empty()) continue;   // forward-only layout has no backward tables
+    add_reduce(L.pX_off[li], L.R1_all + (size_t)B * c.row0, st[li].Qx, c.cin);
+    add_reduce(L.pT_off[li], L.T_all + (size_t)B * c.demod_off, st[li].QT, c.cout);
+    if (li == 0 || (li % 2) == 0) add_reduce(L.pR_off[li], L.ds_all + (size_t)B * rgbs[li / 2].row0, st[li].QT, c.cout);
+    gi.push_back(GradItem{(int64_t)(L.R1_all + (size_t)B * c.row0), (int64_t)(L.s_all + (size_t)B * c.row0),
+                          (int64_t)(L.T_all + (size_t)B * c.demod_off), (int64_t)(L.d_all + (size_t)B * c.demod_off),
+                          (int64_t)(L.ds_all + (size_t)B * c.row0), c.wsq, c.cin, c.cout});
+    for (int cb = 0; cb < (c.cin + 31) / 32; ++cb) gb.push_back(make_int2((int)gi.size() - 1, cb));
+  }
+  Tables t;
+  LFP_TRY(upload(owned, ri, &t.ritems)); LFP_TRY(upload(owned, rb, &t.rblocks)); t.nrblocks = (int)rb.size();
+  LFP_TRY(upload(owned, gi, &t.gitems)); LFP_TRY(upload(owned, gb, &t.gblocks)); t.ngblocks = (int)gb.size();
+  LFP_TRY(upload(owned, di, &t.ditems)); LFP_TRY(upload(owned, db, &t.dblocks)); t.ndblocks = (int)db.size();
+  *out = &(tables[key] = t);
+  return 0;
 }
 
 extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int channel_multiplier,
@@ -389,6 +489,10 @@ extern "C" size_t lfp_synth_workspace_bytes(const lfp_synth* h, int batch) {
   if (!h || batch <= 0) return 0;
   return h->layout(batch).total * sizeof(float);
 }
+extern "C" size_t lfp_synth_generate_workspace_bytes(const lfp_synth* h, int batch) {
+  if (!h || batch <= 0) return 0;
+  return h->layout(batch, true).total * sizeof(float);
+}
 
 static void plain_taps(ConvGeom& g) {  // out[y,x] += in[y+ky-1, x+kx-1] * W[ky,kx]
   g.ntaps = 9;
@@ -396,39 +500,41 @@ static void plain_taps(ConvGeom& g) {  // out[y,x] += in[y+ky-1, x+kx-1] * W[ky,
     for (int kx = 0; kx < 3; ++kx) { const int t = ky * 3 + kx; g.dy[t] = (signed char)(ky - 1); g.dx[t] = (signed char)(kx - 1); g.widx[t] = (signed char)t; }
 }
 
-static int check_run(const lfp_synth* h, int batch, const void* ws, size_t ws_bytes, int precision) {
+static int check_run(const lfp_synth* h, int batch, const void* ws, size_t ws_bytes, int precision, const Layout& L) {
   LFP_CHECK_ARG(h != nullptr && ws != nullptr, "synth: null plan or workspace");
   LFP_CHECK_ARG(batch >= 1 && batch <= 65535, "synth: batch %d out of range", batch);
   if (!h->finalized) { set_error("synth: lfp_synth_finalize has not been called since the last set_param"); return LFP_ESTATE; }
-  if (ws_bytes < h->layout(batch).total * sizeof(float)) { set_error("synth: workspace too small (%zu < %zu bytes)", ws_bytes, h->layout(batch).total * sizeof(float)); return LFP_ENOMEM; }
+  if (ws_bytes < L.total * sizeof(float)) { set_error("synth: workspace too small (%zu < %zu bytes)", ws_bytes, L.total * sizeof(float)); return LFP_ENOMEM; }
   LFP_CHECK_ARG(((uintptr_t)ws & 255) == 0, "synth: workspace must be 256-byte aligned");
   if (precision != LFP_PREC_FP32 && precision != LFP_PREC_TF32) { set_error("synth: unknown precision mode %d", precision); return LFP_EINVAL; }
   return 0;
 }
 
-extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, const float* const* noise,
-                                 const int* noise_batch, float* image, void* workspace, size_t workspace_bytes,
-                                 int precision, void* stream) {
-  LFP_TRY(check_run(h, batch, workspace, workspace_bytes, precision));
+static int synth_forward_impl(lfp_synth* h, int batch, const float* latent, const float* const* noise,
+                              const int* noise_batch, float* image, void* workspace, size_t workspace_bytes,
+                              int precision, void* stream, bool fwd_only) {
+  LFP_CHECK_ARG(h != nullptr && batch >= 1 && batch <= 65535, "synth_forward: null plan or batch out of range");
+  const Layout L = h->layout(batch, fwd_only);
+  LFP_TRY(check_run(h, batch, workspace, workspace_bytes, precision, L));
   LFP_CHECK_ARG(latent && noise && noise_batch && image, "synth_forward: null argument");
   for (int i = 0; i < h->num_noise; ++i)
     LFP_CHECK_ARG(noise[i] != nullptr && (noise_batch[i] == 1 || noise_batch[i] == batch), "synth_forward: noise %d must have batch 1 or %d", i, batch);
   cudaStream_t s = (cudaStream_t)stream;
-  const Layout L = h->layout(batch);
   float* ws = (float*)workspace;
   float* s_all = ws + L.s_all;
   float* d_all = ws + L.d_all;
   const int B = batch;
+  const Tables* tb = nullptr;
+  LFP_TRY(h->get_tables(B, precision, L, h->bwd_steps(precision), &tb));
 
   LFP_TRY(launch_style_affine(latent, h->A_all, h->b_all, h->row_slot, h->row_base, h->row_cin, s_all, B, h->rows, h->n_latent, h->style_dim, s));
-  for (const ConvLayer& c : h->convs)
-    LFP_TRY(launch_demod(s_all + (size_t)B * c.row0, c.cin, c.wsq, d_all + (size_t)B * c.demod_off, c.cout, B, c.cin, c.cout, s));
+  LFP_TRY(launch_batched_demod(tb->ditems, tb->dblocks, tb->ndblocks, ws, B, s));   // all 2 log2(size) - 3 layers in one launch
 
   const float* x = h->const_nhwc;
   int64_t x_bstride = 0;
   for (size_t li = 0; li < h->convs.size(); ++li) {
     const ConvLayer& c = h->convs[li];
-    float* act = ws + c.act_off;
+    float* act = ws + L.act_off[li];
     const float* smod = s_all + (size_t)B * c.row0;
     const float* dmod = d_all + (size_t)B * c.demod_off;
     const int nb = noise_batch[c.noise_idx];
@@ -455,7 +561,7 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
           const size_t ri = li / 2;
           const RgbLayer& r = h->rgbs[ri];
           t.e.s_rgb = s_all + (size_t)B * r.row0; t.e.wrgb = r.wrgb; t.e.rgb_bias = r.bias;
-          t.e.rgb_out = (ri + 1 == h->rgbs.size()) ? image : ws + r.skip_off;
+          t.e.rgb_out = (ri + 1 == h->rgbs.size()) ? image : ws + L.skip_off[ri];
           rgb_fused = true;
         }
         LFP_PROF(h, LFP_KIND_CONV_FWD, conv_flops(g), conv_bytes(g), s, launch_conv_tc(t, s));
@@ -529,8 +635,8 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
       const size_t ri = li / 2;
       const RgbLayer& r = h->rgbs[ri];
       const bool last = ri + 1 == h->rgbs.size();
-      float* dst = last ? image : ws + r.skip_off;
-      const float* skip = ri == 0 ? nullptr : ws + h->rgbs[ri - 1].skip_off;
+      float* dst = last ? image : ws + L.skip_off[ri];
+      const float* skip = ri == 0 ? nullptr : ws + L.skip_off[ri - 1];
       if (rgb_fused) {
         if (skip) LFP_PROF(h, LFP_KIND_TORGB, 0.0, 4.0 * B * r.res * r.res * 6.75, s, launch_skip_add(dst, skip, h->fir + 32, B, r.res, r.res, s));
       } else
@@ -538,24 +644,54 @@ extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, c
                launch_torgb_fwd(act, s_all + (size_t)B * r.row0, r.wrgb, r.bias, skip, h->fir + 32, dst, B, r.res, r.res, r.cin, s));
     }
   }
-  h->fwd_batch = batch;
-  h->fwd_noise.assign(noise, noise + h->num_noise);
-  h->fwd_noise_batch.assign(noise_batch, noise_batch + h->num_noise);
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (h->fwd_recs.size() > 256) h->fwd_recs.clear();   // stale workspaces of long-lived plans
+    FwdRec& rec = h->fwd_recs[workspace];
+    rec.batch = batch; rec.precision = precision; rec.fwd_only = fwd_only;
+    rec.noise.assign(noise, noise + h->num_noise);
+    rec.noise_batch.assign(noise_batch, noise_batch + h->num_noise);
+  }
   return 0;
+}
+
+extern "C" int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, const float* const* noise,
+                                 const int* noise_batch, float* image, void* workspace, size_t workspace_bytes,
+                                 int precision, void* stream) {
+  return synth_forward_impl(h, batch, latent, noise, noise_batch, image, workspace, workspace_bytes, precision, stream, false);
+}
+
+extern "C" int lfp_synth_generate(lfp_synth* h, int batch, const float* latent, const float* const* noise,
+                                  const int* noise_batch, float* image, void* workspace, size_t workspace_bytes,
+                                  int precision, void* stream) {
+  return synth_forward_impl(h, batch, latent, noise, noise_batch, image, workspace, workspace_bytes, precision, stream, true);
 }
 
 extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image, float* d_latent,
                                   void* workspace, size_t workspace_bytes, int precision, void* stream) {
-  LFP_TRY(check_run(h, batch, workspace, workspace_bytes, precision));
-  LFP_CHECK_ARG(d_image && d_latent, "synth_backward: null argument");
-  if (h->fwd_batch != batch) { set_error("synth_backward: no matching forward (forward batch %d, backward batch %d)", h->fwd_batch, batch); return LFP_ESTATE; }
-  cudaStream_t s = (cudaStream_t)stream;
+  LFP_CHECK_ARG(h != nullptr && batch >= 1 && batch <= 65535, "synth_backward: null plan or batch out of range");
   const Layout L = h->layout(batch);
+  LFP_TRY(check_run(h, batch, workspace, workspace_bytes, precision, L));
+  LFP_CHECK_ARG(d_image && d_latent, "synth_backward: null argument");
+  FwdRec rec;
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->fwd_recs.find(workspace);
+    if (it != h->fwd_recs.end()) rec = it->second;
+  }
+  // validated against the forward that ran on THIS workspace (its batch, arithmetic and noise pointers)
+  if (rec.batch != batch || rec.fwd_only || rec.precision != precision) {
+    set_error("synth_backward: no matching forward on this workspace (forward batch %d%s precision %d; backward batch %d precision %d)",
+              rec.batch, rec.fwd_only ? " forward-only," : ",", rec.precision, batch, precision);
+    return LFP_ESTATE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const std::vector<BwdStep> steps = h->bwd_steps(precision);
+  const Tables* tb = nullptr;
+  LFP_TRY(h->get_tables(batch, precision, L, steps, &tb));
   float* ws = (float*)workspace;
   float* s_all = ws + L.s_all;
   float* d_all = ws + L.d_all;
-  float* T_all = ws + L.T_all;
-  float* R1_all = ws + L.R1_all;
   float* ds_all = ws + L.ds_all;
   float* bufs[2] = {ws + L.bufA, ws + L.bufB};
   float* dskips[2] = {ws + L.dskipA, ws + L.dskipB};
@@ -573,28 +709,25 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     float* gbuf = g != nullptr ? g : bufs[cur];
     if (!act_done) {
     ActBwdArgs ab{};
-    ab.batch = B; ab.hw = hw; ab.C = c.cout; ab.act = ws + c.act_off; ab.g = gbuf; ab.g_has_input = g != nullptr;
+    ab.batch = B; ab.hw = hw; ab.C = c.cout; ab.act = ws + L.act_off[li]; ab.g = gbuf; ab.g_has_input = g != nullptr;
     ab.demod = d_all + (size_t)B * c.demod_off;
-    ab.noise = h->fwd_noise[c.noise_idx];
-    ab.noise_bstride = h->fwd_noise_batch[c.noise_idx] == 1 ? 0 : hw;
+    ab.noise = rec.noise[c.noise_idx];
+    ab.noise_bstride = rec.noise_batch[c.noise_idx] == 1 ? 0 : hw;
     ab.noise_w = c.noise_w; ab.bias = c.act_bias;
     if (r) { ab.drgb = dskip; ab.s_rgb = s_all + (size_t)B * r->row0; ab.wrgb = r->wrgb; }
-    ab.pT = ws + L.pT; ab.pR = ws + L.pR;
+    ab.pT = ws + L.pT_off[li]; ab.pR = ws + L.pR_off[li];
     LFP_PROF(h, LFP_KIND_ACTBWD, 0.0, 4.0 * B * hw * c.cout * (g != nullptr ? 3.0 : 2.0), s, launch_act_bwd(ab, s));
-    const int Q = hw / actbwd_seglen(hw, c.cout);
-    LFP_TRY(launch_partial_reduce(ab.pT, T_all + (size_t)B * c.demod_off, B, Q, c.cout, c.cout, s));
-    if (r) LFP_TRY(launch_partial_reduce(ab.pR, ds_all + (size_t)B * r->row0, B, Q, c.cout, c.cout, s));
     }
     if (g == nullptr) { g = gbuf; }
     // g now holds dRaw = d(loss)/d(conv output before demod) * demod, at the layer's output resolution
     float* other = (g == bufs[0]) ? bufs[1] : bufs[0];
-    const float* xin = li == 0 ? h->const_nhwc : ws + h->convs[li - 1].act_off;
+    const float* xin = li == 0 ? h->const_nhwc : ws + L.act_off[li - 1];
     const int64_t xin_bstride = li == 0 ? 0 : (int64_t)c.res_in * c.res_in * c.cin;
     ConvGeom gg{};
     gg.batch = B; gg.gh = gg.gw = c.res_in; gg.in_bstride = 0; gg.K = c.cout; gg.N = c.cin;
     gg.out_h = gg.out_w = c.res_in; gg.out_stride = 1; gg.out_oy = gg.out_ox = 0;
     const float* gin = g;
-    const bool use_tc = precision == LFP_PREC_TF32 && c.tc_bwd && c.res_in >= h->tc_min_res;
+    const bool use_tc = steps[li].use_tc;
     TcConv tq{};
     tq.in_bcast = false; tq.mod = nullptr; tq.wmap = c.map_bwd.bytes;
     tq.out_planes = 1; tq.out_plane = 0; tq.out_h = tq.out_w = c.res_in;
@@ -637,7 +770,7 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
         for (int kx = 0; kx < 3; ++kx) { const int t = ky * 3 + kx; gg.dy[t] = (signed char)ky; gg.dx[t] = (signed char)kx; gg.widx[t] = (signed char)t; }
     }
     ConvEpiArgs e;
-    e.mod_out = s_all + (size_t)B * c.row0; e.xsave = xin; e.xsave_bstride = xin_bstride; e.partial = ws + L.pX;
+    e.mod_out = s_all + (size_t)B * c.row0; e.xsave = xin; e.xsave_bstride = xin_bstride; e.partial = ws + L.pX_off[li];
     float* dx = li == 0 ? nullptr : other;
     // the skip gradient crosses a resolution boundary through the Upsample adjoint; done before the dgrad because the
     // fused epilogue below needs it at this layer's input resolution
@@ -649,40 +782,32 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     }
     // tensor-core path: the dgrad epilogue also runs the backward through noise/bias/lrelu (+ ToRGB branch) of the
     // layer below (what act_bwd_kernel does as a separate pass) - it already holds that layer's saved output
-    const bool fuse = use_tc && li >= 1 && h->fuse_actbwd;
+    const bool fuse = steps[li].fuse;
     const ConvLayer* below = fuse ? &h->convs[li - 1] : nullptr;
     const RgbLayer* rbelow = (fuse && ((li - 1) % 2 == 0)) ? &h->rgbs[(li - 1) / 2] : nullptr;
     if (fuse) {
       tq.epi = EPI_DGRAD_ACT;
       e.demod = d_all + (size_t)B * below->demod_off;
-      e.noise = h->fwd_noise[below->noise_idx];
-      e.noise_bstride = h->fwd_noise_batch[below->noise_idx] == 1 ? 0 : (int64_t)below->res_out * below->res_out;
+      e.noise = rec.noise[below->noise_idx];
+      e.noise_bstride = rec.noise_batch[below->noise_idx] == 1 ? 0 : (int64_t)below->res_out * below->res_out;
       e.noise_w = below->noise_w; e.bias = below->act_bias;
-      e.partial_T = ws + L.pT; e.partial_R = ws + L.pR;
+      e.partial_T = ws + L.pT_off[li - 1]; e.partial_R = ws + L.pR_off[li - 1];
       if (rbelow) { e.drgb = dskip; e.s_rgb = s_all + (size_t)B * rbelow->row0; e.wrgb = rbelow->wrgb; }
     }
-    const int hwi = c.res_in * c.res_in;
-    int Qx = 0;
     if (use_tc) {
       tq.in = gin; tq.out = dx; tq.e = e;
       LFP_PROF(h, LFP_KIND_CONV_DGRAD, conv_flops(gg), conv_bytes(gg) + 4.0 * B * c.res_in * c.res_in * c.cin, s, launch_conv_tc(tq, s));
-      Qx = tc_tiles_per_sample(c.res_in, c.res_in);
     } else {
       LFP_PROF(h, LFP_KIND_CONV_DGRAD, conv_flops(gg), conv_bytes(gg) + 4.0 * B * c.res_in * c.res_in * c.cin, s,
                launch_conv_simt(gin, nullptr, c.wg, dx, gg, EPI_DGRAD, e, s));
-      Qx = hwi / conv_dgrad_seglen(gg);
     }
-    LFP_TRY(launch_partial_reduce(e.partial, R1_all + (size_t)B * c.row0, B, Qx, c.cin, c.cin, s));
-    LFP_TRY(launch_style_grad(R1_all + (size_t)B * c.row0, s_all + (size_t)B * c.row0, c.cin, T_all + (size_t)B * c.demod_off,
-                              d_all + (size_t)B * c.demod_off, c.cout, c.wsq, ds_all + (size_t)B * c.row0, B, c.cin, c.cout, s));
     g = dx;
-    act_done = false;
-    if (fuse) {
-      LFP_TRY(launch_partial_reduce(e.partial_T, T_all + (size_t)B * below->demod_off, B, Qx, below->cout, below->cout, s));
-      if (rbelow) LFP_TRY(launch_partial_reduce(e.partial_R, ds_all + (size_t)B * rbelow->row0, B, Qx, below->cout, below->cout, s));
-      act_done = true;
-    }
+    act_done = fuse;
   }
+  // every partial-sum reduction of the pass (style-gradient sums, act-backward T and ToRGB R sums: 43 launches before),
+  // then every layer's style gradient (17 launches before), then the backward of the modulation linears
+  LFP_TRY(launch_batched_partial_reduce(tb->ritems, tb->rblocks, tb->nrblocks, ws, B, s));
+  LFP_TRY(launch_batched_style_grad(tb->gitems, tb->gblocks, tb->ngblocks, ws, B, s));
   LFP_TRY(launch_style_affine_bwd(ds_all, h->A_all, h->slot_begin, h->slot_end, h->row_base, h->row_cin, d_latent, B, h->rows, h->n_latent, h->style_dim, s));
   return 0;
 }
@@ -698,9 +823,27 @@ extern "C" int lfp_synth_read_activation(lfp_synth* h, int batch, int conv_index
   if (res) *res = c.res_out;
   if (out == nullptr) return 0;
   LFP_CHECK_ARG(workspace != nullptr && batch >= 1, "read_activation: null workspace or bad batch");
-  if (h->fwd_batch != batch) { set_error("read_activation: no forward with batch %d on this plan", batch); return LFP_ESTATE; }
-  h->layout(batch);
-  return launch_nhwc_to_nchw((const float*)workspace + c.act_off, out, batch, c.cout, c.res_out * c.res_out, (cudaStream_t)stream);
+  {
+    std::lock_guard<std::mutex> lock(h->mu);
+    auto it = h->fwd_recs.find(workspace);
+    if (it == h->fwd_recs.end() || it->second.batch != batch || it->second.fwd_only) {
+      set_error("read_activation: no full forward with batch %d on this workspace", batch);
+      return LFP_ESTATE;
+    }
+  }
+  const Layout L = h->layout(batch);
+  return launch_nhwc_to_nchw((const float*)workspace + L.act_off[conv_index], out, batch, c.cout, c.res_out * c.res_out, (cudaStream_t)stream);
+}
+
+// grow-only device buffer `slot` of the host-pointer entry point
+static void* host_buf(lfp_synth* h, int slot, size_t bytes) {
+  if (h->hb.cap[slot] < bytes) {
+    if (h->hb.p[slot]) cudaFree(h->hb.p[slot]);
+    h->hb.p[slot] = nullptr; h->hb.cap[slot] = 0;
+    if (cudaMalloc(&h->hb.p[slot], bytes) != cudaSuccess) return nullptr;
+    h->hb.cap[slot] = bytes;
+  }
+  return h->hb.p[slot];
 }
 
 extern "C" int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const float* latent,
@@ -709,40 +852,45 @@ extern "C" int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const fl
                                                int precision) {
   LFP_CHECK_ARG(h && latent && noise && noise_batch && image, "synth_host: null argument");
   LFP_CHECK_ARG(batch >= 1, "synth_host: bad batch");
+  const bool with_bwd = d_image != nullptr && d_latent != nullptr;
   const size_t nlat = (size_t)batch * h->n_latent * h->style_dim;
   const size_t nimg = (size_t)batch * 3 * h->size * h->size;
-  const size_t wsb = lfp_synth_workspace_bytes(h, batch);
-  std::vector<void*> tmp;
-  auto dalloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr; tmp.push_back(p); return p; };
-  auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
-  float* dlat = (float*)dalloc(nlat * 4);
-  float* dimg = (float*)dalloc(nimg * 4);
-  void* ws = dalloc(wsb);
+  const size_t wsb = with_bwd ? lfp_synth_workspace_bytes(h, batch) : lfp_synth_generate_workspace_bytes(h, batch);
+  // device staging buffers are owned by the plan and only ever grow: a loop over this call allocates nothing after its
+  // first iteration (round 1 allocated and freed ~30 GB per call at B = 20)
+  float* dlat = (float*)host_buf(h, 0, nlat * 4);
+  float* dimg = (float*)host_buf(h, 1, nimg * 4);
+  void* ws = host_buf(h, 2, wsb);
+  float* dg = with_bwd ? (float*)host_buf(h, 3, nimg * 4) : nullptr;
+  float* dl = with_bwd ? (float*)host_buf(h, 4, nlat * 4) : nullptr;
+  bool ok = dlat && dimg && ws && (!with_bwd || (dg && dl));
+  if ((int)h->hb.noise.size() < h->num_noise) { h->hb.noise.resize(h->num_noise, nullptr); h->hb.noise_cap.resize(h->num_noise, 0); }
   std::vector<const float*> dn(h->num_noise);
-  bool ok = dlat && dimg && ws;
   for (int i = 0; ok && i < h->num_noise; ++i) {
     const int res = i == 0 ? 4 : (8 << ((i - 1) / 2));
-    const size_t n = (size_t)noise_batch[i] * res * res;
-    float* p = (float*)dalloc(n * 4);
-    ok = p && cudaMemcpy(p, noise[i], n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
-    dn[i] = p;
+    const size_t n = (size_t)noise_batch[i] * res * res * 4;
+    if (h->hb.noise_cap[i] < n) {
+      if (h->hb.noise[i]) cudaFree(h->hb.noise[i]);
+      h->hb.noise[i] = nullptr; h->hb.noise_cap[i] = 0;
+      ok = cudaMalloc(&h->hb.noise[i], n) == cudaSuccess;
+      if (ok) h->hb.noise_cap[i] = n;
+    }
+    ok = ok && cudaMemcpy(h->hb.noise[i], noise[i], n, cudaMemcpyHostToDevice) == cudaSuccess;
+    dn[i] = (const float*)h->hb.noise[i];
   }
-  if (!ok) { cleanup(); set_error("synth_host: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError())); return LFP_ENOMEM; }
+  if (!ok) { set_error("synth_host: device allocation/copy failed: %s", cudaGetErrorString(cudaGetLastError())); return LFP_ENOMEM; }
   int rc = 0;
   if (cudaMemcpy(dlat, latent, nlat * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = LFP_EINVAL;
-  if (rc == 0) rc = lfp_synth_forward(h, batch, dlat, dn.data(), noise_batch, dimg, ws, wsb, precision, nullptr);
+  if (rc == 0) rc = with_bwd ? lfp_synth_forward(h, batch, dlat, dn.data(), noise_batch, dimg, ws, wsb, precision, nullptr)
+                             : lfp_synth_generate(h, batch, dlat, dn.data(), noise_batch, dimg, ws, wsb, precision, nullptr);
   if (rc == 0 && cudaMemcpy(image, dimg, nimg * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = LFP_EINVAL;
-  if (rc == 0 && d_image != nullptr && d_latent != nullptr) {
-    float* dg = (float*)dalloc(nimg * 4);
-    float* dl = (float*)dalloc(nlat * 4);
-    if (!dg || !dl) rc = LFP_ENOMEM;
-    if (rc == 0 && cudaMemcpy(dg, d_image, nimg * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = LFP_EINVAL;
+  if (rc == 0 && with_bwd) {
+    if (cudaMemcpy(dg, d_image, nimg * 4, cudaMemcpyHostToDevice) != cudaSuccess) rc = LFP_EINVAL;
     if (rc == 0) rc = lfp_synth_backward(h, batch, dg, dl, ws, wsb, precision, nullptr);
     if (rc == 0 && cudaMemcpy(d_latent, dl, nlat * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = LFP_EINVAL;
   }
   cudaError_t e = cudaDeviceSynchronize();
   if (rc == 0 && e != cudaSuccess) { set_error("synth_host: %s", cudaGetErrorString(e)); rc = (int)e; }
-  cleanup();
   return rc;
 }
 

@@ -42,6 +42,8 @@ _PROTOS = {
     "lfp_synth_finalize": (_i, [_vp, _vp]),
     "lfp_synth_workspace_bytes": (_sz, [_vp, _i]),
     "lfp_synth_forward": (_i, [_vp, _i, _vp, C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _sz, _i, _vp]),
+    "lfp_synth_generate_workspace_bytes": (_sz, [_vp, _i]),
+    "lfp_synth_generate": (_i, [_vp, _i, _vp, C.POINTER(_vp), C.POINTER(_i), _vp, _vp, _sz, _i, _vp]),
     "lfp_synth_backward": (_i, [_vp, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "lfp_synth_num_convs": (_i, [_vp]),
     "lfp_synth_read_activation": (_i, [_vp, _i, _i, _vp, _vp, C.POINTER(_i), C.POINTER(_i), _vp]),
@@ -51,6 +53,28 @@ _PROTOS = {
                                    C.POINTER(C.c_double)]),
     "lfp_synth_profile_launches": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(C.c_float), C.POINTER(C.c_double),
                                         C.POINTER(C.c_double)]),
+    "lfp_attrib_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i, _i, _i] + [_vp] * 6 + [_f, _f, C.c_double, _i, _i]),
+    "lfp_attrib_destroy": (None, [_vp]),
+    "lfp_attrib_workspace_bytes": (_sz, [_vp]),
+    "lfp_attrib_bind": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i), _vp, _i] + [_vp] * 7 + [_i, _vp, _sz]),
+    "lfp_attrib_set_step": (_i, [_vp, _i, _vp]),
+    "lfp_attrib_get_w0": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "lfp_attrib_run": (_i, [_vp, _i, _i, _vp]),
+    "lfp_modconv_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _vp, _i]),
+    "lfp_modconv_destroy": (None, [_vp]),
+    "lfp_modconv_set_param": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "lfp_modconv_finalize": (_i, [_vp, _vp]),
+    "lfp_modconv_out_size": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "lfp_modconv_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "lfp_modconv_forward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "lfp_modconv_backward": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "lfp_lpips_create": (_i, [C.POINTER(_vp), _i, _i]),
+    "lfp_lpips_destroy": (None, [_vp]),
+    "lfp_lpips_set_param": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "lfp_lpips_finalize": (_i, [_vp, _vp]),
+    "lfp_lpips_workspace_bytes": (_sz, [_vp, _i]),
+    "lfp_lpips_set_target": (_i, [_vp, _i, _vp, _vp, _sz, _i, _vp]),
+    "lfp_lpips_loss_grad": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "lfp_embed_forward": (_i, [_vp] * 6 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_embed_backward": (_i, [_vp] * 5 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_attrib_bound_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),

@@ -83,14 +83,17 @@ class SynthesisPlan:
             self._sig = sig
 
     # ---- execution ------------------------------------------------------------------------
-    def workspace_bytes(self, batch: int) -> int:
-        return int(capi.lib().lfp_synth_workspace_bytes(self._h, batch))
+    def workspace_bytes(self, batch: int, forward_only: bool = False) -> int:
+        L = capi.lib()
+        return int(L.lfp_synth_generate_workspace_bytes(self._h, batch) if forward_only
+                   else L.lfp_synth_workspace_bytes(self._h, batch))
 
-    def new_workspace(self, batch: int) -> torch.Tensor:
-        return torch.empty(self.workspace_bytes(batch) + 256, dtype=torch.uint8, device=self.device)
+    def new_workspace(self, batch: int, forward_only: bool = False) -> torch.Tensor:
+        return torch.empty(self.workspace_bytes(batch, forward_only) + 256, dtype=torch.uint8, device=self.device)
 
     def shared_workspace(self, batch: int) -> torch.Tensor:
-        need = self.workspace_bytes(batch) + 256
+        """Grow-only scratch for forward-only calls (lfp_synth_generate): nothing is kept for a backward."""
+        need = self.workspace_bytes(batch, forward_only=True) + 256
         if self._ws_cache is None or self._ws_cache.numel() < need:
             self._ws_cache = None
             self._ws_cache = torch.empty(need, dtype=torch.uint8, device=self.device)
@@ -100,8 +103,12 @@ class SynthesisPlan:
     def _aligned(ws: torch.Tensor) -> int:
         return (ws.data_ptr() + 255) // 256 * 256
 
+    def generate(self, latent: torch.Tensor, noise: Sequence[torch.Tensor], precision: int = capi.PREC_FP32) -> torch.Tensor:
+        """Forward only, on the plan's shared forward-only workspace (fingerprinted generation, target rendering)."""
+        return self.forward(latent, noise, self.shared_workspace(latent.shape[0]), precision, forward_only=True)
+
     def forward(self, latent: torch.Tensor, noise: Sequence[torch.Tensor], ws: torch.Tensor,
-                precision: int = capi.PREC_FP32) -> torch.Tensor:
+                precision: int = capi.PREC_FP32, forward_only: bool = False) -> torch.Tensor:
         require_cuda(latent, "latent")
         B = latent.shape[0]
         if tuple(latent.shape) != (B, self.n_latent, self.style_dim):
@@ -122,10 +129,10 @@ class SynthesisPlan:
         nb = (C.c_int * self.num_noise)(*[n.numel() // ((4 if i == 0 else 8 << ((i - 1) // 2)) ** 2)
                                           for i, n in enumerate(nz)])
         base = self._aligned(ws)
+        fn = capi.lib().lfp_synth_generate if forward_only else capi.lib().lfp_synth_forward
         with torch.cuda.device(self.device):
-            capi.check(capi.lib().lfp_synth_forward(self._h, B, ptr(latent), nptr, nb, ptr(image), base,
-                                                    ws.data_ptr() + ws.numel() - base, precision,
-                                                    stream_ptr(self.device)), "synth_forward")
+            capi.check(fn(self._h, B, ptr(latent), nptr, nb, ptr(image), base, ws.data_ptr() + ws.numel() - base, precision,
+                          stream_ptr(self.device)), "synth_generate" if forward_only else "synth_forward")
         self.generation += 1
         self._keep = (latent, nz)  # pointers recorded by the plan must outlive the backward
         return image
@@ -162,7 +169,7 @@ class _Synthesize(torch.autograd.Function):
     def forward(ctx, latent, plan, precision, *noise):
         needs_grad = latent.requires_grad
         ws = plan.new_workspace(latent.shape[0]) if needs_grad else plan.shared_workspace(latent.shape[0])
-        image = plan.forward(latent, noise, ws, precision)
+        image = plan.forward(latent, noise, ws, precision, forward_only=not needs_grad)
         if needs_grad:
             ctx.plan, ctx.ws, ctx.precision = plan, ws, precision
             ctx.generation = plan.generation

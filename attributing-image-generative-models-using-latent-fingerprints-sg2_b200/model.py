@@ -115,10 +115,14 @@ class EqualLinear(nn.Module):
 class ModulatedConv2d(nn.Module):
     """Style-modulated, demodulated conv (src/model.py:169-302).
 
-    Stand-alone use evaluates the activation-modulated form (the reference's ``fused=False``
-    branch, :229-256): input channels scaled by the style, shared weight, output channels scaled
-    by the demodulation coefficients.  Inside ``Generator`` the layer's parameters are consumed by
-    the native synthesis plan instead and this ``forward`` is not called.
+    Stand-alone use runs the native layer (``lfp_modconv_forward / backward``, include/lfp_sg2.h group 5): the
+    activation-modulated form (the reference's ``fused=False`` branch, :229-256) on the same gather-convolution kernels
+    as the whole-synthesis plan - tcgen05 when ``torch.backends.cudnn.allow_tf32`` (what decides the reference's conv
+    arithmetic) and the shape tiles, CUDA-core fp32 otherwise - differentiable w.r.t. the input and the style; the
+    layer's parameters are frozen constants there, exactly as on the ``Generator.forward`` path.  ``native = False`` (or
+    a downsampling layer, which the generator never builds) evaluates the same algebra with torch ops through
+    ``conv2d_gradfix``, which also yields parameter gradients.  Inside ``Generator`` the parameters are consumed by the
+    synthesis plan instead and this ``forward`` is not called.
     """
 
     def __init__(self, in_channel, out_channel, kernel_size, style_dim, demodulate=True, upsample=False,
@@ -139,8 +143,31 @@ class ModulatedConv2d(nn.Module):
         self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
         self.demodulate = demodulate
         self.fused = fused
+        self.blur_kernel = list(blur_kernel)
+        self.native = True        # False: torch-op composite (parameter gradients)
+        self.precision = None     # None: follow torch.backends.cudnn.allow_tf32
+        self._plans = {}
+
+    def _plan(self, device):
+        from lfp_native.modconv import ModConvPlan
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = ModConvPlan(self.in_channel, self.out_channel, self.kernel_size, self.modulation.weight.shape[1],
+                               self.demodulate, self.upsample, self.blur_kernel, device=torch.device("cuda", key[1]))
+            self._plans[key] = plan
+        plan.sync(self.weight, self.modulation.weight, self.modulation.bias)
+        return plan
 
     def forward(self, input, style):
+        if self.native and not self.downsample and self.kernel_size in (1, 3) and len(self.blur_kernel) == 4:
+            if not input.is_cuda:
+                raise RuntimeError("input must be a CUDA tensor")
+            from lfp_native.modconv import modulated_conv2d
+            prec = self.precision
+            if prec is None:
+                prec = _capi.PREC_TF32 if torch.backends.cudnn.allow_tf32 else _capi.PREC_FP32
+            return modulated_conv2d(self._plan(input.device), input, style, prec)
         batch = input.shape[0]
         w = self.scale * self.weight[0]
         s = self.modulation(style)

@@ -132,8 +132,19 @@ size_t lfp_synth_workspace_bytes(const lfp_synth* h, int batch);
 int lfp_synth_forward(lfp_synth* h, int batch, const float* latent, const float* const* noise,
                       const int* noise_batch, float* image, void* workspace,
                       size_t workspace_bytes, int precision, void* stream);
+/* The backward is validated against the forward that last ran on THIS workspace (batch, precision, noise pointers are
+ * recorded per workspace), so two workspaces of one plan can be interleaved freely. */
 int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image, float* d_latent,
                        void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* Forward only (fingerprinted generation, src/generator.py:185-198: no backward follows): same computation and bits as
+ * lfp_synth_forward, but activations and skip images ping-pong between two buffers instead of being kept, so the
+ * workspace is ~3 activation maps instead of all of them (27 GB instead of 93 GB for batch 64 at 1024 px).
+ * lfp_synth_backward / lfp_synth_read_activation refuse a workspace whose last forward was this call. */
+size_t lfp_synth_generate_workspace_bytes(const lfp_synth* h, int batch);
+int lfp_synth_generate(lfp_synth* h, int batch, const float* latent, const float* const* noise,
+                       const int* noise_batch, float* image, void* workspace, size_t workspace_bytes,
+                       int precision, void* stream);
 
 /* Inspection: copy the saved output of StyledConv `conv_index` (0 = conv1, 1 + i = convs.i,
  * src/model.py:552-563) of the last forward on `workspace` to `out` as [B, C, res, res] (NCHW,
@@ -146,7 +157,8 @@ int lfp_synth_read_activation(lfp_synth* h, int batch, int conv_index, const voi
 
 /* Host-buffer convenience (what a non-torch caller binds): latent / noise / image / d_image /
  * d_latent are HOST pointers; copies are inside the call; synchronous.  d_image may be NULL
- * (forward only). */
+ * (forward only: runs lfp_synth_generate).  The device staging buffers and the workspace belong to the
+ * plan and only grow, so calling this in a loop allocates nothing after the first iteration. */
 int lfp_synth_forward_backward_host(lfp_synth* h, int batch, const float* latent,
                                     const float* const* noise, const int* noise_batch,
                                     float* image, const float* d_image, float* d_latent,
@@ -207,6 +219,78 @@ int lfp_attrib_adam_update(const float* d_wx, float* alpha, float* key_logits, c
                            int batch, int n_main, int key_len, int dim, float step_size, float sqrt_bc2,
                            float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float eps,
                            int optimise_alpha, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 6. The whole Adam step of the attribution loop (src/main.py:57-72) as one native call, replayable as a CUDA graph
+ *    (additive): embed -> lfp_synth_forward -> MSE -> lfp_synth_backward -> bound loss -> Adam, for `batch` trajectories.
+ *    All buffers are bound once (lfp_attrib_bind); the per-step schedule scalars lr_i / (1 - beta1^t), sqrt(1 - beta2^t)
+ *    (src/main.py:42-43, 67; torch.optim.Adam defaults) come from a device table indexed by a device step counter, so a
+ *    captured step can be replayed unchanged.  lfp_attrib_run(h, n, use_graph = 1, stream) runs the first step eagerly,
+ *    captures the second and replays it for the rest: one host call per step instead of ~95 launches.  Results are
+ *    bit-identical to driving the group 3/4 entry points one by one.
+ *    U [n_main, dim], V [key_len, dim], sigma_key [key_len], mu [dim], max_alpha / min_alpha [n_main] (device, borrowed
+ *    for the handle's lifetime); state alpha [B, n_main], key_logits [B, key_len] and the Adam moments are updated in
+ *    place; loss_total [B] holds the loss of the last step run.
+ * --------------------------------------------------------------------------------- */
+typedef struct lfp_attrib lfp_attrib;
+int lfp_attrib_create(lfp_attrib** out, lfp_synth* plan, int size, int batch, int n_main, int key_len, int dim,
+                      const float* U, const float* V, const float* sigma_key, const float* mu, const float* max_alpha,
+                      const float* min_alpha, float sd, float bound_weight, double lr0, int max_steps, int precision);
+void lfp_attrib_destroy(lfp_attrib* h);
+size_t lfp_attrib_workspace_bytes(const lfp_attrib* h);
+int lfp_attrib_bind(lfp_attrib* h, const float* const* noise, const int* noise_batch, const float* target, int target_batch,
+                    float* alpha, float* key_logits, float* m_alpha, float* v_alpha, float* m_key, float* v_key,
+                    float* loss_total, int optimise_alpha, void* workspace, size_t workspace_bytes);
+int lfp_attrib_set_step(lfp_attrib* h, int step, void* stream);   /* index of the next step (0-based) */
+int lfp_attrib_get_w0(const lfp_attrib* h, const float** w0, const float** wx);   /* latents of the last step, [B, dim] */
+int lfp_attrib_run(lfp_attrib* h, int steps, int use_graph, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 5. Stand-alone modulated convolution (additive).  Replaces ModulatedConv2d.forward(input, style)
+ *    (src/model.py:169-302; fused branch :258-302, algebra of the unfused branch :229-256) for ONE layer and its
+ *    autograd backward to the input and the style: plain k x k (k = 1: ToRGB's conv, no demodulation; k = 3), or the
+ *    3x3 stride-2 transposed conv followed by Blur (upsample = 1, :269-282).  What model.ModulatedConv2d / StyledConv /
+ *    ToRGB run when they are used outside Generator.forward.
+ *    input [B, Cin, H, W], style [B, style_dim], out / d_out [B, Cout, H', W'] (H' = 2H when upsample), d_input like
+ *    input, d_style like style; all NCHW fp32 device pointers.  Parameters by name: "weight" [1, Cout, Cin, k, k],
+ *    "modulation.weight" [Cin, style_dim], "modulation.bias" [Cin]; they are frozen constants (no weight gradients).
+ *    Any channel count works (padded inside); shapes the tcgen05 kernel tiles run on it when precision = LFP_PREC_TF32.
+ *    The workspace keeps what the backward needs; one forward in flight per handle.
+ * --------------------------------------------------------------------------------- */
+typedef struct lfp_modconv lfp_modconv;
+int lfp_modconv_create(lfp_modconv** out, int in_channel, int out_channel, int kernel_size, int style_dim,
+                       int demodulate, int upsample, const float* blur_kernel_1d, int blur_taps);
+void lfp_modconv_destroy(lfp_modconv* h);
+int lfp_modconv_set_param(lfp_modconv* h, const char* name, const float* data, int64_t numel, void* stream);
+int lfp_modconv_finalize(lfp_modconv* h, void* stream);
+int lfp_modconv_out_size(const lfp_modconv* h, int in_h, int in_w, int* out_h, int* out_w);
+size_t lfp_modconv_workspace_bytes(const lfp_modconv* h, int batch, int in_h, int in_w);
+int lfp_modconv_forward(lfp_modconv* h, int batch, int in_h, int in_w, const float* input, const float* style,
+                        float* out, void* workspace, size_t workspace_bytes, int precision, void* stream);
+/* d_input or d_style may be NULL when that gradient is not needed */
+int lfp_modconv_backward(lfp_modconv* h, int batch, int in_h, int in_w, const float* d_out, float* d_input,
+                         float* d_style, void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * 7. Perceptual loss (additive).  Replaces `percept(target, est)` (src/utils.py:16, 44-50) =
+ *    PNetLin.forward, LPIPS v0.1 with the VGG16 backbone and linear heads (src/custom_lpips/networks_basic.py:27-91,
+ *    pretrained_networks.py:97-135), forward and backward to the estimated image.  The target's features are computed
+ *    once (lfp_lpips_set_target) instead of every step as the reference does (networks_basic.py:66).
+ *    Parameters by PNetLin state_dict name: "net.slice<S>.<I>.weight" [Cout, Cin, 3, 3] / ".bias" [Cout] for the 13
+ *    convolutions (I = torchvision vgg16.features index 0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28 in slices 1..5) and
+ *    "lin<K>.model.1.weight" [1, C_K, 1, 1], K = 0..4.  Images are [B, 3, H, W] NCHW in [-1, 1], H and W multiples of 16.
+ *    loss[b] = LPIPS(target[b or 0], est[b]); d_est = d loss[b] / d est[b] (may be NULL: value only).
+ * --------------------------------------------------------------------------------- */
+typedef struct lfp_lpips lfp_lpips;
+int lfp_lpips_create(lfp_lpips** out, int height, int width);
+void lfp_lpips_destroy(lfp_lpips* h);
+int lfp_lpips_set_param(lfp_lpips* h, const char* name, const float* data, int64_t numel, void* stream);
+int lfp_lpips_finalize(lfp_lpips* h, void* stream);
+size_t lfp_lpips_workspace_bytes(const lfp_lpips* h, int batch);
+int lfp_lpips_set_target(lfp_lpips* h, int target_batch, const float* target, void* workspace, size_t workspace_bytes,
+                         int precision, void* stream);
+int lfp_lpips_loss_grad(lfp_lpips* h, int batch, const float* est, float* loss, float* d_est, void* workspace,
+                        size_t workspace_bytes, int precision, void* stream);
 
 #ifdef __cplusplus
 }

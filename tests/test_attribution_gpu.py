@@ -284,3 +284,67 @@ def test_config4_at_512px_three_steps_against_oracle(prec):
         assert float(da.max()) <= 5e-3 and float(dk.max()) <= 5e-3
     else:
         assert float((da <= 5e-2).float().mean()) >= 0.99 and float((dk <= 5e-2).float().mean()) >= 0.99
+
+
+@pytest.mark.parametrize("size,prec", [(32, "fp32"), (64, "tf32")])
+def test_native_graph_step_is_bitwise_the_python_driven_step(size, prec):
+    """lfp_attrib_run (whole step in native code, CUDA-graph replay, schedule scalars from a device table) against the
+    Python-driven sequence of the same kernels: alpha, key logits, Adam moments and loss after 7 steps, bit for bit; also
+    without the graph, and continuing a trajectory in two calls."""
+    from lfp_native import capi
+    precision = capi.PREC_FP32 if prec == "fp32" else capi.PREC_TF32
+    eng, params, noise, sp, mean = make_engine(size, 11, precision=precision)
+    B = 3
+    target = eng.render(fx.seeded((1, 512), 23).to(DEV)).clone()
+    a0 = (sp["sigma_main"].t() * fx.seeded((B, 448), 81)).contiguous()
+    ref = eng.run(a0, target, steps=7, native=False)
+    for graph, split in ((True, None), (False, None), (True, 3)):
+        st = eng.init_state(a0)
+        stepper = eng.native_stepper(st, target, max_steps=16)
+        if split:
+            stepper.run(split, graph=graph)
+            stepper.run(7 - split, graph=graph)
+        else:
+            stepper.run(7, graph=graph)
+        torch.cuda.synchronize()
+        assert st["step"] == 7
+        for k in ("alpha", "key", "m_a", "v_a", "m_k", "v_k", "loss"):
+            assert torch.equal(st[k], ref[k]), (k, graph, split)
+    # the default engine.run is the native loop
+    st = eng.run(a0, target, steps=7)
+    assert torch.equal(st["alpha"], ref["alpha"]) and torch.equal(st["key"], ref["key"]) and torch.equal(st["loss"], ref["loss"])
+
+
+def test_lpips_loop_two_steps_against_oracle():
+    """The hot loop with the reference's DEFAULT loss (LPIPS-VGG16, src/utils.py:44-50, src/main.py:63) on the native path
+    (synthesis + lfp_lpips_*) against the oracle loop with oracle/lpips_oracle.py as the loss, 2 steps at 64 px, fp32.
+    Backbone weights random (unpinned), linear heads random non-negative."""
+    from lfp_native import capi
+    from lfp_native.synthesis import SynthesisPlan
+    from attribution import AttributionEngine
+    from oracle import lpips_oracle as lo
+    size, seed = 64, 11
+    params = fx.make_params(size, seed)
+    noise = fx.make_noise(size, seed + 1)
+    pc, sigma_512, mean = fx.make_pca_basis(2)
+    sp = fx.split_basis(pc, sigma_512, 64, 448, 1.0)
+    vgg = lo.make_vgg_params(seed=3)
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(params)
+    eng = AttributionEngine(plan, noise, pc, sigma_512, mean, precision=capi.PREC_FP32, loss="lpips", lpips_params=vgg)
+    alpha_t = sp["sigma_main"] * fx.seeded((448, 1), 33)
+    key_t = (fx.seeded((64, 1), 35) > 0).long()
+    with torch.no_grad():
+        target, _, _ = oracle.generate_with_alpha(params, size, alpha_t, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean, key_t, noise)
+    # random-init images are not in [-1, 1]; LPIPS does not care, but keep the scale sane for the normalisation
+    a0 = sp["sigma_main"] * fx.seeded((448, 1), 36)
+    st = eng.run(a0.t().contiguous(), target.to(DEV), steps=2)
+
+    def render(wx):
+        return oracle.generator_forward(params, [wx.reshape(1, -1)], size, input_is_latent=True, noise=noise)
+
+    l_o, a_o, k_o = oracle.attribute_one_guess(render, target, a0, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean, sp["max_alpha"],
+                                               sp["min_alpha"], steps=2, loss_fn=lambda t, e: lo.perceptual_loss(vgg, t, e).reshape(()))
+    np.testing.assert_allclose(float(st["loss"][0]), float(l_o), rtol=2e-3)
+    np.testing.assert_allclose(st["alpha"][0].cpu().numpy(), a_o[:, 0].detach().numpy(), rtol=0, atol=5e-3)
+    np.testing.assert_allclose(st["key"][0].cpu().numpy(), k_o[:, 0].detach().numpy(), rtol=0, atol=5e-3)

@@ -172,3 +172,23 @@ def test_lhs_centered_is_latin():
     assert s.shape == (20, 7)
     for d in range(7):
         assert sorted(np.round(s[:, d] * 20 - 0.5).astype(int).tolist()) == list(range(20))
+
+
+def test_lpips_oracle_matches_reference_pnetlin():
+    """oracle/lpips_oracle.py against the reference's own PNetLin (tests/golden/make_golden_lpips.py: random VGG16 weights,
+    shipped linear heads): distance and its gradient w.r.t. the second image."""
+    import os
+    from oracle import lpips_oracle as lo
+    from golden.make_golden_lpips import CASES
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lpips.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    heads = {f"lin{k}.model.1.weight": torch.from_numpy(g[f"lpips/head{k}"]) for k in range(5)}
+    params = lo.make_vgg_params(seed=5, lin_weights=heads)
+    for name, B, size, seed in CASES:
+        h, w = (size, size) if isinstance(size, int) else size
+        a = fx.seeded((B, 3, h, w), seed, scale=0.5)
+        b = fx.seeded((B, 3, h, w), seed + 100, scale=0.5).requires_grad_(True)
+        val = lo.lpips(params, a, b)
+        (gb,) = torch.autograd.grad(val.sum(), b)
+        np.testing.assert_allclose(val.detach().numpy(), g[f"lpips/{name}/val"], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(gb.numpy(), g[f"lpips/{name}/grad_in1"], rtol=1e-4, atol=1e-6 * np.abs(g[f"lpips/{name}/grad_in1"]).max())

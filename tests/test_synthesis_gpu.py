@@ -326,3 +326,112 @@ def test_host_buffer_entry_point_matches():
     (gref,) = torch.autograd.grad((ref * ct).sum(), lr)
     img_close(img.numpy(), ref.detach().numpy(), 1e-4)
     assert np.linalg.norm(dlat.numpy() - gref.numpy()) <= KINK_TOL * np.linalg.norm(gref.numpy())
+
+
+def test_forward_only_workspace_matches_and_refuses_backward():
+    """lfp_synth_generate (ping-pong activations, nothing kept) gives the same bits as lfp_synth_forward, its workspace is
+    a fraction of the full one, and a backward on it is refused (LFP_ESTATE) instead of reading stale memory."""
+    from lfp_native import capi
+    from lfp_native.synthesis import SynthesisPlan
+    size, seed, B = 128, 81, 3
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(fx.make_params(size, seed))
+    noise = [n.to(DEV) for n in fx.make_noise(size, seed + 1)]
+    lat = fx.seeded((B, plan.n_latent, 512), seed + 2).to(DEV)
+    for prec in (capi.PREC_FP32, capi.PREC_TF32):
+        ws = plan.new_workspace(B)
+        full = plan.forward(lat, noise, ws, prec).clone()
+        wsg = plan.new_workspace(B, forward_only=True)
+        gen = plan.forward(lat, noise, wsg, prec, forward_only=True)
+        assert torch.equal(full, gen)
+        assert plan.workspace_bytes(B, forward_only=True) < plan.workspace_bytes(B)
+        with pytest.raises(capi.LfpError, match="no matching forward|workspace too small"):
+            plan.backward(torch.zeros_like(gen), B, wsg, prec)
+        plan.forward(lat, noise, ws, prec, forward_only=True)   # a forward-only pass on a FULL-size workspace
+        with pytest.raises(capi.LfpError, match="no matching forward"):
+            plan.backward(torch.zeros_like(gen), B, ws, prec)
+
+
+def test_two_workspaces_interleaved_through_the_c_abi():
+    """Forward on workspace A, forward on workspace B (different noise), then both backwards: each backward uses the
+    noise and batch recorded for ITS workspace (the plan kept one global record)."""
+    from lfp_native import capi
+    from lfp_native.synthesis import SynthesisPlan
+    size, seed = 32, 83
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(fx.make_params(size, seed))
+    nA = [n.to(DEV) for n in fx.make_noise(size, seed + 1)]
+    nB = [n.to(DEV) for n in fx.make_noise(size, seed + 7)]
+    lat = fx.seeded((2, plan.n_latent, 512), seed + 2).to(DEV)
+    ct = fx.seeded((2, 3, size, size), seed + 3).to(DEV)
+
+    def alone(noise):
+        ws = plan.new_workspace(2)
+        plan.forward(lat, noise, ws, capi.PREC_FP32)
+        return plan.backward(ct, 2, ws, capi.PREC_FP32).clone()
+
+    gA, gB = alone(nA), alone(nB)
+    assert not torch.equal(gA, gB)
+    wsA, wsB = plan.new_workspace(2), plan.new_workspace(2)
+    plan.forward(lat, nA, wsA, capi.PREC_FP32)
+    plan.forward(lat, nB, wsB, capi.PREC_FP32)
+    assert torch.equal(plan.backward(ct, 2, wsA, capi.PREC_FP32), gA)
+    assert torch.equal(plan.backward(ct, 2, wsB, capi.PREC_FP32), gB)
+    # a backward with another batch size or arithmetic than the forward on that workspace is refused
+    with pytest.raises(capi.LfpError, match="no matching forward"):
+        plan.backward(ct, 2, wsA, capi.PREC_TF32)
+
+
+def test_generation_batch64_at_1024px_forward_only():
+    """BASELINE.json configs[1]: fingerprinted generation, batch 64 at 1024 px, one call (a [64,32,1024,1024] activation is
+    exactly 2^31 elements: the reference's int-indexed ops cannot run it un-chunked).  Samples of the
+    batched call equal single-sample calls bit for bit, and those are oracle-checked by test_full_size_oracle_parity."""
+    from lfp_native import capi
+    from lfp_native.synthesis import SynthesisPlan
+    size, seed, B = 1024, 1324, 64   # the seed of test_full_size_oracle_parity[*-1024]
+    params = fx.make_params(size, seed)
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(params)
+    noise = [n.to(DEV) for n in fx.make_noise(size, seed + 1)]
+    lat1 = fx.seeded((1, plan.n_latent, 512), seed + 2)
+    lat = torch.cat([lat1, fx.seeded((B - 1, plan.n_latent, 512), seed + 9)]).to(DEV)
+    img = plan.generate(lat, noise, capi.PREC_TF32).clone()
+    assert torch.isfinite(img).all()
+    for b in (0, 31, 63):
+        one = plan.generate(lat[b:b + 1].contiguous(), noise, capi.PREC_TF32)
+        assert torch.equal(one[0], img[b]), b
+    # sample 0 is the latent of the oracle-checked full-size test: compare with the oracle directly as well
+    with torch.no_grad():
+        ref = oracle.synthesis(params, lat1, fx.make_noise(size, seed + 1))
+    img_close(img[:1].cpu().numpy(), ref.numpy(), 5e-3)
+    print(f"generation B=64 @1024: forward-only workspace {plan.workspace_bytes(B, forward_only=True) / 1e9:.1f} GB "
+          f"(full: {plan.workspace_bytes(B) / 1e9:.1f} GB)")
+
+
+def test_host_entry_point_in_a_loop_does_not_allocate():
+    """lfp_synth_forward_backward_host keeps its staging buffers: device memory in use is flat across repeated calls."""
+    import ctypes as C
+    from lfp_native import capi
+    from lfp_native.synthesis import SynthesisPlan
+    size, seed, B = 32, 70, 2
+    plan = SynthesisPlan(size, device=DEV)
+    plan.load(fx.make_params(size, seed))
+    noise = fx.make_noise(size, seed + 1)
+    lat = fx.seeded((B, plan.n_latent, 512), seed + 2).contiguous()
+    ct = fx.seeded((B, 3, size, size), seed + 3).contiguous()
+    img, dlat = torch.empty(B, 3, size, size), torch.empty_like(lat)
+    nptr = (C.c_void_p * plan.num_noise)(*[n.data_ptr() for n in noise])
+    nb = (C.c_int * plan.num_noise)(*[1] * plan.num_noise)
+
+    def call():
+        capi.check(capi.lib().lfp_synth_forward_backward_host(plan._h, B, lat.data_ptr(), nptr, nb, img.data_ptr(),
+                                                              ct.data_ptr(), dlat.data_ptr(), capi.PREC_FP32))
+        return torch.cuda.mem_get_info()[0]
+
+    call()
+    first = dlat.clone()
+    free0 = call()
+    for _ in range(5):
+        free = call()
+    assert free == free0
+    assert torch.equal(first, dlat)
