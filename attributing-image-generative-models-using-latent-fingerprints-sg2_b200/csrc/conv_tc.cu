@@ -47,8 +47,8 @@ constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
 constexpr int MAX_SA = 8, MAX_SB = 12;
 // warp 0 TMA, warp 1 MMA, warps 2-5 transform (or a third epilogue set when there is nothing to transform),
 // warps 6-9 / 10-13 epilogue sets; warps 14-15 of the modulated (forward) kernels only pad the block to 512 threads
-constexpr int NTHREADS_MOD = 512, NTHREADS_PLAIN = 480;   // both are charged as 512 threads: 128 registers
-constexpr int MMA2_WARP = 14;                              // second MMA issuer (tiles alternate between warps 1 and 14)
+constexpr int NTHREADS_MOD = 512, NTHREADS_PLAIN = 448;   // both are charged as 512 threads: 128 registers
+constexpr int MMA2_WARP = 14;                              // optional second MMA issuer of the modulated layout (LFP_TC_ISSUE=2)
 constexpr int MAX_ACC = 4;                // TMEM accumulator stages
 constexpr int MAX_XS = 4;                 // stages of the saved-input (xsave) tile ring of the data-gradient epilogues
 constexpr int XS_CHUNK = 128 * 128;       // one 128-pixel x 32-channel tile
@@ -68,6 +68,8 @@ struct Args {
   int nacc;                   // TMEM accumulator stages (1, 2 or 4)
   int epi_off;                // byte offset of the epilogue scratch in dynamic shared memory
   int XS, xs_off;             // xsave ring: stages (0 = epilogue reads xsave from global) and byte offset in dynamic smem
+  int px_ok;                  // host: tensor maps for the per-pixel scalars exist (PXS kernel when a ring is planned)
+  int xs_stride;              // bytes per ring stage: BN / 32 saved-input chunks (+ 2 KB of per-pixel scalars, PXS kernels)
   int xs_bcast;
   int nsets;                  // epilogue warp sets (2, or 3 when the transform warps are free and smem allows)
   int nissue;                 // MMA-issuing warps (1 or 2): tile i of a CTA is issued by warp i % nissue
@@ -105,6 +107,18 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -172,7 +186,12 @@ __device__ __forceinline__ Work decode(const Args& a, int w) {
 
 // Persistent: CTA c processes work items c, c + gridDim.x, ...  (consecutive CTAs work on neighbouring
 // tiles at the same time, so halo rows and weight slices are L2 hits).
-template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
+// PXS (EPI_DGRAD_ACT, 16x256b epilogue, saved-input ring present): the per-pixel scalars of the fused act-backward - the
+// noise map and the three planes of the skip-image gradient - arrive in the ring stage by TMA next to the saved input,
+// instead of being prefetched into registers one tile ahead.  ncu on the stride-2 32 -> 64 layer at 1024 px: 22 % of all
+// stall samples sat on those prefetch loads (the compiler merges the "next" and "current" registers, which collapses the
+// prefetch distance to zero), and the prefetch registers are what pushed the RGB variant into 96 bytes of spills.
+template <int EPI, bool MOD, bool RES, bool E2, bool RGB, bool PXS>
 // Register budget: the register file is handed out to a CTA in units of four warps, so a 576-thread block is charged as
 // 640 threads and gets 96 registers per thread.  At 96 the epilogues spilled to local memory - and with (almost) all of
 // the SM's memory carved out as shared memory there is no L1 behind a spill: every STL / LDL was an L2 round trip (ncu:
@@ -181,7 +200,9 @@ template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
 // stay at <= 512 threads = 128 registers: the modulated kernels run two epilogue sets instead of three.
 __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
-                                                             const __grid_constant__ CUtensorMap tmX, const Args a) {
+                                                             const __grid_constant__ CUtensorMap tmX,
+                                                             const __grid_constant__ CUtensorMap tmNz,
+                                                             const __grid_constant__ CUtensorMap tmRg, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[NBARS];
   __shared__ uint32_t tmem_base_s;
@@ -278,11 +299,16 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         if (DGX && a.XS > 0) {
           // saved forward input of this tile for the epilogue (128 px x BN channels, one 16 KB box per 32 channels)
           const int nch = a.BN >> 5;
+          const uint32_t st0 = smem0 + a.xs_off + (uint32_t)sx * (uint32_t)a.xs_stride;
           mbar_wait(bar_xs_empty(sx), px ^ 1u);
-          mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK);
+          mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK + (PXS ? 512u + (RGB ? 1536u : 0u) : 0u));
           for (int c = 0; c < nch; ++c)
-            tma_load_5d(smem0 + a.xs_off + (uint32_t)(sx * nch + c) * XS_CHUNK, &tmX, bar_xs_full(sx), wk.n0 + c * 32, wk.x0, wk.y0, 0,
-                        a.xs_bcast ? 0 : wk.b);
+            tma_load_5d(st0 + (uint32_t)c * XS_CHUNK, &tmX, bar_xs_full(sx), wk.n0 + c * 32, wk.x0, wk.y0, 0, a.xs_bcast ? 0 : wk.b);
+          if (PXS) {
+            // noise tile [16 rows][8] floats, then the skip-gradient planes [3][16][8]; pixels outside the map read as 0
+            tma_load_3d(st0 + (uint32_t)nch * XS_CHUNK, &tmNz, bar_xs_full(sx), wk.x0, wk.y0, a.e.noise_bstride == 0 ? 0 : wk.b);
+            if (RGB) tma_load_4d(st0 + (uint32_t)nch * XS_CHUNK + 512u, &tmRg, bar_xs_full(sx), wk.x0, wk.y0, 0, wk.b);
+          }
           if (++sx == a.XS) { sx = 0; px ^= 1u; }
         }
       }
@@ -474,7 +500,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       const int nchunk = a.BN >> 5;
       const int nphase = a.taps.nphase;
       float nz_n[4], rg_n[4][3];
-      LFP_FETCH2(eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work, nz_n, rg_n)
+      if (!PXS) LFP_FETCH2(eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work, nz_n, rg_n)
       int it = eset;
       for (int w = eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work; w < a.total_work; w += wstep, it += a.nsets) {
         const Work wk = decode(a, w);
@@ -482,9 +508,11 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         const int b = wk.b, n0 = wk.n0;
         const int gx = wk.x0 + x;
         float cnz[4], crg[4][3];
+        if (!PXS) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { cnz[r] = nw2 * nz_n[r]; crg[r][0] = rg_n[r][0]; crg[r][1] = rg_n[r][1]; crg[r][2] = rg_n[r][2]; }
-        LFP_FETCH2(w + wstep, nz_n, rg_n)
+          for (int r = 0; r < 4; ++r) { cnz[r] = nw2 * nz_n[r]; crg[r][0] = rg_n[r][0]; crg[r][1] = rg_n[r][1]; crg[r][2] = rg_n[r][2]; }
+          LFP_FETCH2(w + wstep, nz_n, rg_n)
+        }
         bool valid[4];
         float* outp[4];
 #pragma unroll
@@ -499,8 +527,18 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         const bool xs_smem2 = DGX && a.XS > 0;
         const int sx = xs_smem2 ? it % a.XS : 0;
         // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x
-        const uint8_t* xbase = smem_al + a.xs_off + (size_t)sx * nchunk * XS_CHUNK + (32 * q + x) * 128 + (cq & 1) * 8;
+        const uint8_t* xbase = smem_al + a.xs_off + (size_t)sx * a.xs_stride + (32 * q + x) * 128 + (cq & 1) * 8;
         if (xs_smem2) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
+        if (PXS) {
+          // per-pixel scalars of this tile from the ring stage: noise[row][x], skip gradient [plane][row][x]
+          const float* px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)nchunk * XS_CHUNK);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = (4 * q + r) * 8 + x;
+            cnz[r] = nw2 * px[i];
+            crg[r][0] = RGB ? px[128 + i] : 0.f; crg[r][1] = RGB ? px[256 + i] : 0.f; crg[r][2] = RGB ? px[384 + i] : 0.f;
+          }
+        }
         const float* xg[4];   // without the ring (BN = 128): the saved input straight from global memory
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -734,7 +772,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       if (DGX && valid && !xs_smem) xs = a.e.xsave + (int64_t)b * a.e.xsave_bstride + (int64_t)pix * a.N + n0;
       // saved-input tile in shared memory (TMA, SWIZZLE_128B): pixel m is row m, channel quad j at position j ^ (m & 7)
       const int sx = xs_smem ? it % a.XS : 0;
-      const uint8_t* xrow = smem_al + a.xs_off + (size_t)sx * nchunk * XS_CHUNK + m * 128;
+      const uint8_t* xrow = smem_al + a.xs_off + (size_t)sx * a.xs_stride + m * 128;
       if (xs_smem) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
       auto load_x = [&](int c, int j) -> float4 {
         if (xs_smem) return *reinterpret_cast<const float4*>(xrow + c * XS_CHUNK + ((j ^ (m & 7)) << 4));
@@ -950,6 +988,19 @@ static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t
   return 0;
 }
 
+// plain (un-swizzled) tile map: the per-pixel scalar planes of the PXS kernels
+static int encode_plain(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                        const cuuint32_t* box) {
+  PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+  if (fn == nullptr) { set_error("conv_tc: cuTensorMapEncodeTiled is not available from this driver"); return LFP_EUNSUPPORTED; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("conv_tc: cuTensorMapEncodeTiled (plain) failed with CUresult %d", (int)r); return LFP_EINVAL; }
+  return 0;
+}
+
 }  // namespace tc
 
 int tc_block_n(int N) { return N >= 256 ? 256 : N; }
@@ -983,28 +1034,35 @@ int tc_make_weight_maps(void* maps_out, const float* table, int rows, int K, int
   return 0;
 }
 
-template <int EPI, bool MOD, bool RES, bool E2, bool RGB>
-static int tc_launch4(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+template <int EPI, bool MOD, bool RES, bool E2, bool RGB, bool PXS>
+static int tc_launch4(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const CUtensorMap& tmNz, const CUtensorMap& tmRg,
+                      const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
   // the opt-in shared-memory limit is a per-device function attribute
   static unsigned long long attr_done_mask = 0;
   int dev = 0;
   LFP_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !((attr_done_mask >> dev) & 1ull)) {
-    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES, E2, RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LFP_CUDA(cudaFuncSetAttribute(tc::conv_tc_kernel<EPI, MOD, RES, E2, RGB, PXS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(tc::SMEM_OPTIN - tc::STATIC_SMEM_RESERVE)));
     if (dev < 64) attr_done_mask |= 1ull << dev;
   }
   const int max_ctas = num_sms();
   const dim3 grid((unsigned)(a.total_work < max_ctas ? a.total_work : max_ctas));
-  tc::conv_tc_kernel<EPI, MOD, RES, E2, RGB><<<grid, MOD ? tc::NTHREADS_MOD : tc::NTHREADS_PLAIN, dyn_smem, s>>>(tmA, tmB, tmX, a);
+  tc::conv_tc_kernel<EPI, MOD, RES, E2, RGB, PXS><<<grid, MOD ? tc::NTHREADS_MOD : tc::NTHREADS_PLAIN, dyn_smem, s>>>(tmA, tmB, tmX, tmNz, tmRg, a);
   LFP_LAUNCH_CHECK();
   return 0;
 }
 
 template <int EPI, bool MOD, bool RES, bool E2>
-static int tc_launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
-  if (EPI == EPI_DGRAD_ACT && E2 && a.e.drgb != nullptr) return tc_launch4<EPI, MOD, RES, E2, EPI == EPI_DGRAD_ACT && E2>(tmA, tmB, tmX, a, dyn_smem, s);
-  return tc_launch4<EPI, MOD, RES, E2, false>(tmA, tmB, tmX, a, dyn_smem, s);
+static int tc_launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const CUtensorMap& tmNz, const CUtensorMap& tmRg,
+                      const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+  constexpr bool da = EPI == EPI_DGRAD_ACT && E2;
+  const bool pxs = da && a.px_ok && a.XS > 0;
+  if (da && a.e.drgb != nullptr)
+    return pxs ? tc_launch4<EPI, MOD, RES, E2, da, da>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s)
+               : tc_launch4<EPI, MOD, RES, E2, da, false>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s);
+  return pxs ? tc_launch4<EPI, MOD, RES, E2, false, da>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s)
+             : tc_launch4<EPI, MOD, RES, E2, false, false>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s);
 }
 
 static bool tc_use_e2(int bn) {
@@ -1016,14 +1074,16 @@ static bool tc_use_e2(int bn) {
 }
 
 template <int EPI, bool MOD, bool RES>
-static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
+static int tc_launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const CUtensorMap& tmNz, const CUtensorMap& tmRg,
+                      const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
   const bool e2 = tc_use_e2(a.BN);
   LFP_CHECK_ARG(e2 || (EPI != EPI_RELU && EPI != EPI_DGRAD_RELU), "conv_tc: the ReLU epilogues need the 16x256b epilogue (LFP_TC_E2=0 is set)");
-  return e2 ? tc_launch3<EPI, MOD, RES, true>(tmA, tmB, tmX, a, dyn_smem, s) : tc_launch3<EPI, MOD, RES, false>(tmA, tmB, tmX, a, dyn_smem, s);
+  return e2 ? tc_launch3<EPI, MOD, RES, true>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s) : tc_launch3<EPI, MOD, RES, false>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s);
 }
 
 template <int EPI, bool MOD>
-static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, tc::Args& a, int ntaps, cudaStream_t s) {
+static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, tc::Args& a, int ntaps, cudaStream_t s,
+                     const CUtensorMap* tmNz = nullptr, const CUtensorMap* tmRg = nullptr) {
   // shared-memory plan: the weight slice stays resident when it fits beside >= 3 activation stages
   const size_t b_all = (size_t)ntaps * (a.K / 32) * a.BN * 128;
   // an epilogue set that finished tile i waits next for tile i + nsets; the parity wait on that TMEM stage is only
@@ -1033,6 +1093,9 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT || EPI == EPI_DGRAD_RELU;
   // data-gradient epilogues of the HBM-bound layers (N <= 64) get their saved-input tiles through a TMA ring
   const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : 0;
+  // ring stage = BN / 32 saved-input chunks, plus 2 KB of per-pixel scalars for the fused act-backward (PXS kernels)
+  const size_t xs_stride = (size_t)(a.BN / 32) * tc::XS_CHUNK + ((EPI == EPI_DGRAD_ACT && a.px_ok && tc_use_e2(a.BN)) ? 2048 : 0);
+  a.xs_stride = (int)xs_stride;
   size_t xs_smem = 0, epi_smem = 0;
   // LFP_TC_SMEM_CAP (bytes): cap the shared memory a launch asks for, which leaves the rest of the 228 KB to the L1
   static const size_t smem_cap = getenv("LFP_TC_SMEM_CAP") ? (size_t)atol(getenv("LFP_TC_SMEM_CAP")) : (size_t)tc::SMEM_OPTIN;
@@ -1050,7 +1113,7 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
       if (xs == 1) continue;                       // a one-stage ring serialises the epilogue sets
       int nsets = nsets0;
       if (xs > 0 && nsets > xs) nsets = xs;
-      const size_t xsm = (size_t)xs * (a.BN / 32) * tc::XS_CHUNK;
+      const size_t xsm = (size_t)xs * xs_stride;
       const size_t epi = tc::EPI_SMEM(EPI, nsets, a.BN, tc_use_e2(a.BN)) + xsm;
       if (optin < tc::STATIC_SMEM_RESERVE + 1024 + epi) continue;
       const size_t budget = optin - tc::STATIC_SMEM_RESERVE - 1024 - epi;
@@ -1065,7 +1128,7 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     // same parity argument for the saved-input ring: a set may only wait on stage (i + nsets) % XS when the stage's
     // previous use (tile i + nsets - XS) is one it has already seen complete, i.e. nsets <= XS
     if (xs > 0 && a.nsets > xs) a.nsets = xs;
-    xs_smem = (size_t)xs * (a.BN / 32) * tc::XS_CHUNK;
+    xs_smem = (size_t)xs * xs_stride;
     epi_smem = tc::EPI_SMEM(EPI, a.nsets, a.BN, tc_use_e2(a.BN)) + xs_smem;
     const size_t budget = optin - tc::STATIC_SMEM_RESERVE - 1024 - epi_smem;
     if (a.n_ntiles == 1 && b_all + 3 * (size_t)tc::A_STAGE <= budget) {
@@ -1096,13 +1159,15 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // half of the activation stages, and the shallower prefetch costs more than the overlapped per-tile issue overhead
   // gains - so the default stays one issuer.
   static const int issue_env = getenv("LFP_TC_ISSUE") ? atoi(getenv("LFP_TC_ISSUE")) : 1;
-  a.nissue = (a.nacc >= 2 && issue_env >= 2 && a.SA >= 4 && (a.b_resident || a.SB >= 4)) ? 2 : 1;   // >= 2 stages per ring
+  a.nissue = (MOD && a.nacc >= 2 && issue_env >= 2 && a.SA >= 4 && (a.b_resident || a.SB >= 4)) ? 2 : 1;   // >= 2 stages per ring; warp 14 exists in the modulated layout only
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
   // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
   a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
   a.epi_off = (int)((size_t)a.xs_off + xs_smem);
   const size_t smem = (size_t)a.xs_off + epi_smem + 1024;
-  return a.b_resident ? tc_launch2<EPI, MOD, true>(tmA, tmB, tmX, a, smem, s) : tc_launch2<EPI, MOD, false>(tmA, tmB, tmX, a, smem, s);
+  const CUtensorMap& nzm = tmNz ? *tmNz : tmA;
+  const CUtensorMap& rgm = tmRg ? *tmRg : tmA;
+  return a.b_resident ? tc_launch2<EPI, MOD, true>(tmA, tmB, tmX, nzm, rgm, a, smem, s) : tc_launch2<EPI, MOD, false>(tmA, tmB, tmX, nzm, rgm, a, smem, s);
 }
 
 int launch_conv_tc(const TcConv& c, cudaStream_t s) {
@@ -1152,7 +1217,28 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
     const cuuint32_t xbox[5] = {32, tc::TILE_W, tc::TILE_H, 1, 1};
     LFP_TRY(tc::encode(&tmX, c.e.xsave, 5, xd, xst, xbox));
   }
-  if (c.epi == EPI_DGRAD_ACT) return tc_launch<EPI_DGRAD_ACT, false>(tmA, tmB, tmX, a, ntaps, s);
+  if (c.epi == EPI_DGRAD_ACT) {
+    // per-pixel scalars (noise, skip-image gradient) as TMA tiles: needs 16-byte aligned planes and rows
+    alignas(64) CUtensorMap tmNz, tmRg;
+    static const bool pxs_off = getenv("LFP_TC_PXS") != nullptr && atoi(getenv("LFP_TC_PXS")) == 0;
+    const bool nb1 = c.e.noise_bstride == 0;
+    bool ok = !pxs_off && c.e.noise != nullptr && (c.gw % 4) == 0 && ((uintptr_t)c.e.noise & 15) == 0 &&
+              (c.e.drgb == nullptr || ((uintptr_t)c.e.drgb & 15) == 0) && (nb1 || c.e.noise_bstride == (int64_t)c.gh * c.gw);
+    if (ok) {
+      const cuuint64_t nd[3] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, (cuuint64_t)(nb1 ? 1 : c.batch)};
+      const cuuint64_t ns[2] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4};
+      const cuuint32_t nbx[3] = {tc::TILE_W, tc::TILE_H, 1};
+      ok = tc::encode_plain(&tmNz, c.e.noise, 3, nd, ns, nbx) == 0;
+    }
+    if (ok && c.e.drgb != nullptr) {
+      const cuuint64_t rd[4] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, 3, (cuuint64_t)c.batch};
+      const cuuint64_t rs[3] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4, (cuuint64_t)3 * c.gh * c.gw * 4};
+      const cuuint32_t rbx[4] = {tc::TILE_W, tc::TILE_H, 3, 1};
+      ok = tc::encode_plain(&tmRg, c.e.drgb, 4, rd, rs, rbx) == 0;
+    }
+    a.px_ok = ok ? 1 : 0;
+    return tc_launch<EPI_DGRAD_ACT, false>(tmA, tmB, tmX, a, ntaps, s, ok ? &tmNz : nullptr, (ok && c.e.drgb != nullptr) ? &tmRg : nullptr);
+  }
   if (c.epi == EPI_DGRAD_RELU) return tc_launch<EPI_DGRAD_RELU, false>(tmA, tmB, tmX, a, ntaps, s);
   return tc_launch<EPI_DGRAD, false>(tmA, tmB, tmX, a, ntaps, s);
 }

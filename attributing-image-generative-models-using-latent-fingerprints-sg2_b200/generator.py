@@ -4,8 +4,9 @@ without the argparse global: settings are constructor arguments.
 
     wx = w0 + sd * V^T diag(sigma) k,   w0 = U^T alpha + mu,   V = pc[shift:shift+key_len]
 
-PCA (src/PCA.py:62-108) is one-off set-up outside the hot path: it runs the mapping network on the
-GPU through this package's ops and the eigendecomposition of the 512x512 covariance in torch.
+PCA (src/PCA.py:62-108) is one-off set-up outside the hot path: the mapping network of the 10 000 samples and the fp64
+mean / covariance run on the native kernels (lfp_mapping_forward, lfp_pca_covariance); only the 512 x 512 symmetric
+eigen-decomposition is a library call (torch.linalg.eigh).
 """
 from __future__ import annotations
 
@@ -39,11 +40,14 @@ def perform_pca(g_ema: Generator, n_samples: int = 10000, seed: Optional[int] = 
     gen = torch.Generator(device=dev)
     if seed is not None:
         gen.manual_seed(seed)
+    from lfp_native.mapping import MappingPlan, covariance
     with torch.no_grad():
         z = torch.randn(n_samples, g_ema.style_dim, device=dev, generator=gen)
-        w = g_ema.style(z).double()
-        mean = w.mean(0)
-        cov = (w - mean).t() @ (w - mean) / (n_samples - 1)
+        n_mlp = len(g_ema.style) - 1
+        plan = MappingPlan(g_ema.style_dim, n_mlp, g_ema.style[1].lr_mul, device=dev)
+        plan.load({k: v for k, v in g_ema.state_dict().items() if k.startswith("style.")})
+        w = plan.forward(z)                       # src/PCA.py:69 g_ema.style(noise_sample)
+        mean, cov = covariance(w)                 # what sklearn's PCA().fit diagonalises (src/PCA.py:72-73)
         evals, evecs = torch.linalg.eigh(cov)
         order = torch.argsort(evals, descending=True)
         pc = evecs[:, order].t().float().contiguous()
@@ -54,7 +58,8 @@ def perform_pca(g_ema: Generator, n_samples: int = 10000, seed: Optional[int] = 
 class GetGen:
     def __init__(self, img_size: int = 256, key_len: int = 64, shift: int = 448, sigma: float = 1.0, sd: int = 1,
                  ckpt: Optional[str] = None, device="cuda:0", pca=None, seed: Optional[int] = None,
-                 batch_size: int = 1):
+                 batch_size: int = 1, augmentation: str = "None", noise_sigma: float = 0.1, blur_sigma: float = 0.5,
+                 jpeg_quality: float = 50):
         self.device = torch.device(device)
         self.img_size, self.key_len, self.batch_size, self.sd_moved = img_size, key_len, batch_size, sd
         self.style_space_dim, self.mapping_network_layer = 512, 8
@@ -74,6 +79,12 @@ class GetGen:
         self.sigma_64 = sigma * torch.ones(key_len, 1, device=self.device)
         self.sigma_448 = torch.cat([self.sigma_512[:shift], self.sigma_512[shift + key_len:]], 0)
         self.key = None
+        # robustness attack applied once per target image (src/params.py:27-32 flag names and defaults)
+        self.augmentation_name = augmentation
+        self._attack = None
+        if augmentation != "None":
+            import attacks
+            self._attack = attacks.attack_initializer(augmentation, noise_sigma, blur_sigma, jpeg_quality).to(self.device)
 
     def get_new_latent(self, v, s, k, w0):
         """``w0 + sd * (V^T diag(s)) k`` (src/generator.py:148-161)."""
@@ -97,5 +108,8 @@ class GetGen:
         return imgs.detach(), w0.detach(), wx.detach(), key
 
     def augmentation(self, target_img):
-        """Attacks (src/generator.py:163-168) are outside this package's scope: identity."""
-        return target_img
+        """Image augmentation, default None (src/generator.py:163-168): the test-time attack of ``attacks.py``."""
+        if self._attack is None:
+            return target_img
+        with torch.no_grad():
+            return self._attack(target_img)

@@ -75,6 +75,12 @@ _PROTOS = {
     "lfp_lpips_workspace_bytes": (_sz, [_vp, _i]),
     "lfp_lpips_set_target": (_i, [_vp, _i, _vp, _vp, _sz, _i, _vp]),
     "lfp_lpips_loss_grad": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "lfp_mapping_create": (_i, [C.POINTER(_vp), _i, _i, _f]),
+    "lfp_mapping_destroy": (None, [_vp]),
+    "lfp_mapping_set_param": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "lfp_mapping_finalize": (_i, [_vp, _vp]),
+    "lfp_mapping_forward": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "lfp_pca_covariance": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "lfp_embed_forward": (_i, [_vp] * 6 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_embed_backward": (_i, [_vp] * 5 + [_f, _i, _i, _i, _i, _vp, _vp, _vp]),
     "lfp_attrib_bound_loss": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp, _vp]),

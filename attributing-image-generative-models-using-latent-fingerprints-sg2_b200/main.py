@@ -37,8 +37,13 @@ def parse():
     ap.add_argument("--lr", type=float, default=0.2)
     ap.add_argument("--shift", type=int, default=448)
     ap.add_argument("--sigma", type=float, default=1.0)
+    ap.add_argument("--augmentation", type=str, default="None", help="Augmentation method: Noise, Blur, Jpeg, Combination")
+    ap.add_argument("--jpeg_quality", type=int, default=50)
+    ap.add_argument("--noise_sigma", type=float, default=0.1)
+    ap.add_argument("--blur_sigma", type=float, default=0.5)
     ap.add_argument("--batch", type=int, default=0, help="trajectories per launch sequence (default: n)")
     ap.add_argument("--seed", type=int, default=1346)
+    ap.add_argument("--dump_rows", type=str, default=None, help="rank 0 saves the gathered [pairs, 1 + key_len + n_main] rows here (torch.save)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"],
                     help="convolution arithmetic: tf32 = tcgen05 tensor cores (what the reference's cuDNN convs use by default), "
                          "fp32 = CUDA-core FFMA")
@@ -66,7 +71,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(opt.seed)
     np.random.seed(2022)  # Generator.__init__ of the reference (src/model.py:404)
-    gen = GetGen(opt.img_size, opt.key_len, opt.shift, opt.sigma, opt.sd, ckpt=opt.ckpt, device=dev, seed=opt.seed)
+    gen = GetGen(opt.img_size, opt.key_len, opt.shift, opt.sigma, opt.sd, ckpt=opt.ckpt, device=dev, seed=opt.seed,
+                 augmentation=opt.augmentation, noise_sigma=opt.noise_sigma, blur_sigma=opt.blur_sigma,
+                 jpeg_quality=opt.jpeg_quality)
     noise = get_noise(opt.img_size, dev)
     plan = gen.g_ema._plan()
     eng = AttributionEngine(plan, noise, gen.pc, gen.sigma_512, gen.latent_mean, opt.key_len, opt.shift, opt.sigma,
@@ -81,7 +88,7 @@ def main():
             alpha, key, lhs = image_fixture(opt, gen, i)
             _, wx = eng.embed_with_key(alpha.t(), key.t())
             cache.clear()  # consecutive pairs share an image; keep one
-            cache[i] = (eng.render(wx).clone(), key, lhs)
+            cache[i] = (gen.augmentation(eng.render(wx).clone()), key, lhs)   # attack once per target image (src/main.py:124)
         return cache[i]
 
     rows, t0 = [], time.time()
@@ -98,6 +105,8 @@ def main():
     full = sharding.gather_rows(local_rows, len(pairs), rank, world)
     torch.cuda.synchronize()
     if rank == 0:
+        if opt.dump_rows:
+            torch.save(full.cpu(), opt.dump_rows)
         best, keys, _ = sharding.select_best(full, opt.n, opt.key_len)
         true = torch.cat([image_fixture(opt, gen, i)[1].t() for i in range(opt.sample_size)])
         acc = sharding.bit_accuracy(keys, true)

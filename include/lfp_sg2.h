@@ -292,6 +292,21 @@ int lfp_lpips_set_target(lfp_lpips* h, int target_batch, const float* target, vo
 int lfp_lpips_loss_grad(lfp_lpips* h, int batch, const float* est, float* loss, float* d_est, void* workspace,
                         size_t workspace_bytes, int precision, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * 8. Set-up of the fingerprint basis (additive): the mapping network Generator.style = PixelNorm +
+ *    n_mlp x (EqualLinear(lr_mul) + fused bias-lrelu) (src/model.py:407-416) on [n, dim] latents - what
+ *    GetPCA.perform_pca runs on 10 000 samples (src/PCA.py:68-70) - and the fp64 mean / covariance of the mapped latents
+ *    whose eigen-decomposition is the PCA (src/PCA.py:72-74).  Parameters by state_dict name "style.<i>.weight" [dim, dim]
+ *    / "style.<i>.bias" [dim], i = 1..n_mlp.  lfp_mapping_forward needs 2 * n * dim floats of scratch.
+ * --------------------------------------------------------------------------------- */
+typedef struct lfp_mapping lfp_mapping;
+int lfp_mapping_create(lfp_mapping** out, int dim, int n_mlp, float lr_mul);
+void lfp_mapping_destroy(lfp_mapping* h);
+int lfp_mapping_set_param(lfp_mapping* h, const char* name, const float* data, int64_t numel, void* stream);
+int lfp_mapping_finalize(lfp_mapping* h, void* stream);
+int lfp_mapping_forward(lfp_mapping* h, const float* z, int64_t n, float* w_out, void* scratch, size_t scratch_bytes, void* stream);
+int lfp_pca_covariance(const float* w, int64_t n, int dim, double* mean, double* cov, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,8 @@
 """Op-level microbenchmark (BASELINE.json configs[4]): op.upfirdn2d / op.fused_leaky_relu forward and backward on the
-hot-path shapes, CUDA-event timed, reported as algorithmic GB/s against the measured HBM peak.
+hot-path shapes, reported as algorithmic GB/s against the measured HBM peak, and model.ModulatedConv2d (native stand-alone
+layer, lfp_modconv_*) forward and forward+backward over 4-1024 px and batch 1-256, reported as TFLOP/s (2 Cin Cout 9 Hout^2
+plain, 2 Cin Cout 9 Hin^2 up; backward = data gradient, the same again) and as a fraction of max(tensor, HBM) bound.
+CUDA-event timed, L2 flushed between iterations.
     python tools/op_microbench.py [--json out.json]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,6 +20,7 @@ dev = "cuda"
 
 
 def timeit(fn, iters=20, warm=3):
+    torch.cuda.synchronize()
     for _ in range(warm):
         fn()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -60,6 +64,46 @@ for (n, c, h) in [(1, 32, 1024), (8, 32, 1024), (8, 64, 512), (16, 512, 64), (64
         rows.append(("upfirdn2d up2 pad(2,1)", (n, c, h // 2, h // 2), 4 * (numel + numel // 4), t))
         del xs
     del x
+# ---- ModulatedConv2d sweep: every generator layer shape, batch 1 .. 256 capped by the activation footprint ----
+from model import ModulatedConv2d
+from lfp_native import capi
+try:
+    TC_PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] / 2.0   # kind::tf32 = half the bf16 rate
+except Exception:
+    TC_PEAK = 700.0
+conv_rows = []
+LAYERS = [(512, 512, 4, False), (512, 512, 8, True), (512, 512, 16, False), (512, 512, 32, True), (512, 512, 64, False),
+          (512, 256, 128, True), (256, 256, 128, False), (256, 128, 256, True), (128, 128, 256, False), (128, 64, 512, True),
+          (64, 64, 512, False), (64, 32, 1024, True), (32, 32, 1024, False)]
+for (cin, cout, res, up) in LAYERS:
+    m = ModulatedConv2d(cin, cout, 3, 512, upsample=up).to(dev)
+    m.precision = capi.PREC_TF32
+    hin = res // 2 if up else res
+    for B in (1, 4, 16, 64, 256):
+        if B * max(cin * hin * hin, cout * res * res) * 4 > (3 << 30):    # keep one activation under 3 GB
+            continue
+        x = torch.randn(B, cin, hin, hin, device=dev, requires_grad=True)
+        st = torch.randn(B, 512, device=dev, requires_grad=True)
+        gy = torch.randn(B, cout, res, res, device=dev)
+        flops = 2.0 * B * cin * cout * 9 * (hin * hin if up else res * res)
+        nbytes = 4.0 * (B * cin * hin * hin + B * cout * res * res + 9 * cin * cout)
+        t_f = timeit(lambda: m(x.detach(), st.detach()), iters=8)
+
+        def fb():
+            y = m(x, st)
+            torch.autograd.grad(y, [x, st], gy)
+
+        t_fb = timeit(fb, iters=8)
+        conv_rows.append((f"modconv {cin}->{cout}{' up' if up else ''} @{res}", B, flops, nbytes, t_f, t_fb))
+        del x, st, gy
+    del m
+print(f"{'ModulatedConv2d (tf32 path)':34s} {'B':>4s} {'fwd ms':>8s} {'TF/s':>7s} {'of bound':>8s} {'fwd+bwd ms':>10s} {'TF/s':>7s}")
+conv_out = []
+for name, B, flops, nbytes, t_f, t_fb in conv_rows:
+    bound = max(flops / (TC_PEAK * 1e12), nbytes / (PEAK * 1e9))
+    print(f"{name:34s} {B:4d} {t_f*1e3:8.3f} {flops/t_f/1e12:7.1f} {bound/t_f:8.2f} {t_fb*1e3:10.3f} {2*flops/t_fb/1e12:7.1f}")
+    conv_out.append({"op": name, "batch": B, "fwd_ms": t_f * 1e3, "fwd_tflops": flops / t_f / 1e12, "fwd_frac_of_bound": bound / t_f,
+                     "fwd_bwd_ms": t_fb * 1e3, "fwd_bwd_tflops": 2 * flops / t_fb / 1e12})
 out = []
 print(f"{'op':30s} {'shape':24s} {'ms':>8s} {'GB/s':>8s} {'of HBM':>7s}")
 for name, shape, nbytes, t in rows:
@@ -67,4 +111,4 @@ for name, shape, nbytes, t in rows:
     print(f"{name:30s} {str(shape):24s} {t*1e3:8.3f} {gbs:8.0f} {gbs/PEAK:7.2f}")
     out.append({"op": name, "shape": list(shape), "ms": t * 1e3, "gbs": gbs, "frac_of_measured_hbm": gbs / PEAK})
 if len(sys.argv) > 2 and sys.argv[1] == "--json":
-    json.dump({"hbm_peak_gbs": PEAK, "rows": out}, open(sys.argv[2], "w"), indent=1)
+    json.dump({"hbm_peak_gbs": PEAK, "tf32_peak_tflops": TC_PEAK, "rows": out, "modconv_rows": conv_out}, open(sys.argv[2], "w"), indent=1)
