@@ -101,6 +101,8 @@ class Jpeg(nn.Module):
         return rec.permute(0, 1, 3, 2, 4).reshape(B, H, W)
 
     def forward(self, image):
+        if self.basis.device != image.device:     # follow the image like the reference's `.to(opt.device)` (attack_initializer.py:22)
+            self.to(image.device)
         x = (image + 1.0) / 2.0 * 255.0                                                           # Jpeg_compression.py:16 + compress(image * 255)
         ycc = torch.einsum("bchw,kc->bkhw", x, self.to_ycc)
         y, cb, cr = ycc[:, 0], ycc[:, 1] + 128.0, ycc[:, 2] + 128.0
