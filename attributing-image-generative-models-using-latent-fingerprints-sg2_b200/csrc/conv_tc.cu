@@ -61,8 +61,21 @@ constexpr int EPI_NRED(int epi) { return epi == EPI_DGRAD_ACT ? 3 : (epi == EPI_
 __host__ __device__ constexpr int EPI_SCR(bool e2, int nsets) { return e2 ? 0 : nsets * 4 * 32 * 33; }   // floats; the 16x256b epilogue reduces with shuffles
 constexpr int EPI_SMEM(int epi, int nsets, int bn, bool e2) { return EPI_NRED(epi) == 0 ? 0 : (EPI_SCR(e2, nsets) + nsets * EPI_NRED(epi) * 4 * bn) * 4; }
 
+// Division by a launch constant as a multiply-high: q = (n * M) >> (32 + s), M = ceil(2^(32+s) / d), s = ceil(log2 d), exact
+// for n < 2^31.  decode() runs per tile in every warp role; ncu attributed 13 % of all stall samples of the 32 -> 32 layer to
+// the I2F / RCP / fix-up chains of its three runtime integer divisions.
+struct FastDiv { uint64_t M; int s; int d; };
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f; f.d = d; f.s = 0;
+  while ((1ll << f.s) < d) ++f.s;
+  f.M = (uint64_t)((((unsigned __int128)1 << (32 + f.s)) + (unsigned)d - 1) / (unsigned)d);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.M == 0 ? n / f.d : (int)(((uint64_t)(uint32_t)n * f.M) >> (32 + f.s)); }
+
 struct Args {
   int batch, gh, gw, tiles_x, tiles_y, K, N, BN;
+  FastDiv d_ntiles, d_tiles_per, d_tiles_x;
   int n_ntiles, total_work;   // work item = (sample, tile, n-tile)
   int SA, SB, b_resident;     // A stages; B stages (streaming) or 0 with the whole weight slice resident
   int nacc;                   // TMEM accumulator stages (1, 2 or 4)
@@ -172,12 +185,12 @@ __device__ __forceinline__ float lrelu(float v) { return (v > 0.f ? v : v * kLre
 struct Work { int b, tile, nt, y0, x0, n0; };
 __device__ __forceinline__ Work decode(const Args& a, int w) {
   Work r;
-  r.nt = w % a.n_ntiles;
-  const int bt = w / a.n_ntiles;
+  const int bt = fdiv(w, a.d_ntiles);
+  r.nt = w - bt * a.n_ntiles;
   const int tiles_per = a.tiles_x * a.tiles_y;
-  r.b = bt / tiles_per;
+  r.b = fdiv(bt, a.d_tiles_per);
   r.tile = bt - r.b * tiles_per;
-  const int ty = r.tile / a.tiles_x;
+  const int ty = fdiv(r.tile, a.d_tiles_x);
   r.y0 = ty * TILE_H;
   r.x0 = (r.tile - ty * a.tiles_x) * TILE_W;
   r.n0 = r.nt * a.BN;
@@ -1197,6 +1210,9 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   a.out_stride = c.out_stride > 0 ? c.out_stride : 1; a.out_oy = c.out_oy; a.out_ox = c.out_ox;
   a.mod = c.mod; a.e = c.e;
   a.n_ntiles = c.N / a.BN;
+  a.d_ntiles = tc::make_fastdiv(a.n_ntiles); a.d_tiles_per = tc::make_fastdiv(a.tiles_x * a.tiles_y); a.d_tiles_x = tc::make_fastdiv(a.tiles_x);
+  static const bool plain_div = getenv("LFP_TC_FASTDIV") != nullptr && atoi(getenv("LFP_TC_FASTDIV")) == 0;   // A/B switch
+  if (plain_div) a.d_ntiles.M = a.d_tiles_per.M = a.d_tiles_x.M = 0;
   const int64_t total = (int64_t)a.tiles_x * a.tiles_y * c.batch * a.n_ntiles;
   LFP_CHECK_ARG(total < (1ll << 31), "conv_tc: too many tiles");
   a.total_work = (int)total;
