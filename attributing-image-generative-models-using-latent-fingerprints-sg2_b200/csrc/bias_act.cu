@@ -244,27 +244,23 @@ extern "C" int lfp_fused_bias_act_host(const void* x, const void* bias, const vo
   LFP_CHECK_ARG(dtype >= 0 && dtype <= 2, "fused_bias_act_host: bad dtype");
   if (size_x == 0) return 0;
   const size_t es = dtype_size(dtype);
-  void *dx = nullptr, *db = nullptr, *dr = nullptr, *dout = nullptr;
-  int rc = 0;
+  HostStaging& hs = host_staging();
+  void* dx = hs.get(0, size_x * es);
+  void* dout = hs.get(1, size_x * es);
+  void* db = bias ? hs.get(2, size_b * es) : nullptr;
+  void* dr = ref ? hs.get(3, size_x * es) : nullptr;
+  if (!dx || !dout || (bias && !db) || (ref && !dr)) { set_error("fused_bias_act_host: device allocation failed"); return LFP_ENOMEM; }
   cudaStream_t s = 0;
-  LFP_CUDA(cudaMalloc(&dx, size_x * es));
-  LFP_CUDA(cudaMalloc(&dout, size_x * es));
-  LFP_CUDA(cudaMemcpyAsync(dx, x, size_x * es, cudaMemcpyHostToDevice, s));
-  if (bias) {
-    LFP_CUDA(cudaMalloc(&db, size_b * es));
-    LFP_CUDA(cudaMemcpyAsync(db, bias, size_b * es, cudaMemcpyHostToDevice, s));
-  }
-  if (ref) {
-    LFP_CUDA(cudaMalloc(&dr, size_x * es));
-    LFP_CUDA(cudaMemcpyAsync(dr, ref, size_x * es, cudaMemcpyHostToDevice, s));
-  }
-  rc = lfp_fused_bias_act(dx, db, dr, dout, dtype, size_x, step_b, size_b, act, grad, alpha, scale, s);
+  cudaError_t e = cudaMemcpyAsync(dx, x, size_x * es, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && bias) e = cudaMemcpyAsync(db, bias, size_b * es, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && ref) e = cudaMemcpyAsync(dr, ref, size_x * es, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { set_error("fused_bias_act_host: %s", cudaGetErrorString(e)); return (int)e; }
+  int rc = lfp_fused_bias_act(dx, db, dr, dout, dtype, size_x, step_b, size_b, act, grad, alpha, scale, s);
   if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(out, dout, size_x * es, cudaMemcpyDeviceToHost, s);
+    e = cudaMemcpyAsync(out, dout, size_x * es, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { set_error("fused_bias_act_host: %s", cudaGetErrorString(e)); rc = (int)e; }
   }
-  cudaFree(dx); cudaFree(dout); cudaFree(db); cudaFree(dr);
   return rc;
 }
 

@@ -63,6 +63,37 @@ static inline int num_sms() {
   return n;
 }
 
+// Device staging buffers of the host-pointer ("_host") entry points: per host thread and device, grow-only, so a caller
+// looping over such an entry point allocates nothing after its first iteration and no return path can leak (round 1
+// allocated and freed on every call and leaked on an error between two allocations).  Freed when the thread exits.
+struct HostStaging {
+  static constexpr int kSlots = 4;
+  int dev = -1;
+  void* p[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kSlots] = {0, 0, 0, 0};
+  ~HostStaging() { release(); }
+  void release() {
+    for (int i = 0; i < kSlots; ++i) { if (p[i]) cudaFree(p[i]); p[i] = nullptr; cap[i] = 0; }
+  }
+  // nullptr on allocation failure (the slot is left empty)
+  void* get(int slot, size_t bytes) {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d != dev) { release(); dev = d; }
+    if (cap[slot] < bytes) {
+      if (p[slot]) cudaFree(p[slot]);
+      p[slot] = nullptr; cap[slot] = 0;
+      if (cudaMalloc(&p[slot], bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+      cap[slot] = bytes;
+    }
+    return p[slot];
+  }
+};
+inline HostStaging& host_staging() {
+  static thread_local HostStaging hs;
+  return hs;
+}
+
 __device__ __forceinline__ int floor_div_i(int a, int b) {
   int q = a / b;
   return (q * b > a) ? q - 1 : q;

@@ -309,9 +309,9 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             if (++sa == SAr) { sa = 0; pa ^= 1u; }
           }
         if (ring) { sa_1 = sa; sb_1 = sb; pa_1 = pa; pb_1 = pb; } else { sa_0 = sa; sb_0 = sb; pa_0 = pa; pb_0 = pb; }
-        if (DGX && a.XS > 0) {
-          // saved forward input of this tile for the epilogue (128 px x BN channels, one 16 KB box per 32 channels)
-          const int nch = a.BN >> 5;
+        if ((DGX || PXS) && a.XS > 0) {
+          // saved forward input of this tile for the epilogue (data-gradient kernels) and / or its per-pixel scalars (PXS) (128 px x BN channels, one 16 KB box per 32 channels)
+          const int nch = DGX ? a.BN >> 5 : 0;
           const uint32_t st0 = smem0 + a.xs_off + (uint32_t)sx * (uint32_t)a.xs_stride;
           mbar_wait(bar_xs_empty(sx), px ^ 1u);
           mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK + (PXS ? 512u + (RGB ? 1536u : 0u) : 0u));
@@ -537,14 +537,15 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             outp[r] = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
                                (gx * a.out_stride + a.out_ox)) * a.N + n0;
         }
-        const bool xs_smem2 = DGX && a.XS > 0;
-        const int sx = xs_smem2 ? it % a.XS : 0;
+        const bool xs_smem2 = DGX && a.XS > 0;              // saved input comes from the ring
+        const bool ring2 = (DGX || PXS) && a.XS > 0;       // the ring exists (saved input and / or per-pixel scalars)
+        const int sx = ring2 ? it % a.XS : 0;
         // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x
         const uint8_t* xbase = smem_al + a.xs_off + (size_t)sx * a.xs_stride + (32 * q + x) * 128 + (cq & 1) * 8;
-        if (xs_smem2) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
+        if (ring2) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
         if (PXS) {
           // per-pixel scalars of this tile from the ring stage: noise[row][x], skip gradient [plane][row][x]
-          const float* px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)nchunk * XS_CHUNK);
+          const float* px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)(DGX ? nchunk : 0) * XS_CHUNK);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int i = (4 * q + r) * 8 + x;
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               }
             }
           }
-        if (xs_smem2) mbar_arrive(bar_xs_empty(sx));
+        if (ring2) mbar_arrive(bar_xs_empty(sx));
         if (do_rgb2) {
 #pragma unroll
           for (int r = 0; r < 4; ++r)
@@ -1069,11 +1070,12 @@ static int tc_launch4(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 template <int EPI, bool MOD, bool RES, bool E2>
 static int tc_launch3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmX, const CUtensorMap& tmNz, const CUtensorMap& tmRg,
                       const tc::Args& a, size_t dyn_smem, cudaStream_t s) {
-  constexpr bool da = EPI == EPI_DGRAD_ACT && E2;
+  constexpr bool da = (EPI == EPI_DGRAD_ACT || EPI == EPI_ACT) && E2;   // epilogues with per-pixel scalars
   const bool pxs = da && a.px_ok && a.XS > 0;
-  if (da && a.e.drgb != nullptr)
-    return pxs ? tc_launch4<EPI, MOD, RES, E2, da, da>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s)
-               : tc_launch4<EPI, MOD, RES, E2, da, false>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s);
+  constexpr bool rgbv = EPI == EPI_DGRAD_ACT && E2;   // only the fused act-backward has a skip-gradient variant
+  if (rgbv && a.e.drgb != nullptr)
+    return pxs ? tc_launch4<EPI, MOD, RES, E2, rgbv, da>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s)
+               : tc_launch4<EPI, MOD, RES, E2, rgbv, false>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s);
   return pxs ? tc_launch4<EPI, MOD, RES, E2, false, da>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s)
              : tc_launch4<EPI, MOD, RES, E2, false, false>(tmA, tmB, tmX, tmNz, tmRg, a, dyn_smem, s);
 }
@@ -1105,9 +1107,10 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   a.nsets = (a.BN <= 128 && !MOD) ? 3 : 2;   // the modulated kernels have two epilogue sets (512-thread layout)
   constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT || EPI == EPI_DGRAD_RELU;
   // data-gradient epilogues of the HBM-bound layers (N <= 64) get their saved-input tiles through a TMA ring
-  const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : 0;
-  // ring stage = BN / 32 saved-input chunks, plus 2 KB of per-pixel scalars for the fused act-backward (PXS kernels)
-  const size_t xs_stride = (size_t)(a.BN / 32) * tc::XS_CHUNK + ((EPI == EPI_DGRAD_ACT && a.px_ok && tc_use_e2(a.BN)) ? 2048 : 0);
+  const bool px_kernel = (EPI == EPI_DGRAD_ACT || EPI == EPI_ACT) && a.px_ok && tc_use_e2(a.BN);
+  const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : ((EPI == EPI_ACT && px_kernel) ? 3 : 0);
+  // ring stage = BN / 32 saved-input chunks (data-gradient kernels), plus 2 KB of per-pixel scalars (PXS kernels)
+  const size_t xs_stride = (dg ? (size_t)(a.BN / 32) * tc::XS_CHUNK : 0) + (px_kernel ? 2048 : 0);
   a.xs_stride = (int)xs_stride;
   size_t xs_smem = 0, epi_smem = 0;
   // LFP_TC_SMEM_CAP (bytes): cap the shared memory a launch asks for, which leaves the rest of the 228 KB to the L1
@@ -1219,7 +1222,23 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   const int ntaps = c.taps.group_tap0[c.taps.ngroups];
   const CUtensorMap& tmB = *reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const unsigned char*>(c.wmap) + 128 * tc_bn_index(a.BN));
   const bool mod = c.mod != nullptr;
-  if (c.epi == EPI_ACT) return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_ACT, false>(tmA, tmB, tmA, a, ntaps, s);
+  if (c.epi == EPI_ACT) {
+    // the noise tile of every work item by TMA (PXS): needs a 16-byte aligned map with rows that are multiples of 16 bytes
+    alignas(64) CUtensorMap tmNz;
+    static const bool pxs_off = getenv("LFP_TC_PXS") != nullptr && atoi(getenv("LFP_TC_PXS")) == 0;
+    static const bool pxs_fwd_off = getenv("LFP_TC_PXS_FWD") != nullptr && atoi(getenv("LFP_TC_PXS_FWD")) == 0;
+    const bool nb1 = c.e.noise_bstride == 0;
+    bool ok = !pxs_off && !pxs_fwd_off && c.e.rgb_out == nullptr && c.e.noise != nullptr && (c.gw % 4) == 0 && ((uintptr_t)c.e.noise & 15) == 0 &&
+              (nb1 || c.e.noise_bstride == (int64_t)c.gh * c.gw);
+    if (ok) {
+      const cuuint64_t nd[3] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, (cuuint64_t)(nb1 ? 1 : c.batch)};
+      const cuuint64_t ns[2] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4};
+      const cuuint32_t nbx[3] = {tc::TILE_W, tc::TILE_H, 1};
+      ok = tc::encode_plain(&tmNz, c.e.noise, 3, nd, ns, nbx) == 0;
+    }
+    a.px_ok = ok ? 1 : 0;
+    return mod ? tc_launch<EPI_ACT, true>(tmA, tmB, tmA, a, ntaps, s, ok ? &tmNz : nullptr) : tc_launch<EPI_ACT, false>(tmA, tmB, tmA, a, ntaps, s, ok ? &tmNz : nullptr);
+  }
   if (c.epi == EPI_STORE) return mod ? tc_launch<EPI_STORE, true>(tmA, tmB, tmA, a, ntaps, s) : tc_launch<EPI_STORE, false>(tmA, tmB, tmA, a, ntaps, s);
   LFP_CHECK_ARG(!mod, "conv_tc: this epilogue takes an unmodulated input");
   if (c.epi == EPI_RELU) return tc_launch<EPI_RELU, false>(tmA, tmB, tmA, a, ntaps, s);

@@ -746,17 +746,18 @@ extern "C" int lfp_upfirdn2d_host(const void* input, const void* kernel, void* o
   const size_t es = dtype == LFP_F64 ? 8 : dtype == LFP_F16 ? 2 : 4;
   const size_t nin = (size_t)major * in_h * in_w * minor, nout = (size_t)major * (oh > 0 ? oh : 0) * (ow > 0 ? ow : 0) * minor;
   if (nin == 0 || nout == 0) return 0;
-  void *din = nullptr, *dk = nullptr, *dout = nullptr;
-  LFP_CUDA(cudaMalloc(&din, nin * es));
-  LFP_CUDA(cudaMalloc(&dk, (size_t)kh * kw * es));
-  LFP_CUDA(cudaMalloc(&dout, nout * es));
-  LFP_CUDA(cudaMemcpy(din, input, nin * es, cudaMemcpyHostToDevice));
-  LFP_CUDA(cudaMemcpy(dk, kernel, (size_t)kh * kw * es, cudaMemcpyHostToDevice));
+  HostStaging& hs = host_staging();
+  void* din = hs.get(0, nin * es);
+  void* dout = hs.get(1, nout * es);
+  void* dk = hs.get(2, (size_t)kh * kw * es);
+  if (!din || !dout || !dk) { set_error("upfirdn2d_host: device allocation failed"); return LFP_ENOMEM; }
+  cudaError_t e = cudaMemcpy(din, input, nin * es, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dk, kernel, (size_t)kh * kw * es, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { set_error("upfirdn2d_host: %s", cudaGetErrorString(e)); return (int)e; }
   int rc = lfp_upfirdn2d(din, dk, dout, dtype, major, in_h, in_w, minor, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, nullptr);
   if (rc == 0) {
-    cudaError_t e = cudaMemcpy(out, dout, nout * es, cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(out, dout, nout * es, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { set_error("upfirdn2d_host: %s", cudaGetErrorString(e)); rc = (int)e; }
   }
-  cudaFree(din); cudaFree(dk); cudaFree(dout);
   return rc;
 }
