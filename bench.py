@@ -40,6 +40,10 @@ WORKLOADS = {
     "attribution_1024px_n20_mse": dict(kind="attribution", size=1024, key_len=64, shift=448, sigma=1.0, guesses=20),
     "attribution_512px_k128_n20_mse": dict(kind="attribution", size=512, key_len=128, shift=384, sigma=1.5, guesses=20),
     "generation_1024px_b64": dict(kind="generation", size=1024, key_len=64, shift=448, sigma=1.0, guesses=64),
+    # the reference's default loss (LPIPS-VGG16, src/utils.py:44-50) on the native kernels; random VGG16 weights (no ImageNet
+    # weights offline), target features cached per image
+    "attribution_1024px_n20_lpips": dict(kind="attribution", size=1024, key_len=64, shift=448, sigma=1.0, guesses=20, loss="lpips"),
+    "attribution_256px_n20_lpips": dict(kind="attribution", size=256, key_len=64, shift=448, sigma=1.0, guesses=20, loss="lpips"),
 }
 # whole-step bound of SURVEY.md 8d: (fwd + dgrad GFLOP, ideal fused fp32 GB) per trajectory-step
 WHOLE_STEP = {256: (180.5, 0.83), 512: (238.7, 1.74), 1024: (297.0, 3.60)}
@@ -135,7 +139,7 @@ def synthetic_setup(size):
 
 def config_of(args, wl):
     """Identical for both arms (the driver compares it); arm-specific facts go to top-level keys."""
-    return {"workload": args.workload, "size": wl["size"], "trajectories_per_rank": wl["guesses"], "loss": "mse",
+    return {"workload": args.workload, "size": wl["size"], "trajectories_per_rank": wl["guesses"], "loss": wl.get("loss", "mse"),
             "key_len": wl["key_len"], "shift": wl["shift"], "sigma": wl["sigma"]}
 
 
@@ -291,8 +295,12 @@ def run_ours(args):
     params, noise, pc, sigma, mean = synthetic_setup(size)
     plan = SynthesisPlan(size, device=dev)
     plan.load(params)
+    loss_kind = wl.get("loss", "mse")
+    lpips_params = None
+    if loss_kind == "lpips":
+        lpips_params = fx.make_vgg_params(seed=1346)   # seeded random-init VGG16 weights + non-negative heads
     eng = AttributionEngine(plan, noise, pc, sigma, mean, key_len=wl["key_len"], shift=wl["shift"], sigma=wl["sigma"],
-                            sd=1.0, lr=0.2, precision=prec)
+                            sd=1.0, lr=0.2, precision=prec, loss=loss_kind, lpips_params=lpips_params)
 
     def barrier():
         if world > 1:
@@ -327,7 +335,7 @@ def run_ours(args):
     W = max(args.warmup, 3)
     # the whole Adam step is one native call replayed as a CUDA graph (lfp_attrib_run); --python-steps drives the same
     # kernels launch by launch from Python instead
-    stepper = None if args.python_steps else eng.native_stepper(st, target, max_steps=W + args.steps + args.sustained_steps + 64)
+    stepper = None if (args.python_steps or loss_kind != "mse") else eng.native_stepper(st, target, max_steps=W + args.steps + args.sustained_steps + 64)
     step_fn = (lambda: eng.step(st, target)) if stepper is None else (lambda: stepper.run(1))
     for _ in range(W):
         step_fn()
@@ -390,7 +398,7 @@ def run_ours(args):
 
     # ---- fp32 (exact-parity) path, a few steps, reported inside the same line ----
     fp32 = None
-    if args.fp32_steps > 0 and prec != capi.PREC_FP32:
+    if args.fp32_steps > 0 and prec != capi.PREC_FP32 and loss_kind == "mse":
         eng.precision = capi.PREC_FP32
         st32 = eng.init_state(eng.alpha0_from_lhs(lhs))
         eng.step(st32, target)

@@ -86,23 +86,6 @@ def perceptual_loss(params, target, est):
 
 
 def make_vgg_params(seed: int = 0, lin_weights: Dict[str, torch.Tensor] = None) -> Dict[str, torch.Tensor]:
-    """Seeded random VGG16 conv weights in torchvision's initialisation scale (kaiming-normal fan-out, zero... here small
-    seeded biases so the bias path is exercised) and non-negative linear heads (the trained heads are non-negative)."""
-    import numpy as np
-    rs = np.random.RandomState(seed)
-    p = {}
-    cin = 3
-    for si, convs in enumerate(VGG_SLICES):
-        cout = VGG_CHANNELS[si]
-        for idx in convs:
-            std = (2.0 / (cout * 9)) ** 0.5
-            p[f"net.slice{si + 1}.{idx}.weight"] = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * std).astype(np.float32))
-            p[f"net.slice{si + 1}.{idx}.bias"] = torch.from_numpy((rs.standard_normal(cout) * 0.05).astype(np.float32))
-            cin = cout
-    for k in range(5):
-        name = f"lin{k}.model.1.weight"
-        if lin_weights is not None and name in lin_weights:
-            p[name] = lin_weights[name].clone().float()
-        else:
-            p[name] = torch.from_numpy(np.abs(rs.standard_normal((1, VGG_CHANNELS[k], 1, 1))).astype(np.float32) * 0.1)
-    return p
+    """Seeded random PNetLin parameters: the shared fixture builder lives in tests/fixtures.py (bench.py uses it too)."""
+    import fixtures
+    return fixtures.make_vgg_params(seed, lin_weights)

@@ -101,3 +101,32 @@ def split_basis(pc, sigma, key_len: int = 64, shift: int = 448, fixed_sigma: flo
 
 def seeded(shape, seed, scale=1.0):
     return _randn(np.random.RandomState(seed), *shape, scale=scale)
+
+
+# torchvision vgg16().features indices of the 13 convolutions by LPIPS slice (src/custom_lpips/pretrained_networks.py:108-117)
+VGG_SLICES = ((0, 2), (5, 7), (10, 12, 14), (17, 19, 21), (24, 26, 28))
+VGG_CHANNELS = (64, 128, 256, 512, 512)
+
+
+def make_vgg_params(seed: int = 0, lin_weights: Dict[str, torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Seeded random ``PNetLin`` state dict (src/custom_lpips/networks_basic.py:27-61): VGG16 conv weights in torchvision's
+    initialisation scale (kaiming-normal, fan-out), small seeded biases so the bias path is exercised, and non-negative
+    linear heads (the trained heads are non-negative) unless ``lin_weights`` supplies them.  The ImageNet weights cannot be
+    downloaded in this environment: every LPIPS number in this repository is on these random weights."""
+    rs = np.random.RandomState(seed)
+    p: Dict[str, torch.Tensor] = {}
+    cin = 3
+    for si, convs in enumerate(VGG_SLICES):
+        cout = VGG_CHANNELS[si]
+        for idx in convs:
+            std = (2.0 / (cout * 9)) ** 0.5
+            p[f"net.slice{si + 1}.{idx}.weight"] = torch.from_numpy((rs.standard_normal((cout, cin, 3, 3)) * std).astype(np.float32))
+            p[f"net.slice{si + 1}.{idx}.bias"] = torch.from_numpy((rs.standard_normal(cout) * 0.05).astype(np.float32))
+            cin = cout
+    for k in range(5):
+        name = f"lin{k}.model.1.weight"
+        if lin_weights is not None and name in lin_weights:
+            p[name] = lin_weights[name].clone().float()
+        else:
+            p[name] = torch.from_numpy(np.abs(rs.standard_normal((1, VGG_CHANNELS[k], 1, 1))).astype(np.float32) * 0.1)
+    return p
