@@ -19,8 +19,19 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(const float* __restrict_
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int b = blockIdx.y;
   if (j >= dim) return;
-  float acc = 0.f;
-  for (int i = 0; i < n_main; ++i) acc = fmaf(__ldg(U + (int64_t)i * dim + j), __ldg(alpha + (int64_t)b * n_main + i), acc);
+  // four interleaved accumulators (rows i, i+1, i+2, i+3 of U): one dependent chain of 448 loads made the launch
+  // latency-bound (80 us per step)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* al = alpha + (int64_t)b * n_main;
+  int i = 0;
+  for (; i + 4 <= n_main; i += 4) {
+    a0 = fmaf(__ldg(U + (int64_t)i * dim + j), __ldg(al + i), a0);
+    a1 = fmaf(__ldg(U + (int64_t)(i + 1) * dim + j), __ldg(al + i + 1), a1);
+    a2 = fmaf(__ldg(U + (int64_t)(i + 2) * dim + j), __ldg(al + i + 2), a2);
+    a3 = fmaf(__ldg(U + (int64_t)(i + 3) * dim + j), __ldg(al + i + 3), a3);
+  }
+  for (; i < n_main; ++i) a0 = fmaf(__ldg(U + (int64_t)i * dim + j), __ldg(al + i), a0);
+  const float acc = (a0 + a1) + (a2 + a3);
   const float base = acc + __ldg(mu + j);
   float e = 0.f;
   for (int k = 0; k < key_len; ++k)

@@ -1175,41 +1175,52 @@ int launch_style_affine(const float* latent, const float* A, const float* bias, 
 }
 
 // d_latent[b, slot, j] = sum over the rows r of the slot of ds[b, r] * A[r, j], eight samples per CTA: a row of A is read
-// once for the eight (it was read once per sample: 20 x 12 MB through L2 per step).  Same per-sample summation order as
-// style_affine_bwd_kernel: warp w walks rows r0 + w + 8u (u < 4) + 32i with one accumulator per u.
+// once for the eight.  The slot's ds values are staged in shared memory 256 rows at a time (coalesced), then warp w walks
+// rows w + 8u (u < 8) + 64i of the chunk with eight independent loads of A in flight (the first version issued one
+// dependent L2 round trip per row and took 210 us per step; this one is bandwidth-shaped).  Fixed summation order per
+// sample: two accumulators per sample (even / odd u), warps combined in ascending order.
 __global__ void __launch_bounds__(256) style_affine_bwd8_kernel(const float* __restrict__ ds, const float* __restrict__ A,
                                                                 const int* __restrict__ row_begin, const int* __restrict__ row_end,
                                                                 const int* __restrict__ row_base, const int* __restrict__ row_cin,
                                                                 float* __restrict__ d_latent, int batch, int n_latent, int dim) {
+  __shared__ float ds_s[8][256];
   __shared__ float part[8][8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   const int slot = blockIdx.y, b0 = blockIdx.z * 8;
   const int nb = min(8, batch - b0);
   const int r0 = row_begin[slot], r1 = row_end[slot];
-  float acc[8][4];
+  float acc[8][2];
 #pragma unroll
-  for (int bb = 0; bb < 8; ++bb)
+  for (int bb = 0; bb < 8; ++bb) acc[bb][0] = acc[bb][1] = 0.f;
+  for (int c0 = r0; c0 < r1; c0 += 256) {
+    const int nrow = min(256, r1 - c0);
+    __syncthreads();
+    {   // thread t stages row c0 + t of the eight samples
+      const int r = c0 + threadIdx.x;
+      if (threadIdx.x < nrow) {
+        const int base = row_base[r], cin = row_cin[r];
+        const float* dsr = ds + (int64_t)batch * base + (int64_t)b0 * cin + (r - base);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[bb][u] = 0.f;
-  if (j < dim) {
-    for (int rr = r0 + w; rr < r1; rr += 32) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = rr + u * 8;
-        if (r < r1) {
-          const int base = row_base[r], cin = row_cin[r];
-          const float av = __ldg(A + (int64_t)r * dim + j);
-          const float* dsr = ds + (int64_t)batch * base + (int64_t)b0 * cin + (r - base);
-#pragma unroll
-          for (int bb = 0; bb < 8; ++bb)
-            if (bb < nb) acc[bb][u] = fmaf(__ldg(dsr + (int64_t)bb * cin), av, acc[bb][u]);
-        }
+        for (int bb = 0; bb < 8; ++bb) ds_s[bb][threadIdx.x] = bb < nb ? __ldg(dsr + (int64_t)bb * cin) : 0.f;
       }
     }
+    __syncthreads();
+    if (j < dim)
+      for (int rr = w; rr < nrow; rr += 64) {
+        float av[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) av[u] = rr + 8 * u < nrow ? __ldg(A + (int64_t)(c0 + rr + 8 * u) * dim + j) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = rr + 8 * u < nrow ? rr + 8 * u : 0;
+#pragma unroll
+          for (int bb = 0; bb < 8; ++bb) acc[bb][u & 1] = fmaf(ds_s[bb][r], av[u], acc[bb][u & 1]);
+        }
+      }
   }
 #pragma unroll
-  for (int bb = 0; bb < 8; ++bb) part[bb][w][lane] = (acc[bb][0] + acc[bb][1]) + (acc[bb][2] + acc[bb][3]);
+  for (int bb = 0; bb < 8; ++bb) part[bb][w][lane] = acc[bb][0] + acc[bb][1];
   __syncthreads();
   if (w < nb && j < dim) {   // warp w finishes sample b0 + w
     float t = 0.f;
@@ -1312,16 +1323,20 @@ __global__ void __launch_bounds__(1024) batched_partial_reduce_kernel(const Redu
   const int Q = it.Q, C = it.C;
   const int per = (Q + NR - 1) / NR;
   const int q0 = qy * per, q1 = min(Q, q0 + per);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  // eight independent accumulators: the loads of a range are L2 round trips, and four in flight per thread left the
+  // launch latency-bound (210 us per step for ~100 MB of partials)
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
   if (c < C && qy < NR) {
     const float* p = ws + it.src_off + ((int64_t)b * Q + q0) * C + c;
+    const int64_t Cs = C;
     int q = q0;
-    for (; q + 4 <= q1; q += 4, p += 4 * (int64_t)C) {
-      a0 += __ldg(p); a1 += __ldg(p + C); a2 += __ldg(p + 2 * (int64_t)C); a3 += __ldg(p + 3 * (int64_t)C);
+    for (; q + 8 <= q1; q += 8, p += 8 * Cs) {
+      a0 += __ldg(p); a1 += __ldg(p + Cs); a2 += __ldg(p + 2 * Cs); a3 += __ldg(p + 3 * Cs);
+      a4 += __ldg(p + 4 * Cs); a5 += __ldg(p + 5 * Cs); a6 += __ldg(p + 6 * Cs); a7 += __ldg(p + 7 * Cs);
     }
-    for (; q < q1; ++q, p += C) a0 += __ldg(p);
+    for (; q < q1; ++q, p += Cs) a0 += __ldg(p);
   }
-  sm[qy][cx] = (a0 + a1) + (a2 + a3);
+  sm[qy][cx] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
   __syncthreads();
   if (qy == 0 && c < C) {
     float t = 0.f;
