@@ -208,7 +208,7 @@ class AttributionEngine:
         whole step is one captured CUDA graph replayed per step; otherwise every step is driven from Python through the
         same kernels (bit-identical results, tests/test_attribution_gpu.py)."""
         st = self.init_state(alpha0, optimise_alpha)
-        if native and steps > 0 and self.loss_kind == "mse":   # the captured step covers the MSE loss
+        if native and steps > 0:
             self.native_stepper(st, target, max_steps=max(steps, 1)).run(steps)
             return st
         for _ in range(steps):
@@ -250,6 +250,13 @@ class NativeStepper:
                                          ptr(st["key"]), ptr(st["m_a"]), ptr(st["v_a"]), ptr(st["m_k"]), ptr(st["v_k"]),
                                          ptr(self.loss), 1 if st["optimise_alpha"] else 0, base,
                                          self.ws.data_ptr() + self.ws.numel() - base), "attrib_bind")
+            if eng.loss_kind == "lpips":    # the perceptual loss inside the captured step
+                eng.lpips.set_target(self.target, eng.precision)
+                n = int(L.lfp_lpips_workspace_bytes(eng.lpips._h, B))
+                self.lpips_ws = torch.empty(n + 256, dtype=torch.uint8, device=self.device)
+                lbase = (self.lpips_ws.data_ptr() + 255) // 256 * 256
+                capi.check(L.lfp_attrib_set_lpips(self._h, eng.lpips._h, lbase, self.lpips_ws.data_ptr() + self.lpips_ws.numel() - lbase),
+                           "attrib_set_lpips")
             self.stream = torch.cuda.Stream(self.device)
             self._dev_step = None
 

@@ -61,6 +61,7 @@ struct lfp_attrib {
   float *w0 = nullptr, *wx = nullptr, *latent = nullptr, *image = nullptr, *d_image = nullptr, *mse = nullptr, *d_latent = nullptr, *d_wx = nullptr;
   void* mse_scratch = nullptr; size_t mse_scratch_bytes = 0;
   void* synth_ws = nullptr; size_t synth_ws_bytes = 0;
+  lfp_lpips* lpips = nullptr; void* lpips_ws = nullptr; size_t lpips_ws_bytes = 0;   // optional perceptual loss instead of MSE
   cudaGraphExec_t exec = nullptr; cudaGraph_t graph = nullptr; bool warmed = false;
   ~lfp_attrib() {
     if (exec) cudaGraphExecDestroy(exec);
@@ -96,8 +97,11 @@ int enqueue_step(lfp_attrib* h, cudaStream_t s) {
   broadcast_latent_kernel<<<(unsigned)ceil_div(nl, 256), 256, 0, s>>>(h->wx, h->latent, h->n_latent, h->dim, nl);
   LFP_LAUNCH_CHECK();
   LFP_TRY(lfp_synth_forward(h->plan, B, h->latent, h->noise.data(), h->noise_batch.data(), h->image, h->synth_ws, h->synth_ws_bytes, h->precision, s));
-  LFP_TRY(lfp_mse_loss_grad(h->image, h->target, h->target_batch, B, (int64_t)3 * h->size * h->size, h->mse, h->d_image, h->mse_scratch,
-                            h->mse_scratch_bytes, s));
+  if (h->lpips != nullptr)   // src/main.py:63 with the reference's default loss; target features were cached by lfp_lpips_set_target
+    LFP_TRY(lfp_lpips_loss_grad(h->lpips, B, h->image, h->mse, h->d_image, h->lpips_ws, h->lpips_ws_bytes, h->precision, s));
+  else
+    LFP_TRY(lfp_mse_loss_grad(h->image, h->target, h->target_batch, B, (int64_t)3 * h->size * h->size, h->mse, h->d_image, h->mse_scratch,
+                              h->mse_scratch_bytes, s));
   LFP_TRY(lfp_synth_backward(h->plan, B, h->d_image, h->d_latent, h->synth_ws, h->synth_ws_bytes, h->precision, s));
   const int64_t nw = (int64_t)B * h->dim;
   slot_sum_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, s>>>(h->d_latent, h->d_wx, h->n_latent, h->dim, nw);
@@ -171,6 +175,17 @@ extern "C" int lfp_attrib_bind(lfp_attrib* h, const float* const* noise, const i
   if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }   // pointers are baked into a captured graph
   if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
   h->bound = true; h->warmed = false;
+  return 0;
+}
+
+extern "C" int lfp_attrib_set_lpips(lfp_attrib* h, lfp_lpips* lpips, void* workspace, size_t workspace_bytes) {
+  LFP_CHECK_ARG(h != nullptr, "attrib_set_lpips: null handle");
+  LFP_CHECK_ARG(lpips == nullptr || (workspace != nullptr && workspace_bytes >= lfp_lpips_workspace_bytes(lpips, h->batch)),
+                "attrib_set_lpips: workspace missing or smaller than lfp_lpips_workspace_bytes(batch)");
+  h->lpips = lpips; h->lpips_ws = workspace; h->lpips_ws_bytes = workspace_bytes;
+  if (h->exec) { cudaGraphExecDestroy(h->exec); h->exec = nullptr; }
+  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  h->warmed = false;
   return 0;
 }
 

@@ -57,6 +57,7 @@ _PROTOS = {
     "lfp_attrib_destroy": (None, [_vp]),
     "lfp_attrib_workspace_bytes": (_sz, [_vp]),
     "lfp_attrib_bind": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i), _vp, _i] + [_vp] * 7 + [_i, _vp, _sz]),
+    "lfp_attrib_set_lpips": (_i, [_vp, _vp, _vp, _sz]),
     "lfp_attrib_set_step": (_i, [_vp, _i, _vp]),
     "lfp_attrib_get_w0": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "lfp_attrib_run": (_i, [_vp, _i, _i, _vp]),

@@ -335,7 +335,7 @@ def run_ours(args):
     W = max(args.warmup, 3)
     # the whole Adam step is one native call replayed as a CUDA graph (lfp_attrib_run); --python-steps drives the same
     # kernels launch by launch from Python instead
-    stepper = None if (args.python_steps or loss_kind != "mse") else eng.native_stepper(st, target, max_steps=W + args.steps + args.sustained_steps + 64)
+    stepper = None if args.python_steps else eng.native_stepper(st, target, max_steps=W + args.steps + args.sustained_steps + 64)
     step_fn = (lambda: eng.step(st, target)) if stepper is None else (lambda: stepper.run(1))
     for _ in range(W):
         step_fn()

@@ -241,6 +241,10 @@ size_t lfp_attrib_workspace_bytes(const lfp_attrib* h);
 int lfp_attrib_bind(lfp_attrib* h, const float* const* noise, const int* noise_batch, const float* target, int target_batch,
                     float* alpha, float* key_logits, float* m_alpha, float* v_alpha, float* m_key, float* v_key,
                     float* loss_total, int optimise_alpha, void* workspace, size_t workspace_bytes);
+/* Use the perceptual loss (group 7) instead of the MSE in the step: `lpips` must have had lfp_lpips_set_target called with
+ * this step's target; `workspace` >= lfp_lpips_workspace_bytes(lpips, batch).  NULL switches back to the MSE. */
+struct lfp_lpips;
+int lfp_attrib_set_lpips(lfp_attrib* h, struct lfp_lpips* lpips, void* workspace, size_t workspace_bytes);
 int lfp_attrib_set_step(lfp_attrib* h, int step, void* stream);   /* index of the next step (0-based) */
 int lfp_attrib_get_w0(const lfp_attrib* h, const float** w0, const float** wx);   /* latents of the last step, [B, dim] */
 int lfp_attrib_run(lfp_attrib* h, int steps, int use_graph, void* stream);

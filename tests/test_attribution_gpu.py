@@ -342,7 +342,10 @@ def test_lpips_loop_two_steps_against_oracle():
         target, _, _ = oracle.generate_with_alpha(params, size, alpha_t, sp["u_cap"], sp["v_cap"], sp["sigma_key"], mean, key_t, noise)
     # random-init images are not in [-1, 1]; LPIPS does not care, but keep the scale sane for the normalisation
     a0 = sp["sigma_main"] * fx.seeded((448, 1), 36)
-    st = eng.run(a0.t().contiguous(), target.to(DEV), steps=2)
+    st = eng.run(a0.t().contiguous(), target.to(DEV), steps=2)                      # native: LPIPS inside the captured step
+    st_py = eng.run(a0.t().contiguous(), target.to(DEV), steps=2, native=False)     # the same kernels driven from Python
+    for k in ("alpha", "key", "loss"):
+        assert torch.equal(st[k], st_py[k]), k
 
     def render(wx):
         return oracle.generator_forward(params, [wx.reshape(1, -1)], size, input_is_latent=True, noise=noise)
