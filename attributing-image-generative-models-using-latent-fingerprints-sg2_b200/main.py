@@ -1,7 +1,7 @@
 """Sharded attribution driver - the experiment of src/main.py:93-154 on N GPUs of one box.
 
     python main.py --img_size 1024 --sample_size 100 --n 20 --steps 2000 --key_len 64 --shift 448
-    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 main.py ...
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 main.py ... --guesses 20   (not --n: torchrun's parser claims it)
 
 Every (image, guess) pair is an independent trajectory (sharding.py); each rank runs its slice in
 batches through ``attribution.AttributionEngine`` and the final rows are gathered once over NCCL.
@@ -31,7 +31,9 @@ def parse():
     ap.add_argument("--sample_size", type=int, default=100)
     ap.add_argument("--sd", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--n", type=int, default=20)
+    ap.add_argument("--n", "--guesses", dest="n", type=int, default=20,
+                    help="Latin-hypercube guesses per image (src/params.py:17); spell it --guesses under torchrun, whose own "
+                         "argument parser claims --n as an abbreviation of --nnodes / --nproc-per-node")
     ap.add_argument("--key_len", type=int, default=64)
     ap.add_argument("--save_dir", type=str, default="../result/")
     ap.add_argument("--lr", type=float, default=0.2)

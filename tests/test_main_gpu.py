@@ -17,14 +17,21 @@ ARGS = ["--img_size", "64", "--sample_size", "3", "--n", "4", "--steps", "6", "-
 
 def run_main(tmp, tag, world, extra=()):
     rows = os.path.join(tmp, f"rows_{tag}.pt")
-    cmd = [sys.executable]
-    if world > 1:
-        cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-                "--master-port", str(29600 + world)]
-    cmd += [MAIN] + ARGS + ["--save_dir", os.path.join(tmp, tag), "--dump_rows", rows] + list(extra)
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr[-2000:]
-    summary = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    cmd = [sys.executable, MAIN] + ARGS + ["--save_dir", os.path.join(tmp, tag), "--dump_rows", rows] + list(extra)
+    # one process per GPU, rendezvous through the environment (what torchrun sets; torchrun's own argparse would claim the
+    # reference's `--n` flag as an abbreviation of its `--nnodes` / `--nproc-per-node`)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(29600 + world))
+        if world == 1:
+            for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+                env.pop(k)
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    summary = json.loads([l for l in outs[0][0].splitlines() if l.startswith("{")][-1])
     assert os.path.isfile(os.path.join(tmp, tag, "result.txt"))
     return torch.load(rows), summary
 
