@@ -81,6 +81,7 @@ struct Args {
   int nacc;                   // TMEM accumulator stages (1, 2 or 4)
   int epi_off;                // byte offset of the epilogue scratch in dynamic shared memory
   int XS, xs_off;             // xsave ring: stages (0 = epilogue reads xsave from global) and byte offset in dynamic smem
+  int xs_has_x;               // the ring stages carry the saved-input chunks (0: per-pixel scalars only, saved input from global)
   int px_ok;                  // host: tensor maps for the per-pixel scalars exist (PXS kernel when a ring is planned)
   int xs_stride;              // bytes per ring stage: BN / 32 saved-input chunks (+ 2 KB of per-pixel scalars, PXS kernels)
   int xs_bcast;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         if (ring) { sa_1 = sa; sb_1 = sb; pa_1 = pa; pb_1 = pb; } else { sa_0 = sa; sb_0 = sb; pa_0 = pa; pb_0 = pb; }
         if ((DGX || PXS) && a.XS > 0) {
           // saved forward input of this tile for the epilogue (data-gradient kernels) and / or its per-pixel scalars (PXS) (128 px x BN channels, one 16 KB box per 32 channels)
-          const int nch = DGX ? a.BN >> 5 : 0;
+          const int nch = (DGX && a.xs_has_x) ? a.BN >> 5 : 0;
           const uint32_t st0 = smem0 + a.xs_off + (uint32_t)sx * (uint32_t)a.xs_stride;
           mbar_wait(bar_xs_empty(sx), px ^ 1u);
           mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK + (PXS ? 512u + (RGB ? 1536u : 0u) : 0u));
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             outp[r] = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
                                (gx * a.out_stride + a.out_ox)) * a.N + n0;
         }
-        const bool xs_smem2 = DGX && a.XS > 0;              // saved input comes from the ring
+        const bool xs_smem2 = DGX && a.XS > 0 && a.xs_has_x;   // saved input comes from the ring
         const bool ring2 = (DGX || PXS) && a.XS > 0;       // the ring exists (saved input and / or per-pixel scalars)
         const int sx = ring2 ? it % a.XS : 0;
         // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         if (ring2) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
         if (PXS) {
           // per-pixel scalars of this tile from the ring stage: noise[row][x], skip gradient [plane][row][x]
-          const float* px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)(DGX ? nchunk : 0) * XS_CHUNK);
+          const float* px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)((DGX && a.xs_has_x) ? nchunk : 0) * XS_CHUNK);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int i = (4 * q + r) * 8 + x;
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     const int wstep = a.nsets * gridDim.x;
     float nz_n, rg0_n, rg1_n, rg2_n;
     fetch(blockIdx.x + eset * gridDim.x, nz_n, rg0_n, rg1_n, rg2_n);
-    const bool xs_smem = DGX && a.XS > 0;
+    const bool xs_smem = DGX && a.XS > 0 && a.xs_has_x;
     const int nchunk = a.BN >> 5;
     int it = eset;
     for (int w = eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work; w < a.total_work; w += wstep, it += a.nsets) {
@@ -1108,9 +1109,12 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   constexpr bool dg = EPI == EPI_DGRAD || EPI == EPI_DGRAD_ACT || EPI == EPI_DGRAD_RELU;
   // data-gradient epilogues of the HBM-bound layers (N <= 64) get their saved-input tiles through a TMA ring
   const bool px_kernel = (EPI == EPI_DGRAD_ACT || EPI == EPI_ACT) && a.px_ok && tc_use_e2(a.BN);
-  const int xs_max = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 3 : ((EPI == EPI_ACT && px_kernel) ? 3 : 0);
-  // ring stage = BN / 32 saved-input chunks (data-gradient kernels), plus 2 KB of per-pixel scalars (PXS kernels)
-  const size_t xs_stride = (dg ? (size_t)(a.BN / 32) * tc::XS_CHUNK : 0) + (px_kernel ? 2048 : 0);
+  // the ring carries the saved-input tiles of the HBM-bound data-gradient layers (N <= 64) and / or, for the PXS kernels
+  // of any width, the per-pixel scalars
+  a.xs_has_x = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 1 : 0;
+  const int xs_max = (a.xs_has_x || px_kernel) ? 3 : 0;
+  // ring stage = BN / 32 saved-input chunks (when carried), plus 2 KB of per-pixel scalars (PXS kernels)
+  const size_t xs_stride = (a.xs_has_x ? (size_t)(a.BN / 32) * tc::XS_CHUNK : 0) + (px_kernel ? 2048 : 0);
   a.xs_stride = (int)xs_stride;
   size_t xs_smem = 0, epi_smem = 0;
   // LFP_TC_SMEM_CAP (bytes): cap the shared memory a launch asks for, which leaves the rest of the 228 KB to the L1
@@ -1165,7 +1169,8 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // 1649 -> 1396 us with six stages instead of eight)
   if (a.b_resident && smem_cap >= (size_t)tc::SMEM_OPTIN) {
     const size_t fixed = (size_t)b_all + epi_smem + 1024 + tc::STATIC_SMEM_RESERVE;
-    while (a.SA > 5 && fixed + (size_t)a.SA * tc::A_STAGE > 196u * 1024u) --a.SA;
+    static const int l1_min_sa = getenv("LFP_TC_L1_MIN_SA") ? atoi(getenv("LFP_TC_L1_MIN_SA")) : 5;
+    while (a.SA > l1_min_sa && fixed + (size_t)a.SA * tc::A_STAGE > 196u * 1024u) --a.SA;
   }
   if (const char* e = getenv("LFP_TC_SA_MAX")) { const int v = atoi(e); if (v >= 2 && a.SA > v) a.SA = v; }
   a.nacc = a.BN * a.taps.nphase <= 128 ? 4 : (a.BN * a.taps.nphase <= 256 ? 2 : 1);

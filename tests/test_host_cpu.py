@@ -101,3 +101,17 @@ def test_plan_param_names_cover_synthesis_parameters():
     g = Generator(64, 512, 8)
     synth = {k for k, _ in g.named_parameters() if not k.startswith("style.")}
     assert set(plan_param_names(64)) == synth
+
+
+def test_generator_constructor_reseeds_numpy_like_the_reference(golden):
+    """src/model.py:404: Generator.__init__ calls np.random.seed(2022), and utils.get_noise() (src/utils.py:128-138) draws every
+    noise map after the 4x4 from that global stream.  Constructing this package's Generator and then building the noise the
+    reference's way must reproduce the reference's maps (golden: first 8 values of each map at 32 px)."""
+    import numpy as np
+    from model import Generator
+    from generator import get_noise
+    np.random.seed(123)                       # whatever the caller did before
+    Generator(32, 512, 8)
+    maps = get_noise(32, "cpu")
+    head = np.stack([m.reshape(-1)[:8].numpy() for m in maps])
+    np.testing.assert_array_equal(head, golden["embed/get_noise_head"])
