@@ -527,22 +527,37 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
           for (int r = 0; r < 4; ++r) { cnz[r] = nw2 * nz_n[r]; crg[r][0] = rg_n[r][0]; crg[r][1] = rg_n[r][1]; crg[r][2] = rg_n[r][2]; }
           LFP_FETCH2(w + wstep, nz_n, rg_n)
         }
-        bool valid[4];
-        float* outp[4];
+        // Addresses are built once per tile (row pointers) and once per 32-channel chunk; inside the unrolled (k, row) body every
+        // load / store is base register + immediate.  ncu on the 32 -> 32 act-backward launch at 1024 px: the epilogue sets were
+        // busy > 90 % of the time at ~1140 warp instructions per tile, a third of them 64-bit address arithmetic, null-pointer
+        // tests and the generic -> shared conversion repeated for every saved-input load; 17 % of their stall samples were
+        // instruction-fetch misses of the ~25 KB unrolled body.
+        bool valid[4], st_ok[4];
+        float* outq[4];        // output row pointers at channel n0 + 2 cq (never dereferenced when !st_ok)
+        const float* xg0;      // without the ring (BN = 128): the saved input straight from global memory (first row, same channel offset)
+        int64_t xrow;
+        {
+          const int gy0 = wk.y0 + 4 * q;
+          float* const o0 = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy0 * a.out_stride + a.out_oy)) * a.out_w +
+                                     (gx * a.out_stride + a.out_ox)) * a.N + n0 + 2 * cq;
+          const int64_t orow = (int64_t)a.out_stride * a.out_w * a.N;
+          xg0 = DGX ? a.e.xsave + (int64_t)b * a.e.xsave_bstride + ((int64_t)gy0 * a.gw + gx) * a.N + n0 + 2 * cq : nullptr;
+          xrow = (int64_t)a.gw * a.N;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int gy = wk.y0 + 4 * q + r;
-          valid[r] = gy < a.gh && gx < a.gw;
-          outp[r] = nullptr;
-          if (a.out != nullptr && valid[r])
-            outp[r] = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy * a.out_stride + a.out_oy)) * a.out_w +
-                               (gx * a.out_stride + a.out_ox)) * a.N + n0;
+          for (int r = 0; r < 4; ++r) {
+            valid[r] = gy0 + r < a.gh && gx < a.gw;
+            st_ok[r] = valid[r] && a.out != nullptr;
+            outq[r] = o0 + r * orow;
+          }
         }
         const bool xs_smem2 = DGX && a.XS > 0 && a.xs_has_x;   // saved input comes from the ring
         const bool ring2 = (DGX || PXS) && a.XS > 0;       // the ring exists (saved input and / or per-pixel scalars)
         const int sx = ring2 ? it % a.XS : 0;
-        // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x
-        const uint8_t* xbase = smem_al + a.xs_off + (size_t)sx * a.xs_stride + (32 * q + x) * 128 + (cq & 1) * 8;
+        // saved-input tile (TMA, SWIZZLE_128B): pixel m = 32q + 8r + x is row m, its 16-byte channel quad j sits at j ^ x;
+        // quad of channel pair (k, cq) is j = 2k + (cq >> 1), so its byte position is xo0 ^ (k << 5)
+        const uint32_t xs_stage = smem0 + (uint32_t)a.xs_off + (uint32_t)sx * (uint32_t)a.xs_stride;
+        const uint32_t xs_row = xs_stage + (uint32_t)((32 * q + x) * 128 + (cq & 1) * 8);
+        const uint32_t xo0 = (uint32_t)(((cq >> 1) ^ x) << 4);
         if (ring2) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
         if (PXS) {
           // per-pixel scalars of this tile from the ring stage: noise[row][x], skip gradient [plane][row][x]
@@ -554,20 +569,30 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             crg[r][0] = RGB ? px[128 + i] : 0.f; crg[r][1] = RGB ? px[256 + i] : 0.f; crg[r][2] = RGB ? px[384 + i] : 0.f;
           }
         }
-        const float* xg[4];   // without the ring (BN = 128): the saved input straight from global memory
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          xg[r] = nullptr;
-          if (DGX && !xs_smem2 && valid[r])
-            xg[r] = a.e.xsave + (int64_t)b * a.e.xsave_bstride + ((int64_t)(wk.y0 + 4 * q + r) * a.gw + gx) * a.N + n0;
-        }
         float rgbacc[4][3];
 #pragma unroll
         for (int r = 0; r < 4; ++r) rgbacc[r][0] = rgbacc[r][1] = rgbacc[r][2] = 0.f;
-        mbar_wait(bar_acc_full(as), ((uint32_t)it >> acc_shift) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr bool VEC_DB = EPI == EPI_ACT || EPI == EPI_DGRAD_ACT;   // per-(sample, channel) demodulation and per-channel bias
+        constexpr bool VEC_B = VEC_DB || EPI == EPI_RELU;
         for (int ph = 0; ph < nphase; ++ph)
           for (int c = 0; c < nchunk; ++c) {
+            // per-channel vectors of this chunk, all four k at once and (first chunk) before the wait for the accumulator:
+            // one L2 round trip per chunk instead of one per k behind the stores of the previous k
+            const int64_t bn0 = (int64_t)b * a.N + n0 + c * 32 + 2 * cq;
+            const int nc0 = n0 + c * 32 + 2 * cq;
+            // (forward epilogues only: the data-gradient epilogues have no registers to spare for them and load per k)
+            constexpr bool VPRE = !DG;
+            float2 vD[4], vB[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              vD[k] = vB[k] = make_float2(0.f, 0.f);
+              if (VPRE && VEC_DB) vD[k] = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn0) + 4 * k);
+              if (VPRE && VEC_B) vB[k] = __ldg(reinterpret_cast<const float2*>(a.e.bias + nc0) + 4 * k);
+            }
+            if (ph == 0 && c == 0) {
+              mbar_wait(bar_acc_full(as), ((uint32_t)it >> acc_shift) & 1u);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             uint32_t acc[2][16];   // [half][4k + 2 j2 + e]: row r = 2 half + j2
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -584,40 +609,52 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
               mbar_arrive(bar_acc_empty(as));
             }
-            float* op[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) op[r] = outp[r];
-            if (EPI == EPI_STORE && nphase > 1) {
+            // store pointers of this (phase, chunk) at channel 2 cq of the chunk (+ 8 k floats per k): the row pointers themselves,
+            // advanced by 32 channels at the end of every chunk
+            if (EPI == EPI_STORE && nphase > 1 && c == 0) {
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
                 const int gy = wk.y0 + 4 * q + r;
-                op[r] = nullptr;
-                if (a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1)) {
-                  if (a.out_stride == 2)   // phases interleaved into the [2H+1, 2W+1] image: (2 gy + a, 2 gx + b)
-                    op[r] = a.out + (((int64_t)b * (2 * a.out_h - 1) + (2 * gy + (ph >> 1))) * (2 * a.out_w - 1) + (2 * gx + (ph & 1))) * a.N + n0;
-                  else
-                    op[r] = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0;
-                }
+                st_ok[r] = a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1);
+                if (a.out_stride == 2)   // phases interleaved into the [2H+1, 2W+1] image: (2 gy + a, 2 gx + b)
+                  outq[r] = a.out + (((int64_t)b * (2 * a.out_h - 1) + (2 * gy + (ph >> 1))) * (2 * a.out_w - 1) + (2 * gx + (ph & 1))) * a.N + n0 + 2 * cq;
+                else
+                  outq[r] = a.out + ((((int64_t)b * a.out_planes + ph) * a.out_h + gy) * a.out_w + gx) * a.N + n0 + 2 * cq;
               }
             }
+            const uint32_t xs_c = xs_row + (uint32_t)c * XS_CHUNK;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int ch = c * 32 + 8 * k + 2 * cq;       // channel offset inside this CTA's BN slice
-              const int64_t bn = (int64_t)b * a.N + n0 + ch;
               auto av = [&](int r, int e) { return __uint_as_float(acc[r >> 1][4 * k + 2 * (r & 1) + e]); };
+              auto st2 = [&](int r, float v0, float v1) { if (st_ok[r]) *reinterpret_cast<float2*>(outq[r] + 8 * k) = make_float2(v0, v1); };
+              // saved forward input of the four rows (channel pair of this k)
+              float2 xk[4];
+              if (DGX) {
+                if (xs_smem2) {
+                  const uint32_t ad = xs_c + (xo0 ^ (uint32_t)(k << 5));
+#pragma unroll
+                  for (int r = 0; r < 4; ++r)
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(xk[r].x), "=f"(xk[r].y) : "r"(ad + (uint32_t)(r * 8 * 128)));
+                } else {
+#pragma unroll
+                  for (int r = 0; r < 4; ++r) {
+                    xk[r] = make_float2(0.f, 0.f);
+                    if (valid[r]) xk[r] = __ldg(reinterpret_cast<const float2*>(xg0 + r * xrow + c * 32) + 4 * k);
+                  }
+                }
+              }
               if (EPI == EPI_STORE) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(av(r, 0), av(r, 1));
+                for (int r = 0; r < 4; ++r) st2(r, av(r, 0), av(r, 1));
               } else if (EPI == EPI_ACT) {
-                const float2 d2 = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn));
-                const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + n0 + ch));
+                const float2 d2 = vD[k], b2 = vB[k];
                 float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0;
                 if (do_rgb2) {
-                  const float2 s2 = __ldg(reinterpret_cast<const float2*>(a.e.s_rgb + bn));
-                  const float2 w0 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 0 * a.N + n0 + ch));
-                  const float2 w1 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 1 * a.N + n0 + ch));
-                  const float2 w2 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 2 * a.N + n0 + ch));
+                  const float2 s2 = __ldg(reinterpret_cast<const float2*>(a.e.s_rgb + bn0) + 4 * k);
+                  const float2 w0 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 0 * a.N + nc0) + 4 * k);
+                  const float2 w1 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 1 * a.N + nc0) + 4 * k);
+                  const float2 w2 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 2 * a.N + nc0) + 4 * k);
                   q0 = make_float2(s2.x * w0.x, s2.y * w0.y);
                   q1 = make_float2(s2.x * w1.x, s2.y * w1.y);
                   q2 = make_float2(s2.x * w2.x, s2.y * w2.y);
@@ -626,7 +663,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                 for (int r = 0; r < 4; ++r) {
                   const float o0 = lrelu(fmaf(av(r, 0), d2.x, cnz[r]) + b2.x);
                   const float o1 = lrelu(fmaf(av(r, 1), d2.y, cnz[r]) + b2.y);
-                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(o0, o1);
+                  st2(r, o0, o1);
                   if (do_rgb2) {
                     rgbacc[r][0] = fmaf(o0, q0.x, fmaf(o1, q0.y, rgbacc[r][0]));
                     rgbacc[r][1] = fmaf(o0, q1.x, fmaf(o1, q1.y, rgbacc[r][1]));
@@ -634,44 +671,35 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   }
                 }
               } else if (EPI == EPI_RELU) {
-                const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + n0 + ch));
+                const float2 b2 = vB[k];
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(fmaxf(av(r, 0) + b2.x, 0.f), fmaxf(av(r, 1) + b2.y, 0.f));
+                for (int r = 0; r < 4; ++r) st2(r, fmaxf(av(r, 0) + b2.x, 0.f), fmaxf(av(r, 1) + b2.y, 0.f));
               } else if (EPI == EPI_DGRAD_RELU) {
-                const int j16 = (c * 8 + 2 * k + (cq >> 1));
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                  float2 x2 = make_float2(0.f, 0.f);
-                  if (xs_smem2) x2 = *reinterpret_cast<const float2*>(xbase + (size_t)c * XS_CHUNK + r * 8 * 128 + (((j16 & 7) ^ x) << 4));
-                  else if (xg[r]) x2 = __ldg(reinterpret_cast<const float2*>(xg[r] + ch));
-                  if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(x2.x > 0.f ? av(r, 0) : 0.f, x2.y > 0.f ? av(r, 1) : 0.f);
-                }
+                for (int r = 0; r < 4; ++r) st2(r, xk[r].x > 0.f ? av(r, 0) : 0.f, xk[r].y > 0.f ? av(r, 1) : 0.f);
               } else {
-                const float2 m2 = __ldg(reinterpret_cast<const float2*>(a.e.mod_out + bn));
-                float2 d2 = make_float2(0.f, 0.f), b2 = d2, s2 = d2, w0 = d2, w1 = d2, w2 = d2;
+                const float2 m2 = __ldg(reinterpret_cast<const float2*>(a.e.mod_out + bn0) + 4 * k);
+                float2 d2 = make_float2(0.f, 0.f), b2 = d2;
                 if (EPI == EPI_DGRAD_ACT) {
-                  d2 = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn));
-                  b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + n0 + ch));
-                  if (has_rgb2) {
-                    s2 = __ldg(reinterpret_cast<const float2*>(a.e.s_rgb + bn));
-                    w0 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 0 * a.N + n0 + ch));
-                    w1 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 1 * a.N + n0 + ch));
-                    w2 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 2 * a.N + n0 + ch));
-                  }
+                  d2 = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn0) + 4 * k);
+                  b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + nc0) + 4 * k);
+                }
+                float2 s2 = make_float2(0.f, 0.f), w0 = s2, w1 = s2, w2 = s2;
+                if (has_rgb2) {
+                  s2 = __ldg(reinterpret_cast<const float2*>(a.e.s_rgb + bn0) + 4 * k);
+                  w0 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 0 * a.N + nc0) + 4 * k);
+                  w1 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 1 * a.N + nc0) + 4 * k);
+                  w2 = __ldg(reinterpret_cast<const float2*>(a.e.wrgb + 2 * a.N + nc0) + 4 * k);
                 }
                 float X0 = 0.f, X1 = 0.f, T0 = 0.f, T1 = 0.f, R0 = 0.f, R1 = 0.f;
-                const int j16 = (c * 8 + 2 * k + (cq >> 1));   // 16-byte quad index of this channel pair in the chunk row
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                  float2 x2 = make_float2(0.f, 0.f);
-                  if (xs_smem2) x2 = *reinterpret_cast<const float2*>(xbase + (size_t)c * XS_CHUNK + r * 8 * 128 + (((j16 & 7) ^ x) << 4));
-                  else if (xg[r]) x2 = __ldg(reinterpret_cast<const float2*>(xg[r] + ch));
+                  const float2 x2 = xk[r];
                   const float v0 = av(r, 0), v1 = av(r, 1);
                   X0 = fmaf(x2.x, v0, X0);
                   X1 = fmaf(x2.y, v1, X1);
                   if (EPI == EPI_DGRAD) {
-                    if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(v0 * m2.x, v1 * m2.y);
+                    st2(r, v0 * m2.x, v1 * m2.y);
                   } else {
                     float u0 = 0.f, u1 = 0.f;
                     if (has_rgb2) {
@@ -688,7 +716,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                     }
                     R0 = fmaf(x2.x, u0, R0);
                     R1 = fmaf(x2.y, u1, R1);
-                    if (op[r]) *reinterpret_cast<float2*>(op[r] + ch) = make_float2(gp0 * d2.x, gp1 * d2.y);
+                    st2(r, gp0 * d2.x, gp1 * d2.y);
                   }
                 }
                 // sum over the eight pixel columns of this quarter (lanes that share t & 3): fixed xor tree
@@ -705,6 +733,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                 }
               }
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) outq[r] += 32;
           }
         if (ring2) mbar_arrive(bar_xs_empty(sx));
         if (do_rgb2) {
