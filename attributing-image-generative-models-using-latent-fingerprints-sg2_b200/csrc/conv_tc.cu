@@ -32,6 +32,7 @@
 //   of the transposed conv from four accumulators; EPI_DGRAD(_ACT): x s, style-gradient pixel sums and,
 //   fused, the backward through noise / bias / lrelu / ToRGB of the layer below.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <cudaTypedefs.h>
 
@@ -134,6 +135,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// plain 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"((uint64_t)src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -315,13 +322,19 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
           const int nch = (DGX && a.xs_has_x) ? a.BN >> 5 : 0;
           const uint32_t st0 = smem0 + a.xs_off + (uint32_t)sx * (uint32_t)a.xs_stride;
           mbar_wait(bar_xs_empty(sx), px ^ 1u);
-          mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK + (PXS ? 512u + (RGB ? 1536u : 0u) : 0u));
+          const uint32_t vbytes = (uint32_t)a.BN * 4u;   // one per-channel vector of this CTA's slice
+          mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK + (PXS ? 512u + (RGB ? 1536u : 0u) + (DG ? 3u : 2u) * vbytes : 0u));
           for (int c = 0; c < nch; ++c)
             tma_load_5d(st0 + (uint32_t)c * XS_CHUNK, &tmX, bar_xs_full(sx), wk.n0 + c * 32, wk.x0, wk.y0, 0, a.xs_bcast ? 0 : wk.b);
           if (PXS) {
             // noise tile [16 rows][8] floats, then the skip-gradient planes [3][16][8]; pixels outside the map read as 0
             tma_load_3d(st0 + (uint32_t)nch * XS_CHUNK, &tmNz, bar_xs_full(sx), wk.x0, wk.y0, a.e.noise_bstride == 0 ? 0 : wk.b);
             if (RGB) tma_load_4d(st0 + (uint32_t)nch * XS_CHUNK + 512u, &tmRg, bar_xs_full(sx), wk.x0, wk.y0, 0, wk.b);
+            // per-channel vectors of this (sample, slice): demodulation, bias, and (data gradient) the layer's modulation
+            const uint32_t vb = st0 + (uint32_t)nch * XS_CHUNK + 2048u;
+            bulk_load(vb, a.e.demod + (int64_t)wk.b * a.N + wk.n0, vbytes, bar_xs_full(sx));
+            bulk_load(vb + vbytes, a.e.bias + wk.n0, vbytes, bar_xs_full(sx));
+            if (DG) bulk_load(vb + 2u * vbytes, a.e.mod_out + (int64_t)wk.b * a.N + wk.n0, vbytes, bar_xs_full(sx));
           }
           if (++sx == a.XS) { sx = 0; px ^= 1u; }
         }
@@ -559,9 +572,11 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         const uint32_t xs_row = xs_stage + (uint32_t)((32 * q + x) * 128 + (cq & 1) * 8);
         const uint32_t xo0 = (uint32_t)(((cq >> 1) ^ x) << 4);
         if (ring2) mbar_wait(bar_xs_full(sx), (uint32_t)(it / a.XS) & 1u);
+        // per-pixel scalars of this tile from the ring stage: noise[row][x], skip gradient [plane][row][x]; behind them (+ 2 KB)
+        // the per-channel vectors demod[BN], bias[BN], mod_out[BN]
+        const float* const px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)((DGX && a.xs_has_x) ? nchunk : 0) * XS_CHUNK);
+        const float* const pvec = px + 512 + 2 * cq;
         if (PXS) {
-          // per-pixel scalars of this tile from the ring stage: noise[row][x], skip gradient [plane][row][x]
-          const float* px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)((DGX && a.xs_has_x) ? nchunk : 0) * XS_CHUNK);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const int i = (4 * q + r) * 8 + x;
@@ -586,6 +601,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               vD[k] = vB[k] = make_float2(0.f, 0.f);
+              if (PXS) continue;   // staged in the ring
               if (VPRE && VEC_DB) vD[k] = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn0) + 4 * k);
               if (VPRE && VEC_B) vB[k] = __ldg(reinterpret_cast<const float2*>(a.e.bias + nc0) + 4 * k);
             }
@@ -648,7 +664,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
 #pragma unroll
                 for (int r = 0; r < 4; ++r) st2(r, av(r, 0), av(r, 1));
               } else if (EPI == EPI_ACT) {
-                const float2 d2 = vD[k], b2 = vB[k];
+                const float2 d2 = PXS ? *reinterpret_cast<const float2*>(pvec + c * 32 + 8 * k) : vD[k];
+                const float2 b2 = PXS ? *reinterpret_cast<const float2*>(pvec + a.BN + c * 32 + 8 * k) : vB[k];
                 float2 q0 = make_float2(0.f, 0.f), q1 = q0, q2 = q0;
                 if (do_rgb2) {
                   const float2 s2 = __ldg(reinterpret_cast<const float2*>(a.e.s_rgb + bn0) + 4 * k);
@@ -678,11 +695,17 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
 #pragma unroll
                 for (int r = 0; r < 4; ++r) st2(r, xk[r].x > 0.f ? av(r, 0) : 0.f, xk[r].y > 0.f ? av(r, 1) : 0.f);
               } else {
-                const float2 m2 = __ldg(reinterpret_cast<const float2*>(a.e.mod_out + bn0) + 4 * k);
-                float2 d2 = make_float2(0.f, 0.f), b2 = d2;
-                if (EPI == EPI_DGRAD_ACT) {
-                  d2 = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn0) + 4 * k);
-                  b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + nc0) + 4 * k);
+                float2 m2, d2 = make_float2(0.f, 0.f), b2 = d2;
+                if (PXS) {
+                  d2 = *reinterpret_cast<const float2*>(pvec + c * 32 + 8 * k);
+                  b2 = *reinterpret_cast<const float2*>(pvec + a.BN + c * 32 + 8 * k);
+                  m2 = *reinterpret_cast<const float2*>(pvec + 2 * a.BN + c * 32 + 8 * k);
+                } else {
+                  m2 = __ldg(reinterpret_cast<const float2*>(a.e.mod_out + bn0) + 4 * k);
+                  if (EPI == EPI_DGRAD_ACT) {
+                    d2 = __ldg(reinterpret_cast<const float2*>(a.e.demod + bn0) + 4 * k);
+                    b2 = __ldg(reinterpret_cast<const float2*>(a.e.bias + nc0) + 4 * k);
+                  }
                 }
                 float2 s2 = make_float2(0.f, 0.f), w0 = s2, w1 = s2, w2 = s2;
                 if (has_rgb2) {
@@ -1142,9 +1165,12 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // the ring carries the saved-input tiles of the HBM-bound data-gradient layers (N <= 64) and / or, for the PXS kernels
   // of any width, the per-pixel scalars
   a.xs_has_x = (dg && a.BN <= 64 && a.n_ntiles == 1) ? 1 : 0;
-  const int xs_max = (a.xs_has_x || px_kernel) ? 3 : 0;
+  // LFP_TC_XS_WIDE: ring stages when a stage carries two saved-input chunks (BN = 64: 34 KB per stage) - A/B knob
+  static const int xs_wide = getenv("LFP_TC_XS_WIDE") ? atoi(getenv("LFP_TC_XS_WIDE")) : 2;
+  const int xs_max = (a.xs_has_x || px_kernel) ? ((a.xs_has_x && a.BN >= 64) ? xs_wide : 3) : 0;
   // ring stage = BN / 32 saved-input chunks (when carried), plus 2 KB of per-pixel scalars (PXS kernels)
-  const size_t xs_stride = (a.xs_has_x ? (size_t)(a.BN / 32) * tc::XS_CHUNK : 0) + (px_kernel ? 2048 : 0);
+  // (PXS kernels: 2 KB of per-pixel scalars + the three per-channel vectors of the slice, rounded up to 1 KB)
+  const size_t xs_stride = (a.xs_has_x ? (size_t)(a.BN / 32) * tc::XS_CHUNK : 0) + (px_kernel ? 2048 + ((size_t)a.BN * 12 + 1023) / 1024 * 1024 : 0);
   a.xs_stride = (int)xs_stride;
   size_t xs_smem = 0, epi_smem = 0;
   // LFP_TC_SMEM_CAP (bytes): cap the shared memory a launch asks for, which leaves the rest of the 228 KB to the L1
@@ -1216,6 +1242,10 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
   a.epi_off = (int)((size_t)a.xs_off + xs_smem);
   const size_t smem = (size_t)a.xs_off + epi_smem + 1024;
+  static const bool verbose = getenv("LFP_TC_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "conv_tc plan: epi %d mod %d K %d N %d BN %d grid %dx%d taps %d phases %d | SA %d SB %d resident %d XS %d (x %d, stride %d) nsets %d nacc %d smem %zu\n",
+            EPI, (int)MOD, a.K, a.N, a.BN, a.gh, a.gw, ntaps, a.taps.nphase, a.SA, a.SB, a.b_resident, a.XS, a.xs_has_x, a.xs_stride, a.nsets, a.nacc, smem);
   const CUtensorMap& nzm = tmNz ? *tmNz : tmA;
   const CUtensorMap& rgm = tmRg ? *tmRg : tmA;
   return a.b_resident ? tc_launch2<EPI, MOD, true>(tmA, tmB, tmX, nzm, rgm, a, smem, s) : tc_launch2<EPI, MOD, false>(tmA, tmB, tmX, nzm, rgm, a, smem, s);
@@ -1264,7 +1294,8 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
     static const bool pxs_fwd_off = getenv("LFP_TC_PXS_FWD") != nullptr && atoi(getenv("LFP_TC_PXS_FWD")) == 0;
     const bool nb1 = c.e.noise_bstride == 0;
     bool ok = !pxs_off && !pxs_fwd_off && c.e.rgb_out == nullptr && c.e.noise != nullptr && (c.gw % 4) == 0 && ((uintptr_t)c.e.noise & 15) == 0 &&
-              (nb1 || c.e.noise_bstride == (int64_t)c.gh * c.gw);
+              (nb1 || c.e.noise_bstride == (int64_t)c.gh * c.gw) && c.e.demod != nullptr && c.e.bias != nullptr &&
+              (((uintptr_t)c.e.demod | (uintptr_t)c.e.bias) & 15) == 0;
     if (ok) {
       const cuuint64_t nd[3] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, (cuuint64_t)(nb1 ? 1 : c.batch)};
       const cuuint64_t ns[2] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4};
@@ -1293,7 +1324,9 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
     static const bool pxs_off = getenv("LFP_TC_PXS") != nullptr && atoi(getenv("LFP_TC_PXS")) == 0;
     const bool nb1 = c.e.noise_bstride == 0;
     bool ok = !pxs_off && c.e.noise != nullptr && (c.gw % 4) == 0 && ((uintptr_t)c.e.noise & 15) == 0 &&
-              (c.e.drgb == nullptr || ((uintptr_t)c.e.drgb & 15) == 0) && (nb1 || c.e.noise_bstride == (int64_t)c.gh * c.gw);
+              (c.e.drgb == nullptr || ((uintptr_t)c.e.drgb & 15) == 0) && (nb1 || c.e.noise_bstride == (int64_t)c.gh * c.gw) &&
+              c.e.demod != nullptr && c.e.bias != nullptr && c.e.mod_out != nullptr &&
+              (((uintptr_t)c.e.demod | (uintptr_t)c.e.bias | (uintptr_t)c.e.mod_out) & 15) == 0;
     if (ok) {
       const cuuint64_t nd[3] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, (cuuint64_t)(nb1 ? 1 : c.batch)};
       const cuuint64_t ns[2] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4};
