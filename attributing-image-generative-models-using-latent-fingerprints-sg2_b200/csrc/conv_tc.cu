@@ -49,7 +49,7 @@ constexpr int MAX_SA = 8, MAX_SB = 12;
 // warp 0 TMA, warp 1 MMA, warps 2-5 transform (or a third epilogue set when there is nothing to transform),
 // warps 6-9 / 10-13 epilogue sets; warps 14-15 of the modulated (forward) kernels only pad the block to 512 threads
 constexpr int NTHREADS_MOD = 512, NTHREADS_PLAIN = 448;   // both are charged as 512 threads: 128 registers
-constexpr int MMA2_WARP = 14;                              // optional second MMA issuer of the modulated layout (LFP_TC_ISSUE=2)
+constexpr int PAD_WARP = 14;                               // first padding warp of the modulated layout
 constexpr int MAX_ACC = 4;                // TMEM accumulator stages
 constexpr int MAX_XS = 4;                 // stages of the saved-input (xsave) tile ring of the data-gradient epilogues
 constexpr int XS_CHUNK = 128 * 128;       // one 128-pixel x 32-channel tile
@@ -86,8 +86,8 @@ struct Args {
   int px_ok;                  // host: tensor maps for the per-pixel scalars exist (PXS kernel when a ring is planned)
   int xs_stride;              // bytes per ring stage: BN / 32 saved-input chunks (+ 2 KB of per-pixel scalars, PXS kernels)
   int xs_bcast;
+  int bbatch;                 // streamed weight slices issued per elected region (3 when the B ring holds >= 6 slices, else 1)
   int nsets;                  // epilogue warp sets (2, or 3 when the transform warps are free and smem allows)
-  int nissue;                 // MMA-issuing warps (1 or 2): tile i of a CTA is issued by warp i % nissue
   int in_bcast;
   TcTaps taps;
   float* out;
@@ -286,37 +286,29 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
           for (int kc = 0; kc < kchunks; ++kc)
             tma_load_2d(b_base + (uint32_t)(t * kchunks + kc) * b_slice_bytes, &tmB, bar_b_all, kc * 32, (int)a.taps.widx[t] * a.N);
       }
-      // With two MMA issuers the A (and B) stages form two rings, one per issuer: tile i of the CTA uses ring i & 1.  A
-      // parity wait is only meaningful within one phase of its barrier, so an issuer must be the only consumer of the
-      // slots it waits on (an issuer skipping over the other's stages of a shared ring would see an earlier phase of the
-      // same parity as "its" data).
-      // (scalars with selects, not arrays indexed by `ring`: a dynamically indexed array lives in local memory)
-      int sa_0 = 0, sa_1 = 0, sb_0 = 0, sb_1 = 0, sx = 0;
-      uint32_t pa_0 = 0, pa_1 = 0, pb_0 = 0, pb_1 = 0, px = 0;
-      const int SAr = SA / a.nissue, SBr = RES ? 0 : SB / a.nissue;
+      // (A second MMA-issuing warp with its own stage rings was tried - forward convolutions 7.6 -> 8.6 ms at 1024 px, B = 20:
+      // each issuer gets half of the activation stages and the shallower prefetch costs more than the overlapped per-tile
+      // issue overhead gains - and removed; one issuer keeps every value of the issue loop warp-uniform.)
+      int sa = 0, sb = 0, sx = 0;
+      uint32_t pa = 0, pb = 0, px = 0;
       int it = 0;
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++it) {
         const Work wk = decode(a, w);
         const int bin = a.in_bcast ? 0 : wk.b;
-        const int ring = a.nissue == 2 ? (it & 1) : 0;
-        int sa = ring ? sa_1 : sa_0, sb = ring ? sb_1 : sb_0;
-        uint32_t pa = ring ? pa_1 : pa_0, pb = ring ? pb_1 : pb_0;
-        const int a0 = ring * SAr, b0 = ring * SBr;
         for (int kc = 0; kc < kchunks; ++kc)
           for (int g = 0; g < ngroups; ++g) {
-            mbar_wait(bar_a_empty(a0 + sa), pa ^ 1u);
-            mbar_expect_tx(bar_a_full(a0 + sa), A_BYTES);
-            tma_load_5d(a_base + (a0 + sa) * A_STAGE, &tmA, bar_a_full(a0 + sa), kc * 32, wk.x0 - 1, wk.y0 - 1, a.taps.group_plane[g], bin);
+            mbar_wait(bar_a_empty(sa), pa ^ 1u);
+            mbar_expect_tx(bar_a_full(sa), A_BYTES);
+            tma_load_5d(a_base + sa * A_STAGE, &tmA, bar_a_full(sa), kc * 32, wk.x0 - 1, wk.y0 - 1, a.taps.group_plane[g], bin);
             if (!RES)
               for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
-                mbar_wait(bar_b_empty(b0 + sb), pb ^ 1u);
-                mbar_expect_tx(bar_b_full(b0 + sb), b_slice_bytes);
-                tma_load_2d(b_base + (b0 + sb) * b_slice_bytes, &tmB, bar_b_full(b0 + sb), kc * 32, (int)a.taps.widx[t] * a.N + wk.n0);
-                if (++sb == SBr) { sb = 0; pb ^= 1u; }
+                mbar_wait(bar_b_empty(sb), pb ^ 1u);
+                mbar_expect_tx(bar_b_full(sb), b_slice_bytes);
+                tma_load_2d(b_base + sb * b_slice_bytes, &tmB, bar_b_full(sb), kc * 32, (int)a.taps.widx[t] * a.N + wk.n0);
+                if (++sb == SB) { sb = 0; pb ^= 1u; }
               }
-            if (++sa == SAr) { sa = 0; pa ^= 1u; }
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
-        if (ring) { sa_1 = sa; sb_1 = sb; pa_1 = pa; pb_1 = pb; } else { sa_0 = sa; sb_0 = sb; pa_0 = pa; pb_0 = pb; }
         if ((DGX || PXS) && a.XS > 0) {
           // saved forward input of this tile for the epilogue (data-gradient kernels) and / or its per-pixel scalars (PXS) (128 px x BN channels, one 16 KB box per 32 channels)
           const int nch = (DGX && a.xs_has_x) ? a.BN >> 5 : 0;
@@ -340,12 +332,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         }
       }
     }
-  } else if (warp == 1 || warp == MMA2_WARP) {
-    // ---------------- MMA issuer(s) ----------------
-    // Two issuing warps take alternate tiles of the CTA: the per-tile serial part of one (barrier waits, descriptor set-up,
-    // the commit) overlaps the other's issue, so the tensor pipe's queue does not drain between tiles.  A tile's MMAs all
-    // come from one thread (in order, into its own accumulator stage); its A / B stages are the contiguous range of the
-    // producer's sequence that belongs to it.
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
     // The whole warp runs the (warp-uniform) control flow; one elected lane issues tcgen05.mma / commit.
     // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -353,7 +341,6 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     const uint32_t b_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
     const uint32_t a_lo0 = (a_base >> 4) | 0x10000u, b_lo0 = (b_base >> 4) | 0x10000u;
     const uint32_t b_slice16 = b_slice_bytes >> 4;
-    const int issuer = warp == 1 ? 0 : 1;
     // per-tap descriptor offsets (16-byte units), kept in registers: the issue loop below is fully unrolled
     uint32_t tap_a[9], tap_b[9], tap_p[9];
     const int nphase = a.taps.nphase;
@@ -365,14 +352,11 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       tap_b[t] = b_lo0 + (uint32_t)(tt * kchunks) * b_slice16;
       tap_p[t] = nphase > 1 ? (uint32_t)a.taps.acc[tt] : 0u;
     }
-    if (RES && issuer < a.nissue) mbar_wait(bar_b_all, 0);
-    // this issuer's own rings (see the producer): slots [a0, a0 + SAr) and [b0, b0 + SBr), consumed in order
-    const int SAr = SA / a.nissue, SBr = RES ? 0 : SB / a.nissue;
-    const int a0 = issuer * SAr, b0 = issuer * SBr;
+    if (RES) mbar_wait(bar_b_all, 0);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    int it = issuer;
-    for (int w = issuer < a.nissue ? blockIdx.x + issuer * gridDim.x : a.total_work; w < a.total_work; w += a.nissue * gridDim.x, it += a.nissue) {
+    int it = 0;
+    for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++it) {
       const int as = it & (a.nacc - 1);
       mbar_wait(bar_acc_empty(as), (((uint32_t)it >> acc_shift) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -380,9 +364,9 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       uint32_t started = 0;   // bit p: accumulator p of this tile has received its first MMA
       for (int kc = 0; kc < kchunks; ++kc)
         for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(MOD ? bar_a_ready(a0 + sa) : bar_a_full(a0 + sa), pa);
+          mbar_wait(MOD ? bar_a_ready(sa) : bar_a_full(sa), pa);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_stage_lo = a_lo0 + (uint32_t)(a0 + sa) * (A_STAGE >> 4);
+          const uint32_t a_stage_lo = a_lo0 + (uint32_t)sa * (A_STAGE >> 4);
           const int t0 = a.taps.group_tap0[g], t1 = a.taps.group_tap0[g + 1];
           if (RES) {
             // weights resident: every MMA of this activation stage is issued in one elected region
@@ -399,17 +383,62 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
                   started |= 1u << tap_p[t];
                 }
-              umma_commit(bar_a_empty(a0 + sa));
+              umma_commit(bar_a_empty(sa));
             }
             __syncwarp();
             started = (1u << nphase) - 1u;   // every accumulator has taps in every activation stage
           } else {
+            // Weights stream through the B ring.  The taps of this activation stage are issued in batches of up to three
+            // slices - one barrier-wait sequence, one elected region and one round of uniform-register set-up per batch.
+            // ncu on the 64 -> 64 data gradient at 512 px (one slice per region): the issuing warp was busy ~80 % of the
+            // time at ~60 SASS instructions per slice (R2UR / UMOV descriptor set-up, elect, reconvergence) for four MMAs
+            // that occupy the tensor pipe for 4 x 52 cycles, i.e. the launch was bound by instruction issue, not by the pipe.
+            // (Needs a ring of >= 6 slices so that the next batch loads while this one computes; otherwise one slice per region.)
+            if (a.bbatch == 3) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int lo = t0 > 3 * j ? t0 : 3 * j, hi = t1 < 3 * j + 3 ? t1 : 3 * j + 3;   // active taps [lo, hi) of batch j
+              if (lo < hi) {
+                int sbi = sb;
+                uint32_t pbi = pb;
+                for (int i = lo; i < hi; ++i) {
+                  mbar_wait(bar_b_full(sbi), pbi);
+                  if (++sbi == SB) { sbi = 0; pbi ^= 1u; }
+                }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                  int sbk = sb;
+                  uint32_t st = started;
+#pragma unroll
+                  for (int i = 0; i < 3; ++i) {
+                    const int t = 3 * j + i;
+                    if (t >= lo && t < hi) {
+                      const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)sbk * b_slice16;
+                      const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
+                      umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, (st >> tap_p[t]) & 1u);
+                      umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                      umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                      umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                      umma_commit(bar_b_empty(sbk));
+                      st |= 1u << tap_p[t];
+                      if (++sbk == SB) sbk = 0;
+                    }
+                  }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                  if (3 * j + i >= lo && 3 * j + i < hi) started |= 1u << tap_p[3 * j + i];
+                sb = sbi; pb = pbi;
+              }
+            }
+            } else {
 #pragma unroll
             for (int t = 0; t < 9; ++t)
               if (t >= t0 && t < t1) {
-                mbar_wait(bar_b_full(b0 + sb), pb);
+                mbar_wait(bar_b_full(sb), pb);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)(b0 + sb) * b_slice16;
+                const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)sb * b_slice16;
                 const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
                 const uint32_t accumulate = (started >> tap_p[t]) & 1u;
                 if (elect_one()) {
@@ -417,16 +446,17 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
-                  umma_commit(bar_b_empty(b0 + sb));
+                  umma_commit(bar_b_empty(sb));
                 }
                 __syncwarp();
                 started |= 1u << tap_p[t];
-                if (++sb == SBr) { sb = 0; pb ^= 1u; }
+                if (++sb == SB) { sb = 0; pb ^= 1u; }
               }
-            if (elect_one()) umma_commit(bar_a_empty(a0 + sa));
+            }
+            if (elect_one()) umma_commit(bar_a_empty(sa));
             __syncwarp();
           }
-          if (++sa == SAr) { sa = 0; pa ^= 1u; }
+          if (++sa == SA) { sa = 0; pa ^= 1u; }
         }
       if (elect_one()) umma_commit(bar_acc_full(as));
       __syncwarp();
@@ -435,16 +465,12 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     if (MOD) {
       // ---------------- A transform: x * s[b, k], rounded to tf32 ----------------
       const int et = tid - 64;  // 0..127
-      int sa_0 = 0, sa_1 = 0;
-      uint32_t pa_0 = 0, pa_1 = 0;
-      const int SAr = SA / a.nissue;
+      int sa = 0;
+      uint32_t pa = 0;
       int it = 0;
       for (int w = blockIdx.x; w < a.total_work; w += gridDim.x, ++it) {
         const Work wk = decode(a, w);
         const float* sm = a.mod + (int64_t)wk.b * a.K;
-        const int ring = a.nissue == 2 ? (it & 1) : 0;   // the producer's ring of this tile
-        int sa_rel = ring ? sa_1 : sa_0, sa = ring * SAr + sa_rel;
-        uint32_t pa = ring ? pa_1 : pa_0;
         for (int kc = 0; kc < kchunks; ++kc)
           for (int g = 0; g < ngroups; ++g) {
             mbar_wait(bar_a_full(sa), pa);
@@ -469,13 +495,11 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_a_ready(sa));
-            ++sa;
-            if (++sa_rel == SAr) { sa_rel = 0; sa = ring * SAr; pa ^= 1u; }
+            if (++sa == SA) { sa = 0; pa ^= 1u; }
           }
-        if (ring) { sa_1 = sa_rel; pa_1 = pa; } else { sa_0 = sa_rel; pa_0 = pa; }
       }
     }
-  } else if (warp >= MMA2_WARP) {
+  } else if (warp >= PAD_WARP) {
     // padding warp of the 512-thread modulated layout: nothing to do
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
@@ -1231,12 +1255,8 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   if (const char* e = getenv("LFP_TC_SA_MAX")) { const int v = atoi(e); if (v >= 2 && a.SA > v) a.SA = v; }
   a.nacc = a.BN * a.taps.nphase <= 128 ? 4 : (a.BN * a.taps.nphase <= 256 ? 2 : 1);
   if (a.nsets > a.nacc) a.nsets = a.nacc;
-  // LFP_TC_ISSUE=2 turns the second MMA-issuing warp on (needs two accumulator stages and two stages per ring).  Measured
-  // on the 1024 px step, B = 20, same box: forward convolutions 7.6 -> 8.6 ms, data gradients unchanged - each issuer gets
-  // half of the activation stages, and the shallower prefetch costs more than the overlapped per-tile issue overhead
-  // gains - so the default stays one issuer.
-  static const int issue_env = getenv("LFP_TC_ISSUE") ? atoi(getenv("LFP_TC_ISSUE")) : 1;
-  a.nissue = (MOD && a.nacc >= 2 && issue_env >= 2 && a.SA >= 4 && (a.b_resident || a.SB >= 4)) ? 2 : 1;   // >= 2 stages per ring; warp 14 exists in the modulated layout only
+  static const int bbatch_env = getenv("LFP_TC_BBATCH") ? atoi(getenv("LFP_TC_BBATCH")) : 3;   // A/B knob
+  a.bbatch = (!a.b_resident && a.SB >= 6 && bbatch_env == 3) ? 3 : 1;
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
   // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
   a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
