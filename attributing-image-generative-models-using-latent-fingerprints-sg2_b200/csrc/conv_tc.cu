@@ -42,9 +42,8 @@ namespace lfp {
 namespace tc {
 
 constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
-constexpr int A_ROWS = HALO_W * HALO_H;   // 180 rows of 128 bytes
-constexpr int A_BYTES = A_ROWS * 128;     // 23040
-constexpr int A_STAGE = 23552;            // stage stride, multiple of 1024
+// one haloed activation stage: 10 x 18 = 180 rows of 128 bytes (23040 B, stride 23552) for a 16-row tile, 10 x 34 = 340 rows
+// (43520 B, stride 44032) for a tall one - Args::a_rows / a_stage
 constexpr int MAX_SA = 8, MAX_SB = 12;
 // warp 0 TMA, warp 1 MMA, warps 2-5 transform (or a third epilogue set when there is nothing to transform),
 // warps 6-9 / 10-13 epilogue sets; warps 14-15 of the modulated (forward) kernels only pad the block to 512 threads
@@ -78,6 +77,13 @@ struct Args {
   int batch, gh, gw, tiles_x, tiles_y, K, N, BN;
   FastDiv d_ntiles, d_tiles_per, d_tiles_x;
   int n_ntiles, total_work;   // work item = (sample, tile, n-tile)
+  // Tall tiles (nhalf = 2): a work item covers 8 x 32 output pixels = two stacked 128-pixel halves that share every streamed
+  // weight slice (two accumulators, two MMAs per tap and K-step reading the same B tile).  The layers whose weights do not fit
+  // in shared memory re-read them from L2 for every tile and ran at 80-110 % of the L2 -> SM throughput cap with the tensor
+  // pipe 50-69 % busy (tools/umma_rate.cu, profiles/r02_conv_l2_traffic.md); a tall tile halves that traffic.
+  int nhalf;                  // 1 or 2 halves of 16 rows per work item
+  int a_rows, a_stage;        // rows of one haloed activation stage (10 x (16 nhalf + 2)) and its stride in bytes (multiple of 1024)
+  int vtiles_per;             // 16-row tiles per sample (tiles_x * ceil(gh / 16)): index space of the per-tile partial sums
   int SA, SB, b_resident;     // A stages; B stages (streaming) or 0 with the whole weight slice resident
   int nacc;                   // TMEM accumulator stages (1, 2 or 4)
   int epi_off;                // byte offset of the epilogue scratch in dynamic shared memory
@@ -190,7 +196,7 @@ __device__ __forceinline__ float to_tf32(float v) {
 }
 __device__ __forceinline__ float lrelu(float v) { return (v > 0.f ? v : v * kLreluSlope) * kLreluGain; }
 
-struct Work { int b, tile, nt, y0, x0, n0; };
+struct Work { int b, tile, nt, y0, x0, n0, ty, tx; };
 __device__ __forceinline__ Work decode(const Args& a, int w) {
   Work r;
   const int bt = fdiv(w, a.d_ntiles);
@@ -199,8 +205,10 @@ __device__ __forceinline__ Work decode(const Args& a, int w) {
   r.b = fdiv(bt, a.d_tiles_per);
   r.tile = bt - r.b * tiles_per;
   const int ty = fdiv(r.tile, a.d_tiles_x);
-  r.y0 = ty * TILE_H;
-  r.x0 = (r.tile - ty * a.tiles_x) * TILE_W;
+  r.ty = ty;
+  r.tx = r.tile - ty * a.tiles_x;
+  r.y0 = ty * (TILE_H * a.nhalf);
+  r.x0 = r.tx * TILE_W;
   r.n0 = r.nt * a.BN;
   return r;
 }
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int SA = a.SA, SB = a.SB;
   const uint32_t b_slice_bytes = (uint32_t)a.BN * 128u;
-  const uint32_t a_base = smem0, b_base = smem0 + SA * A_STAGE;
+  const uint32_t a_base = smem0, b_base = smem0 + SA * a.a_stage;
   const uint32_t bar0 = smem_u32(bars);
   auto bar_a_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_a_ready = [&](int s) { return bar0 + 8u * (MAX_SA + s); };
@@ -257,11 +265,11 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     for (int s = 0; s < MAX_SA; ++s) { mbar_init(bar_a_full(s), 1); mbar_init(bar_a_ready(s), 128); mbar_init(bar_a_empty(s), 1); }
     for (int s = 0; s < MAX_SB; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
     mbar_init(bar_b_all, 1);
-    for (int s = 0; s < MAX_ACC; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), 128); }
-    for (int s = 0; s < MAX_XS; ++s) { mbar_init(bar_xs_full(s), 1); mbar_init(bar_xs_empty(s), 128); }
+    for (int s = 0; s < MAX_ACC; ++s) { mbar_init(bar_acc_full(s), 1); mbar_init(bar_acc_empty(s), 128 * a.nhalf); }
+    for (int s = 0; s < MAX_XS; ++s) { mbar_init(bar_xs_full(s), 1); mbar_init(bar_xs_empty(s), 128 * a.nhalf); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t tmem_cols = (uint32_t)(a.nacc * a.BN * a.taps.nphase);
+  const uint32_t tmem_cols = (uint32_t)(a.nacc * a.BN * a.taps.nphase * a.nhalf);
   const int acc_shift = a.nacc == 4 ? 2 : (a.nacc == 2 ? 1 : 0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(tmem_cols));
@@ -298,8 +306,8 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         for (int kc = 0; kc < kchunks; ++kc)
           for (int g = 0; g < ngroups; ++g) {
             mbar_wait(bar_a_empty(sa), pa ^ 1u);
-            mbar_expect_tx(bar_a_full(sa), A_BYTES);
-            tma_load_5d(a_base + sa * A_STAGE, &tmA, bar_a_full(sa), kc * 32, wk.x0 - 1, wk.y0 - 1, a.taps.group_plane[g], bin);
+            mbar_expect_tx(bar_a_full(sa), (uint32_t)a.a_rows * 128u);
+            tma_load_5d(a_base + sa * a.a_stage, &tmA, bar_a_full(sa), kc * 32, wk.x0 - 1, wk.y0 - 1, a.taps.group_plane[g], bin);
             if (!RES)
               for (int t = a.taps.group_tap0[g]; t < a.taps.group_tap0[g + 1]; ++t) {
                 mbar_wait(bar_b_empty(sb), pb ^ 1u);
@@ -315,15 +323,16 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
           const uint32_t st0 = smem0 + a.xs_off + (uint32_t)sx * (uint32_t)a.xs_stride;
           mbar_wait(bar_xs_empty(sx), px ^ 1u);
           const uint32_t vbytes = (uint32_t)a.BN * 4u;   // one per-channel vector of this CTA's slice
-          mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK + (PXS ? 512u + (RGB ? 1536u : 0u) + (DG ? 3u : 2u) * vbytes : 0u));
+          const uint32_t nzb = 512u * (uint32_t)a.nhalf;   // one noise tile: [16 nhalf rows][8] floats
+          mbar_expect_tx(bar_xs_full(sx), (uint32_t)nch * XS_CHUNK + (PXS ? nzb + (RGB ? 3u * nzb : 0u) + (DG ? 3u : 2u) * vbytes : 0u));
           for (int c = 0; c < nch; ++c)
             tma_load_5d(st0 + (uint32_t)c * XS_CHUNK, &tmX, bar_xs_full(sx), wk.n0 + c * 32, wk.x0, wk.y0, 0, a.xs_bcast ? 0 : wk.b);
           if (PXS) {
             // noise tile [16 rows][8] floats, then the skip-gradient planes [3][16][8]; pixels outside the map read as 0
             tma_load_3d(st0 + (uint32_t)nch * XS_CHUNK, &tmNz, bar_xs_full(sx), wk.x0, wk.y0, a.e.noise_bstride == 0 ? 0 : wk.b);
-            if (RGB) tma_load_4d(st0 + (uint32_t)nch * XS_CHUNK + 512u, &tmRg, bar_xs_full(sx), wk.x0, wk.y0, 0, wk.b);
+            if (RGB) tma_load_4d(st0 + (uint32_t)nch * XS_CHUNK + nzb, &tmRg, bar_xs_full(sx), wk.x0, wk.y0, 0, wk.b);
             // per-channel vectors of this (sample, slice): demodulation, bias, and (data gradient) the layer's modulation
-            const uint32_t vb = st0 + (uint32_t)nch * XS_CHUNK + 2048u;
+            const uint32_t vb = st0 + (uint32_t)nch * XS_CHUNK + 4u * nzb;
             bulk_load(vb, a.e.demod + (int64_t)wk.b * a.N + wk.n0, vbytes, bar_xs_full(sx));
             bulk_load(vb + vbytes, a.e.bias + wk.n0, vbytes, bar_xs_full(sx));
             if (DG) bulk_load(vb + 2u * vbytes, a.e.mod_out + (int64_t)wk.b * a.N + wk.n0, vbytes, bar_xs_full(sx));
@@ -344,7 +353,9 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     // per-tap descriptor offsets (16-byte units), kept in registers: the issue loop below is fully unrolled
     uint32_t tap_a[9], tap_b[9], tap_p[9];
     const int nphase = a.taps.nphase;
-    const uint32_t stage_cols = (uint32_t)(nphase * a.BN);
+    const uint32_t stage_cols = (uint32_t)(a.nhalf * nphase * a.BN);   // accumulators of one work item: [half][phase][BN]
+    const uint32_t half_a = (uint32_t)(TILE_H * HALO_W * 128) >> 4;     // descriptor offset of the lower half's window (16 rows down)
+    const uint32_t half_c = (uint32_t)(nphase * a.BN);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int tt = t < ntaps ? t : 0;
@@ -366,7 +377,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         for (int g = 0; g < ngroups; ++g) {
           mbar_wait(MOD ? bar_a_ready(sa) : bar_a_full(sa), pa);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_stage_lo = a_lo0 + (uint32_t)sa * (A_STAGE >> 4);
+          const uint32_t a_stage_lo = a_lo0 + (uint32_t)sa * ((uint32_t)a.a_stage >> 4);
           const int t0 = a.taps.group_tap0[g], t1 = a.taps.group_tap0[g + 1];
           if (RES) {
             // weights resident: every MMA of this activation stage is issued in one elected region
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
 #pragma unroll
               for (int t = 0; t < 9; ++t)
                 if (t >= t0 && t < t1) {
-                  const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = tap_b[t] + kc_off;
+                  const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = tap_b[t] + kc_off;   // (resident weights: never a tall item)
                   const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
                   umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, (started >> tap_p[t]) & 1u);
                   umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
@@ -413,12 +424,19 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
                   for (int i = 0; i < 3; ++i) {
                     const int t = 3 * j + i;
                     if (t >= lo && t < hi) {
-                      const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)sbk * b_slice16;
+                      const uint32_t b_lo = b_lo0 + (uint32_t)sbk * b_slice16;
+                      const uint32_t a_lo = a_stage_lo + tap_a[t];
                       const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
                       umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, (st >> tap_p[t]) & 1u);
                       umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                       umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
                       umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                      if (a.nhalf == 2) {   // lower half: the window 16 rows down, its own accumulator, the same weight slice
+                        umma_tf32_lohi(tacc + half_c, a_lo + half_a, a_hi, b_lo, b_hi, idesc, (st >> tap_p[t]) & 1u);
+                        umma_tf32_lohi(tacc + half_c, a_lo + half_a + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                        umma_tf32_lohi(tacc + half_c, a_lo + half_a + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                        umma_tf32_lohi(tacc + half_c, a_lo + half_a + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                      }
                       umma_commit(bar_b_empty(sbk));
                       st |= 1u << tap_p[t];
                       if (++sbk == SB) sbk = 0;
@@ -438,14 +456,21 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
               if (t >= t0 && t < t1) {
                 mbar_wait(bar_b_full(sb), pb);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_lo = a_stage_lo + tap_a[t], b_lo = b_lo0 + (uint32_t)sb * b_slice16;
-                const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
+                const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_slice16;
                 const uint32_t accumulate = (started >> tap_p[t]) & 1u;
                 if (elect_one()) {
+                  const uint32_t a_lo = a_stage_lo + tap_a[t];
+                  const uint32_t tacc = tacc0 + tap_p[t] * (uint32_t)a.BN;
                   umma_tf32_lohi(tacc, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
                   umma_tf32_lohi(tacc, a_lo + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
                   umma_tf32_lohi(tacc, a_lo + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                  if (a.nhalf == 2) {
+                    umma_tf32_lohi(tacc + half_c, a_lo + half_a, a_hi, b_lo, b_hi, idesc, accumulate);
+                    umma_tf32_lohi(tacc + half_c, a_lo + half_a + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+                    umma_tf32_lohi(tacc + half_c, a_lo + half_a + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+                    umma_tf32_lohi(tacc + half_c, a_lo + half_a + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+                  }
                   umma_commit(bar_b_empty(sb));
                 }
                 __syncwarp();
@@ -479,20 +504,24 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             const int pos = et & 7, r0 = et >> 3;
             const int ch = (pos ^ (r0 & 7)) << 2;
             const float4 s4 = __ldg(reinterpret_cast<const float4*>(sm + kc * 32 + ch));
-            float4* p = reinterpret_cast<float4*>(smem_al + sa * A_STAGE + r0 * 128 + pos * 16);
-            float4 v[12];
+            // twelve rows (r0 + 16 i) per pass: 180 rows = one pass, the 340 rows of a tall tile = two
+            for (int rb = 0; rb < a.a_rows; rb += 192) {
+              float4* p = reinterpret_cast<float4*>(smem_al + sa * a.a_stage + (rb + r0) * 128 + pos * 16);
+              const int left = a.a_rows - rb - r0;   // rows r0 + 16 i < left are inside the stage
+              float4 v[12];
 #pragma unroll
-            for (int i = 0; i < 12; ++i)
-              if (i < 11 || r0 + 176 < A_ROWS) v[i] = p[i * 128];   // row r0 + 16 i, 128 float4 apart
+              for (int i = 0; i < 12; ++i)
+                if (16 * i < left) v[i] = p[i * 128];   // row rb + r0 + 16 i, 128 float4 apart
 #pragma unroll
-            for (int i = 0; i < 12; ++i)
-              if (i < 11 || r0 + 176 < A_ROWS) {
-                v[i].x = to_tf32(v[i].x * s4.x);
-                v[i].y = to_tf32(v[i].y * s4.y);
-                v[i].z = to_tf32(v[i].z * s4.z);
-                v[i].w = to_tf32(v[i].w * s4.w);
-                p[i * 128] = v[i];
-              }
+              for (int i = 0; i < 12; ++i)
+                if (16 * i < left) {
+                  v[i].x = to_tf32(v[i].x * s4.x);
+                  v[i].y = to_tf32(v[i].y * s4.y);
+                  v[i].z = to_tf32(v[i].z * s4.z);
+                  v[i].w = to_tf32(v[i].w * s4.w);
+                  p[i * 128] = v[i];
+                }
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_a_ready(sa));
             if (++sa == SA) { sa = 0; pa ^= 1u; }
@@ -526,14 +555,15 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
       // per-pixel scalars of a work item (noise; skip-image gradient), fetched one work item ahead.  Plain register
       // arrays filled by a macro: a struct handed to a lambda ended up in local memory, and the spill store then waited
       // for the load it was meant to overlap.
-#define LFP_FETCH2(W, NZ, RG)                                                                         \
+#define LFP_FETCH2(VT, NZ, RG)                                                                        \
   {                                                                                                   \
     _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) { NZ[r_] = 0.f; RG[r_][0] = RG[r_][1] = RG[r_][2] = 0.f; } \
-    if ((W) < a.total_work) {                                                                         \
-      const Work k_ = decode(a, (W));                                                                 \
+    const int64_t w_ = (int64_t)blockIdx.x + (int64_t)((VT) >> (a.nhalf - 1)) * gridDim.x;           \
+    if ((VT) < 0x40000000 && w_ < a.total_work) {                                                     \
+      const Work k_ = decode(a, (int)w_);                                                             \
       const int gx_ = k_.x0 + x;                                                                      \
       _Pragma("unroll") for (int r_ = 0; r_ < 4; ++r_) {                                              \
-        const int gy_ = k_.y0 + 4 * q + r_;                                                           \
+        const int gy_ = k_.y0 + TILE_H * ((VT) & (a.nhalf - 1)) + 4 * q + r_;                         \
         if (gy_ < a.gh && gx_ < a.gw) {                                                               \
           const int pix_ = gy_ * a.gw + gx_;                                                          \
           if (need_nz2) NZ[r_] = __ldg(a.e.noise + (int64_t)k_.b * a.e.noise_bstride + pix_);         \
@@ -547,22 +577,29 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
     }                                                                                                 \
   }
       constexpr float G = kLreluGain, GS = kLreluGain * kLreluSlope, IG = 1.f / kLreluGain, IGS = 1.f / (kLreluGain * kLreluSlope);
-      const int wstep = a.nsets * gridDim.x;
       const int nchunk = a.BN >> 5;
       const int nphase = a.taps.nphase;
       float nz_n[4], rg_n[4][3];
-      if (!PXS) LFP_FETCH2(eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work, nz_n, rg_n)
-      int it = eset;
-      for (int w = eset < a.nsets ? blockIdx.x + eset * gridDim.x : a.total_work; w < a.total_work; w += wstep, it += a.nsets) {
+      if (!PXS) LFP_FETCH2(eset < a.nsets ? eset : 0x40000000, nz_n, rg_n)
+      // Virtual tiles: half hf of the CTA's it-th work item is virtual tile vt = it * nhalf + hf; set e takes vt = e, e + nsets, ...
+      // (nhalf = 1: vt = it, the plain alternation of work items).  Both halves of an item arrive on its accumulator / ring
+      // "empty" barriers (initialised to 128 * nhalf arrivals).
+      const int hshift = a.nhalf - 1;   // log2(nhalf), also the mask of hf
+      for (int vt = eset < a.nsets ? eset : 0x40000000; (vt >> hshift) < 0x20000000; vt += a.nsets) {
+        const int it = vt >> hshift, hf = vt & hshift;
+        const int64_t w64 = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+        if (w64 >= a.total_work) break;
+        const int w = (int)w64;
         const Work wk = decode(a, w);
         const int as = it & (a.nacc - 1);
         const int b = wk.b, n0 = wk.n0;
         const int gx = wk.x0 + x;
+        const int y0h = wk.y0 + TILE_H * hf;   // first row of this half
         float cnz[4], crg[4][3];
         if (!PXS) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) { cnz[r] = nw2 * nz_n[r]; crg[r][0] = rg_n[r][0]; crg[r][1] = rg_n[r][1]; crg[r][2] = rg_n[r][2]; }
-          LFP_FETCH2(w + wstep, nz_n, rg_n)
+          LFP_FETCH2(vt + a.nsets, nz_n, rg_n)
         }
         // Addresses are built once per tile (row pointers) and once per 32-channel chunk; inside the unrolled (k, row) body every
         // load / store is base register + immediate.  ncu on the 32 -> 32 act-backward launch at 1024 px: the epilogue sets were
@@ -574,7 +611,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         const float* xg0;      // without the ring (BN = 128): the saved input straight from global memory (first row, same channel offset)
         int64_t xrow;
         {
-          const int gy0 = wk.y0 + 4 * q;
+          const int gy0 = y0h + 4 * q;
           float* const o0 = a.out + ((((int64_t)b * a.out_planes + a.out_plane) * a.out_h + (gy0 * a.out_stride + a.out_oy)) * a.out_w +
                                      (gx * a.out_stride + a.out_ox)) * a.N + n0 + 2 * cq;
           const int64_t orow = (int64_t)a.out_stride * a.out_w * a.N;
@@ -599,13 +636,14 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         // per-pixel scalars of this tile from the ring stage: noise[row][x], skip gradient [plane][row][x]; behind them (+ 2 KB)
         // the per-channel vectors demod[BN], bias[BN], mod_out[BN]
         const float* const px = reinterpret_cast<const float*>(smem_al + a.xs_off + (size_t)sx * a.xs_stride + (size_t)((DGX && a.xs_has_x) ? nchunk : 0) * XS_CHUNK);
-        const float* const pvec = px + 512 + 2 * cq;
+        const int npx = 128 * a.nhalf;   // floats per plane of per-pixel scalars
+        const float* const pvec = px + 4 * npx + 2 * cq;
         if (PXS) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            const int i = (4 * q + r) * 8 + x;
+            const int i = (TILE_H * hf + 4 * q + r) * 8 + x;
             cnz[r] = nw2 * px[i];
-            crg[r][0] = RGB ? px[128 + i] : 0.f; crg[r][1] = RGB ? px[256 + i] : 0.f; crg[r][2] = RGB ? px[384 + i] : 0.f;
+            crg[r][0] = RGB ? px[npx + i] : 0.f; crg[r][1] = RGB ? px[2 * npx + i] : 0.f; crg[r][2] = RGB ? px[3 * npx + i] : 0.f;
           }
         }
         float rgbacc[4][3];
@@ -635,13 +673,13 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             }
             uint32_t acc[2][16];   // [half][4k + 2 j2 + e]: row r = 2 half + j2
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const uint32_t taddr = tmem + ((uint32_t)(q * 32 + hf * 16) << 16) + (uint32_t)((as * nphase + ph) * a.BN + c * 32);
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t taddr = tmem + ((uint32_t)(q * 32 + hh * 16) << 16) + (uint32_t)(((as * a.nhalf + hf) * nphase + ph) * a.BN + c * 32);
               asm volatile(
                   "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                  : "=r"(acc[hf][0]), "=r"(acc[hf][1]), "=r"(acc[hf][2]), "=r"(acc[hf][3]), "=r"(acc[hf][4]), "=r"(acc[hf][5]),
-                    "=r"(acc[hf][6]), "=r"(acc[hf][7]), "=r"(acc[hf][8]), "=r"(acc[hf][9]), "=r"(acc[hf][10]), "=r"(acc[hf][11]),
-                    "=r"(acc[hf][12]), "=r"(acc[hf][13]), "=r"(acc[hf][14]), "=r"(acc[hf][15])
+                  : "=r"(acc[hh][0]), "=r"(acc[hh][1]), "=r"(acc[hh][2]), "=r"(acc[hh][3]), "=r"(acc[hh][4]), "=r"(acc[hh][5]),
+                    "=r"(acc[hh][6]), "=r"(acc[hh][7]), "=r"(acc[hh][8]), "=r"(acc[hh][9]), "=r"(acc[hh][10]), "=r"(acc[hh][11]),
+                    "=r"(acc[hh][12]), "=r"(acc[hh][13]), "=r"(acc[hh][14]), "=r"(acc[hh][15])
                   : "r"(taddr));
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -654,7 +692,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             if (EPI == EPI_STORE && nphase > 1 && c == 0) {
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
-                const int gy = wk.y0 + 4 * q + r;
+                const int gy = y0h + 4 * q + r;
                 st_ok[r] = a.out != nullptr && gy < a.gh - (ph >> 1) && gx < a.gw - (ph & 1);
                 if (a.out_stride == 2)   // phases interleaved into the [2H+1, 2W+1] image: (2 gy + a, 2 gx + b)
                   outq[r] = a.out + (((int64_t)b * (2 * a.out_h - 1) + (2 * gy + (ph >> 1))) * (2 * a.out_w - 1) + (2 * gx + (ph & 1))) * a.N + n0 + 2 * cq;
@@ -798,7 +836,7 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
 #pragma unroll
             for (int r = 0; r < 4; ++r)
               if (valid[r]) {
-                float* ro = a.e.rgb_out + (int64_t)b * 3 * hw + (int64_t)(wk.y0 + 4 * q + r) * a.gw + gx;
+                float* ro = a.e.rgb_out + (int64_t)b * 3 * hw + (int64_t)(y0h + 4 * q + r) * a.gw + gx;
                 ro[0] = rgbacc[r][0] + __ldg(a.e.rgb_bias + 0);
                 ro[hw] = rgbacc[r][1] + __ldg(a.e.rgb_bias + 1);
                 ro[2 * hw] = rgbacc[r][2] + __ldg(a.e.rgb_bias + 2);
@@ -807,8 +845,10 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
         }
         if (DG) {
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eset) : "memory");
-          for (int n = et; n < a.BN; n += 128) {
-            const int64_t o = ((int64_t)b * tiles_per + wk.tile) * a.N + n0 + n;
+          // per-tile partial sums are indexed by 16-row tiles (vtiles_per per sample), whatever the height of the work item;
+          // a lower half that lies entirely below the image has no slot (and nothing to add)
+          for (int n = et; n < a.BN && y0h < a.gh; n += 128) {
+            const int64_t o = ((int64_t)b * a.vtiles_per + (wk.ty * a.nhalf + hf) * a.tiles_x + wk.tx) * a.N + n0 + n;
             const int bnn = a.BN;
             a.e.partial[o] = ((red[n] + red[bnn + n]) + red[2 * bnn + n]) + red[3 * bnn + n];
             if (EPI == EPI_DGRAD_ACT) {
@@ -1194,7 +1234,9 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   const int xs_max = (a.xs_has_x || px_kernel) ? ((a.xs_has_x && a.BN >= 64) ? xs_wide : 3) : 0;
   // ring stage = BN / 32 saved-input chunks (when carried), plus 2 KB of per-pixel scalars (PXS kernels)
   // (PXS kernels: 2 KB of per-pixel scalars + the three per-channel vectors of the slice, rounded up to 1 KB)
-  const size_t xs_stride = (a.xs_has_x ? (size_t)(a.BN / 32) * tc::XS_CHUNK : 0) + (px_kernel ? 2048 + ((size_t)a.BN * 12 + 1023) / 1024 * 1024 : 0);
+  const size_t xs_stride = (a.xs_has_x ? (size_t)(a.BN / 32) * tc::XS_CHUNK : 0) + (px_kernel ? 2048 * (size_t)a.nhalf + ((size_t)a.BN * 12 + 1023) / 1024 * 1024 : 0);
+  const size_t a_stage = (size_t)a.a_stage;
+  const size_t min_sa = a.nhalf == 2 ? 2 : 3;   // a tall stage feeds twice the MMAs: double buffering is enough
   a.xs_stride = (int)xs_stride;
   size_t xs_smem = 0, epi_smem = 0;
   // LFP_TC_SMEM_CAP (bytes): cap the shared memory a launch asks for, which leaves the rest of the 228 KB to the L1
@@ -1208,7 +1250,7 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   // stride-2 32 -> 64 layer loses 6 % with a two-stage ring.  So the round-1 order (ring first) stays the default.
   static const bool prefer_res = getenv("LFP_TC_PREFER_RES") && atoi(getenv("LFP_TC_PREFER_RES")) != 0;
   bool planned = false;
-  if (prefer_res && a.n_ntiles == 1)
+  if (prefer_res && a.n_ntiles == 1 && a.nhalf == 1)
     for (int xs = xs_max; xs >= 0 && !planned; --xs) {
       if (xs == 1) continue;                       // a one-stage ring serialises the epilogue sets
       int nsets = nsets0;
@@ -1217,9 +1259,9 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
       const size_t epi = tc::EPI_SMEM(EPI, nsets, a.BN, tc_use_e2(a.BN)) + xsm;
       if (optin < tc::STATIC_SMEM_RESERVE + 1024 + epi) continue;
       const size_t budget = optin - tc::STATIC_SMEM_RESERVE - 1024 - epi;
-      if (b_all + 3 * (size_t)tc::A_STAGE <= budget) {
+      if (b_all + 3 * a_stage <= budget) {
         a.XS = xs; a.nsets = nsets; xs_smem = xsm; epi_smem = epi;
-        a.b_resident = 1; a.SB = 0; a.SA = (int)((budget - b_all) / tc::A_STAGE);
+        a.b_resident = 1; a.SB = 0; a.SA = (int)((budget - b_all) / a_stage);
         planned = true;
       }
     }
@@ -1227,21 +1269,21 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
     a.XS = xs;
     // same parity argument for the saved-input ring: a set may only wait on stage (i + nsets) % XS when the stage's
     // previous use (tile i + nsets - XS) is one it has already seen complete, i.e. nsets <= XS
-    if (xs > 0 && a.nsets > xs) a.nsets = xs;
+    if (xs > 0 && a.nsets > xs * a.nhalf) a.nsets = xs * a.nhalf;   // (a set steps ceil(nsets / nhalf) work items at a time)
     xs_smem = (size_t)xs * xs_stride;
     epi_smem = tc::EPI_SMEM(EPI, a.nsets, a.BN, tc_use_e2(a.BN)) + xs_smem;
     const size_t budget = optin - tc::STATIC_SMEM_RESERVE - 1024 - epi_smem;
-    if (a.n_ntiles == 1 && b_all + 3 * (size_t)tc::A_STAGE <= budget) {
+    if (a.n_ntiles == 1 && a.nhalf == 1 && b_all + 3 * a_stage <= budget) {
       a.b_resident = 1; a.SB = 0;
-      a.SA = (int)((budget - b_all) / tc::A_STAGE);
+      a.SA = (int)((budget - b_all) / a_stage);
     } else {
       // enough weight slices in flight to cover the L2 latency: one slice feeds 4 MMAs of BN/2 cycles each
       a.b_resident = 0; a.SB = a.BN >= 256 ? 4 : (a.BN >= 128 ? 8 : 12);
       if (const char* e = getenv("LFP_TC_SB")) { const int v = atoi(e); if (v >= 2 && v <= tc::MAX_SB) a.SB = v; }
-      while (a.SB > 2 && (size_t)a.SB * a.BN * 128 + 3 * (size_t)tc::A_STAGE > budget) --a.SB;
-      a.SA = (int)((budget - (size_t)a.SB * a.BN * 128) / tc::A_STAGE);
+      while (a.SB > 2 && (size_t)a.SB * a.BN * 128 + min_sa * a_stage > budget) --a.SB;
+      a.SA = (int)((budget - (size_t)a.SB * a.BN * 128) / a_stage);
     }
-    if ((a.SA >= 3 && (a.b_resident || a.SB >= 3)) || xs <= (xs_max > 0 ? 2 : 0)) break;
+    if ((a.SA >= (int)min_sa && (a.b_resident || a.SB >= 3)) || xs <= (xs_max > 0 ? 2 : 0)) break;
   }
   if (a.SA > tc::MAX_SA) a.SA = tc::MAX_SA;
   // resident-weight launches: more than five activation stages buy nothing, while keeping the request under the 196 KB
@@ -1250,22 +1292,23 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   if (a.b_resident && smem_cap >= (size_t)tc::SMEM_OPTIN) {
     const size_t fixed = (size_t)b_all + epi_smem + 1024 + tc::STATIC_SMEM_RESERVE;
     static const int l1_min_sa = getenv("LFP_TC_L1_MIN_SA") ? atoi(getenv("LFP_TC_L1_MIN_SA")) : 5;
-    while (a.SA > l1_min_sa && fixed + (size_t)a.SA * tc::A_STAGE > 196u * 1024u) --a.SA;
+    while (a.SA > l1_min_sa && fixed + (size_t)a.SA * a_stage > 196u * 1024u) --a.SA;
   }
   if (const char* e = getenv("LFP_TC_SA_MAX")) { const int v = atoi(e); if (v >= 2 && a.SA > v) a.SA = v; }
-  a.nacc = a.BN * a.taps.nphase <= 128 ? 4 : (a.BN * a.taps.nphase <= 256 ? 2 : 1);
-  if (a.nsets > a.nacc) a.nsets = a.nacc;
+  const int acc_cols = a.BN * a.taps.nphase * a.nhalf;   // TMEM columns of one work item
+  a.nacc = acc_cols <= 128 ? 4 : (acc_cols <= 256 ? 2 : 1);
+  if (a.nsets > a.nacc * a.nhalf) a.nsets = a.nacc * a.nhalf;
   static const int bbatch_env = getenv("LFP_TC_BBATCH") ? atoi(getenv("LFP_TC_BBATCH")) : 3;   // A/B knob
   a.bbatch = (!a.b_resident && a.SB >= 6 && bbatch_env == 3) ? 3 : 1;
   LFP_CHECK_ARG(a.SA >= 2, "conv_tc: shared-memory plan failed (BN=%d)", a.BN);
   // layout: [A ring][B ring or resident slice][xsave ring (1024-aligned)][epilogue scratch]
-  a.xs_off = (int)((size_t)a.SA * tc::A_STAGE + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
+  a.xs_off = (int)((size_t)a.SA * a_stage + (a.b_resident ? b_all : (size_t)a.SB * a.BN * 128));
   a.epi_off = (int)((size_t)a.xs_off + xs_smem);
   const size_t smem = (size_t)a.xs_off + epi_smem + 1024;
   static const bool verbose = getenv("LFP_TC_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "conv_tc plan: epi %d mod %d K %d N %d BN %d grid %dx%d taps %d phases %d | SA %d SB %d resident %d XS %d (x %d, stride %d) nsets %d nacc %d smem %zu\n",
-            EPI, (int)MOD, a.K, a.N, a.BN, a.gh, a.gw, ntaps, a.taps.nphase, a.SA, a.SB, a.b_resident, a.XS, a.xs_has_x, a.xs_stride, a.nsets, a.nacc, smem);
+    fprintf(stderr, "conv_tc plan: epi %d mod %d K %d N %d BN %d grid %dx%d taps %d phases %d halves %d | SA %d SB %d resident %d XS %d (x %d, stride %d) nsets %d nacc %d smem %zu\n",
+            EPI, (int)MOD, a.K, a.N, a.BN, a.gh, a.gw, ntaps, a.taps.nphase, a.nhalf, a.SA, a.SB, a.b_resident, a.XS, a.xs_has_x, a.xs_stride, a.nsets, a.nacc, smem);
   const CUtensorMap& nzm = tmNz ? *tmNz : tmA;
   const CUtensorMap& rgm = tmRg ? *tmRg : tmA;
   return a.b_resident ? tc_launch2<EPI, MOD, true>(tmA, tmB, tmX, nzm, rgm, a, smem, s) : tc_launch2<EPI, MOD, false>(tmA, tmB, tmX, nzm, rgm, a, smem, s);
@@ -1277,19 +1320,43 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   LFP_CHECK_ARG(c.taps.nphase <= 1 || (c.taps.nphase == 4 && c.epi == EPI_STORE && c.taps.ngroups == 1 && c.N <= 128),
                 "conv_tc: fused phases need EPI_STORE, one tap group and N <= 128");
   LFP_CHECK_ARG(((uintptr_t)c.in & 15) == 0 && c.wmap != nullptr, "conv_tc: input must be 16-byte aligned");
+  // tall work items (two 16-row halves sharing the streamed weight slices): wide slices whose weights can never be resident,
+  // enough work left for every SM, and little padding below the image
+  int bn0 = (c.taps.nphase > 1 || c.e.rgb_out != nullptr) ? tc_block_n(c.N)
+                                                           : tc_pick_bn(c.N, (int64_t)ceil_div(c.gw, tc::TILE_W) * ceil_div(c.gh, tc::TILE_H) * c.batch);
+  // LFP_TC_TALL: 0 = off, 1 (default) = launches whose slice is 128 wide, 2 = 256-wide slices are also split into two 128-wide
+  // tall ones.  Measured at 1024 px, B = 20, same box: 128 -> 128 at 256 px 742 -> 615 us (forward) / 714 -> 598 us (data
+  // gradient) with tall items.  A 256-wide tall item needs all 512 TMEM columns for its two accumulators, which serialises its
+  // epilogue with the next item's MMAs (+8-17 %); splitting it into 128-wide tall items cuts the L2 -> SM traffic per
+  // (pixel x channel) by 40 % but measured 3-10 % slower on five of the six 256 / 512-channel layers - at 730 TFLOP/s those are
+  // already above the sustained tensor peak of MEASURED_PEAKS.json, i.e. bound by power, not by L2 - so mode 2 stays off.
+  static const int tall_mode = getenv("LFP_TC_TALL") != nullptr ? atoi(getenv("LFP_TC_TALL")) : 1;
+  int nhalf = 1;
+  {
+    const int nph = c.taps.nphase > 0 ? c.taps.nphase : 1;
+    const int64_t rows16 = ceil_div(c.gh, 16) * 16, rows32 = ceil_div(c.gh, 32) * 32;
+    const int64_t tall_items = ceil_div(c.gw, tc::TILE_W) * ceil_div(c.gh, 32) * c.batch * (c.N / 128);
+    const size_t w_bytes = (size_t)c.taps.group_tap0[c.taps.ngroups] * (c.K / 32) * 128 * 128;
+    const bool ok128 = tall_mode > 0 && tc_use_e2(128) && nph == 1 && c.e.rgb_out == nullptr && c.N % 128 == 0 &&
+                       rows32 * 100 <= rows16 * 107 && tall_items >= 4 * (int64_t)num_sms() && w_bytes > 160u * 1024u;
+    if (ok128 && (bn0 == 128 || (bn0 == 256 && tall_mode >= 2))) { bn0 = 128; nhalf = 2; }
+  }
   alignas(64) CUtensorMap tmA;
   const int nb = c.in_bcast ? 1 : c.batch;
   const cuuint64_t dims[5] = {(cuuint64_t)c.K, (cuuint64_t)c.in_w, (cuuint64_t)c.in_h, (cuuint64_t)c.in_planes, (cuuint64_t)nb};
   const cuuint64_t strides[4] = {(cuuint64_t)c.K * 4, (cuuint64_t)c.in_w * c.K * 4, (cuuint64_t)c.in_h * c.in_w * c.K * 4,
                                  (cuuint64_t)c.in_planes * c.in_h * c.in_w * c.K * 4};
-  const cuuint32_t box[5] = {32, tc::HALO_W, tc::HALO_H, 1, 1};
+  const cuuint32_t box[5] = {32, tc::HALO_W, (cuuint32_t)(tc::TILE_H * nhalf + 2), 1, 1};
   LFP_TRY(tc::encode(&tmA, c.in, 5, dims, strides, box));
   tc::Args a{};
   a.batch = c.batch; a.gh = c.gh; a.gw = c.gw;
-  a.tiles_x = (int)ceil_div(c.gw, tc::TILE_W); a.tiles_y = (int)ceil_div(c.gh, tc::TILE_H);
+  a.nhalf = nhalf;
+  a.a_rows = tc::HALO_W * (tc::TILE_H * nhalf + 2);
+  a.a_stage = (a.a_rows * 128 + 1023) / 1024 * 1024;
+  a.tiles_x = (int)ceil_div(c.gw, tc::TILE_W); a.tiles_y = (int)ceil_div(c.gh, tc::TILE_H * nhalf);
+  a.vtiles_per = a.tiles_x * (int)ceil_div(c.gh, tc::TILE_H);
   a.K = c.K; a.N = c.N;
-  a.BN = tc_pick_bn(c.N, (int64_t)ceil_div(c.gw, tc::TILE_W) * ceil_div(c.gh, tc::TILE_H) * c.batch);
-  if (c.taps.nphase > 1 || c.e.rgb_out != nullptr) a.BN = tc_block_n(c.N);   // fused phases / fused ToRGB keep all channels in one CTA
+  a.BN = bn0;   // (fused phases / fused ToRGB keep all channels in one CTA)
   LFP_CHECK_ARG(c.e.rgb_out == nullptr || a.BN == c.N, "conv_tc: the fused ToRGB epilogue needs all %d channels in one CTA", c.N);
   a.in_bcast = c.in_bcast ? 1 : 0;
   a.taps = c.taps;
@@ -1319,7 +1386,7 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
     if (ok) {
       const cuuint64_t nd[3] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, (cuuint64_t)(nb1 ? 1 : c.batch)};
       const cuuint64_t ns[2] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4};
-      const cuuint32_t nbx[3] = {tc::TILE_W, tc::TILE_H, 1};
+      const cuuint32_t nbx[3] = {tc::TILE_W, (cuuint32_t)(tc::TILE_H * nhalf), 1};
       ok = tc::encode_plain(&tmNz, c.e.noise, 3, nd, ns, nbx) == 0;
     }
     a.px_ok = ok ? 1 : 0;
@@ -1350,13 +1417,13 @@ int launch_conv_tc(const TcConv& c, cudaStream_t s) {
     if (ok) {
       const cuuint64_t nd[3] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, (cuuint64_t)(nb1 ? 1 : c.batch)};
       const cuuint64_t ns[2] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4};
-      const cuuint32_t nbx[3] = {tc::TILE_W, tc::TILE_H, 1};
+      const cuuint32_t nbx[3] = {tc::TILE_W, (cuuint32_t)(tc::TILE_H * nhalf), 1};
       ok = tc::encode_plain(&tmNz, c.e.noise, 3, nd, ns, nbx) == 0;
     }
     if (ok && c.e.drgb != nullptr) {
       const cuuint64_t rd[4] = {(cuuint64_t)c.gw, (cuuint64_t)c.gh, 3, (cuuint64_t)c.batch};
       const cuuint64_t rs[3] = {(cuuint64_t)c.gw * 4, (cuuint64_t)c.gh * c.gw * 4, (cuuint64_t)3 * c.gh * c.gw * 4};
-      const cuuint32_t rbx[4] = {tc::TILE_W, tc::TILE_H, 3, 1};
+      const cuuint32_t rbx[4] = {tc::TILE_W, (cuuint32_t)(tc::TILE_H * nhalf), 3, 1};
       ok = tc::encode_plain(&tmRg, c.e.drgb, 4, rd, rs, rbx) == 0;
     }
     a.px_ok = ok ? 1 : 0;
