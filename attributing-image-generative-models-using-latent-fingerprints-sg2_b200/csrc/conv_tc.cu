@@ -1138,11 +1138,17 @@ static int encode_plain(CUtensorMap* map, const void* base, int rank, const cuui
 int tc_block_n(int N) { return N >= 256 ? 256 : N; }
 // Output-channel slice of one launch: the widest slice (best MMA shape) unless that leaves SMs idle - then halve it, down
 // to 32, until there is one work item per SM (every CTA also streams 1/n of the weights, which is what the low-resolution
-// 512-channel layers and small batches are bound by).
+// 512-channel layers and small batches are bound by).  If that lands just above one item per SM, step back up: the second
+// round would run on a handful of SMs (4 x 4 and 8 x 8 at B = 20: 160 items of 64 channels in two rounds -> 80 items of 128
+// in one; forward 72 -> 46 us, data gradient 107 -> 67 us per launch).  A full cost model (rounds x MMA cycles) was tried and
+// lost on the 16 - 32 px layers, whose time is set by the weight stream per CTA rather than by the round count.
 static int tc_pick_bn(int N, int64_t tiles_times_batch) {
+  static const bool legacy = getenv("LFP_TC_PICK_BN") != nullptr && atoi(getenv("LFP_TC_PICK_BN")) == 0;   // A/B knob
   int bn = tc_block_n(N);
   const int sms = num_sms();
   while (bn > 32 && tiles_times_batch * (N / bn) < sms) bn >>= 1;
+  const int64_t items = tiles_times_batch * (N / bn);
+  if (!legacy && bn < tc_block_n(N) && items > sms && items * 4 <= (int64_t)sms * 5) bn <<= 1;
   return bn;
 }
 static int tc_bn_index(int bn) { return bn == 256 ? 0 : (bn == 128 ? 1 : (bn == 64 ? 2 : 3)); }
@@ -1317,13 +1323,14 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 int launch_conv_tc(const TcConv& c, cudaStream_t s) {
   LFP_CHECK_ARG(tc_supported(c.K, c.N, c.gh, c.gw), "conv_tc: unsupported shape K=%d N=%d grid %dx%d", c.K, c.N, c.gh, c.gw);
   LFP_CHECK_ARG(c.taps.ngroups >= 1 && c.taps.ngroups <= 4 && c.taps.group_tap0[c.taps.ngroups] <= 9, "conv_tc: bad tap table");
-  LFP_CHECK_ARG(c.taps.nphase <= 1 || (c.taps.nphase == 4 && c.epi == EPI_STORE && c.taps.ngroups == 1 && c.N <= 128),
-                "conv_tc: fused phases need EPI_STORE, one tap group and N <= 128");
+  LFP_CHECK_ARG(c.taps.nphase <= 1 || (c.taps.nphase == 4 && c.epi == EPI_STORE && c.taps.ngroups == 1),
+                "conv_tc: fused phases need EPI_STORE and one tap group");
   LFP_CHECK_ARG(((uintptr_t)c.in & 15) == 0 && c.wmap != nullptr, "conv_tc: input must be 16-byte aligned");
   // tall work items (two 16-row halves sharing the streamed weight slices): wide slices whose weights can never be resident,
   // enough work left for every SM, and little padding below the image
-  int bn0 = (c.taps.nphase > 1 || c.e.rgb_out != nullptr) ? tc_block_n(c.N)
-                                                           : tc_pick_bn(c.N, (int64_t)ceil_div(c.gw, tc::TILE_W) * ceil_div(c.gh, tc::TILE_H) * c.batch);
+  // (fused ToRGB keeps all channels in one CTA; the four accumulators of fused phases cap the slice at 128 channels)
+  int bn0 = c.e.rgb_out != nullptr ? tc_block_n(c.N) : tc_pick_bn(c.N, (int64_t)ceil_div(c.gw, tc::TILE_W) * ceil_div(c.gh, tc::TILE_H) * c.batch);
+  if (c.taps.nphase > 1 && bn0 > 128) bn0 = 128;
   // LFP_TC_TALL: 0 = off, 1 (default) = launches whose slice is 128 wide, 2 = 256-wide slices are also split into two 128-wide
   // tall ones.  Measured at 1024 px, B = 20, same box: 128 -> 128 at 256 px 742 -> 615 us (forward) / 714 -> 598 us (data
   // gradient) with tall items.  A 256-wide tall item needs all 512 TMEM columns for its two accumulators, which serialises its

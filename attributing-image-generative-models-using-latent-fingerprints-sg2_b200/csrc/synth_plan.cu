@@ -101,6 +101,10 @@ struct lfp_synth {
   int tc_min_res = 4;
   bool debug_sync = false;   // env LFP_DEBUG_SYNC=1: synchronise and log after every profiled launch
   int fuse_phases_max_c = 128;   // env LFP_FUSE_PHASES_MAXC
+  // wider layers are fused too while the whole layer is a single wave of work items (input <= 8 px): one launch instead of four
+  // latency-bound ones (4 -> 8 px: 136 -> 72 us, 8 -> 16 px: 138 -> 84 us at B = 20).  From 16 px on the four accumulators of a
+  // 128-wide slice fill the TMEM, the epilogue no longer overlaps the next item's MMAs, and the separate launches win.
+  int fuse_phases_max_res = 8;   // env LFP_FUSE_PHASES_MAXRES
   bool fuse_phases = true;   // one launch for the four sub-pixel phases of the C <= 64 transposed convs (env LFP_FUSE_PHASES=0 disables)
   bool fuse_rgb = false;     // ToRGB inside the forward conv epilogue on the tensor-core path (env LFP_FUSE_RGB=1 enables;
                              // measured slower than the separate kernel: the epilogue is the longer pole at N <= 64)
@@ -315,6 +319,7 @@ extern "C" int lfp_synth_create(lfp_synth** out, int size, int style_dim, int ch
   if (const char* e = getenv("LFP_DEBUG_SYNC")) h->debug_sync = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_PHASES")) h->fuse_phases = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_PHASES_MAXC")) h->fuse_phases_max_c = atoi(e);
+  if (const char* e = getenv("LFP_FUSE_PHASES_MAXRES")) h->fuse_phases_max_res = atoi(e);
   if (const char* e = getenv("LFP_FUSE_RGB")) h->fuse_rgb = atoi(e) != 0;
   if (const char* e = getenv("LFP_FUSE_ACTBWD")) h->fuse_actbwd = atoi(e) != 0;
   if (const char* e = getenv("LFP_TC_MIN_RES")) { const int v = atoi(e); if (v >= 4) h->tc_min_res = v; }
@@ -572,7 +577,7 @@ static int synth_forward_impl(lfp_synth* h, int batch, const float* latent, cons
       // stride-2 transposed conv as four sub-pixel phases into [B, 2H+1, 2W+1, Cout], then blur+epilogue
       float* T = ws + L.scratchT;
       const int H = c.res_in;
-      const bool fuse_phases = use_tc && c.cout <= h->fuse_phases_max_c && h->fuse_phases;
+      const bool fuse_phases = use_tc && (c.cout <= h->fuse_phases_max_c || c.res_in <= h->fuse_phases_max_res) && h->fuse_phases;
       if (fuse_phases) {
         // all four sub-pixel phases in one launch: the activation tile is loaded and modulated once, every tap
         // accumulates into its phase's TMEM accumulator, and the epilogue writes the four planes of [B, 4, H+1, H+1, Cout]
