@@ -504,23 +504,43 @@ __global__ void __launch_bounds__(MOD ? NTHREADS_MOD : NTHREADS_PLAIN, 1) conv_t
             const int pos = et & 7, r0 = et >> 3;
             const int ch = (pos ^ (r0 & 7)) << 2;
             const float4 s4 = __ldg(reinterpret_cast<const float4*>(sm + kc * 32 + ch));
-            // twelve rows (r0 + 16 i) per pass: 180 rows = one pass, the 340 rows of a tall tile = two
-            for (int rb = 0; rb < a.a_rows; rb += 192) {
-              float4* p = reinterpret_cast<float4*>(smem_al + sa * a.a_stage + (rb + r0) * 128 + pos * 16);
-              const int left = a.a_rows - rb - r0;   // rows r0 + 16 i < left are inside the stage
+            // twelve rows (r0 + 16 i) per pass.  The plain 180-row stage is one pass with compile-time bounds (rows 176 + r0 exist
+            // for r0 < 4 only): a version with run-time bounds for both stage heights cost the modulated streaming launches
+            // 10-30 % (64 x 64 px conv 488 -> 531 us, the one-tap phase launches 80 -> 107 us).
+            if (a.nhalf == 1) {
+              float4* p = reinterpret_cast<float4*>(smem_al + sa * a.a_stage + r0 * 128 + pos * 16);
               float4 v[12];
 #pragma unroll
               for (int i = 0; i < 12; ++i)
-                if (16 * i < left) v[i] = p[i * 128];   // row rb + r0 + 16 i, 128 float4 apart
+                if (i < 11 || r0 + 176 < 180) v[i] = p[i * 128];   // row r0 + 16 i, 128 float4 apart
 #pragma unroll
               for (int i = 0; i < 12; ++i)
-                if (16 * i < left) {
+                if (i < 11 || r0 + 176 < 180) {
                   v[i].x = to_tf32(v[i].x * s4.x);
                   v[i].y = to_tf32(v[i].y * s4.y);
                   v[i].z = to_tf32(v[i].z * s4.z);
                   v[i].w = to_tf32(v[i].w * s4.w);
                   p[i * 128] = v[i];
                 }
+            } else {
+              // tall stage, 340 rows: rows 0 .. 191 in full, then rows 192 + r0 + 16 i < 340 (i < 9, or i = 9 for r0 < 4)
+#pragma unroll
+              for (int ps = 0; ps < 2; ++ps) {
+                float4* p = reinterpret_cast<float4*>(smem_al + sa * a.a_stage + (ps * 192 + r0) * 128 + pos * 16);
+                float4 v[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+                  if (ps == 0 || i < 9 || (i == 9 && r0 < 4)) v[i] = p[i * 128];
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+                  if (ps == 0 || i < 9 || (i == 9 && r0 < 4)) {
+                    v[i].x = to_tf32(v[i].x * s4.x);
+                    v[i].y = to_tf32(v[i].y * s4.y);
+                    v[i].z = to_tf32(v[i].z * s4.z);
+                    v[i].w = to_tf32(v[i].w * s4.w);
+                    p[i * 128] = v[i];
+                  }
+              }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(bar_a_ready(sa));
