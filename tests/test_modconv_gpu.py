@@ -78,7 +78,7 @@ def layer_check(Cin, Cout, res, up, B, k=3, demod=True, seed=0, precs=("fp32", "
         y = m(xg, sg)
         gx, gs = torch.autograd.grad((y * ct.to(DEV)).sum(), [xg, sg])
         tol_y, tol_g = (1e-4, 1e-4) if prec_name == "fp32" else (5e-3, 1e-2)
-        err = float((y.detach().cpu() - yr.detach()).abs().max()) / max(1.0, float(yr.abs().max()))
+        err = float((y.detach().cpu() - yr.detach()).abs().max()) / max(1.0, float(yr.detach().abs().max()))
         rel_x = float((gx.cpu() - gxr).norm() / gxr.norm())
         rel_s = float((gs.cpu() - gsr).norm() / gsr.norm())
         assert err <= tol_y and rel_x <= tol_g and rel_s <= tol_g, (Cin, Cout, res, up, B, prec_name, err, rel_x, rel_s)
@@ -130,3 +130,32 @@ def test_styledconv_and_torgb_modules_run_native():
     imgr = oracle.to_rgb(params, "to_rgbs.0", yr, st, skip)
     np.testing.assert_allclose(y.detach().cpu().numpy(), yr.numpy(), rtol=1e-4, atol=1e-4 * float(yr.abs().max()))
     np.testing.assert_allclose(img.detach().cpu().numpy(), imgr.numpy(), rtol=1e-4, atol=1e-4 * float(imgr.abs().max()))
+
+
+def test_tall_work_items_match_oracle_and_single_sample_bits():
+    """128 -> 128 at 256 px with B = 4 runs on tall work items (two 16-row halves per item share the streamed weight slices,
+    conv_tc.cu Args::nhalf; chosen from 3 samples up at this shape), B = 1 does not: the oracle check covers the tall path on
+    both forward and data-gradient kernels, and each sample of the batch has the bits of its single-sample call."""
+    from lfp_native import capi
+    Cin = Cout = 128
+    res, B, sd, k = 256, 4, 512, 3
+    layer_check(Cin, Cout, res, False, B, seed=3, precs=("tf32",))
+    rs = np.random.RandomState(77)
+    t = dict(weight=torch.from_numpy(rs.standard_normal((1, Cout, Cin, k, k)).astype(np.float32)),
+             mod_w=torch.from_numpy(rs.standard_normal((Cin, sd)).astype(np.float32)),
+             mod_b=torch.ones(Cin))
+    x = torch.from_numpy(rs.standard_normal((B, Cin, res, res)).astype(np.float32)).to(DEV)
+    style = torch.from_numpy(rs.standard_normal((B, sd)).astype(np.float32)).to(DEV)
+    ct = torch.from_numpy(rs.standard_normal((B, Cout, res, res)).astype(np.float32)).to(DEV)
+    m = make_module(Cin, Cout, k, sd, True, False, t, capi.PREC_TF32)
+
+    def run(sl):
+        xg, sg = x[sl].clone().requires_grad_(True), style[sl].clone().requires_grad_(True)
+        y = m(xg, sg)
+        gx, gs = torch.autograd.grad((y * ct[sl]).sum(), [xg, sg])
+        return y.detach(), gx, gs
+
+    yb, gxb, gsb = run(slice(0, B))
+    for b in (0, B - 1):
+        y1, gx1, gs1 = run(slice(b, b + 1))
+        assert torch.equal(y1[0], yb[b]) and torch.equal(gx1[0], gxb[b]) and torch.equal(gs1[0], gsb[b]), b
