@@ -2,10 +2,12 @@
 //
 //   D[128 pixels, BN channels] (fp32, TMEM)  +=  A[128 pixels, 32 ch] (tf32, smem) * B[BN, 32 ch]^T (tf32, smem)
 //
-// * One CTA = one 8 (x) x 16 (y) tile of output-grid pixels of one sample x one BN-wide slice of the
-//   output channels.  M = 128 is the UMMA M; a pixel is row m = 8*y + x of the accumulator.
-// * A: TMA loads the haloed 10 x 18 window of the NHWC activation (32 channels = one 128-byte row per
-//   pixel, SWIZZLE_128B, out-of-range pixels zero-filled by TMA = the conv padding) ONCE per 32-channel
+// * One work item = one 8 (x) x 16 (y) tile of output-grid pixels of one sample x one BN-wide slice of the
+//   output channels.  M = 128 is the UMMA M; a pixel is row m = 8*y + x of the accumulator.  A "tall" item
+//   (Args::nhalf = 2) is two such tiles stacked in y with one accumulator each: every streamed weight slice
+//   feeds both, which halves the L2 -> SM weight traffic of the launches that are bound by it.
+// * A: TMA loads the haloed 10 x 18 (tall: 10 x 34) window of the NHWC activation (32 channels = one 128-byte
+//   row per pixel, SWIZZLE_128B, out-of-range pixels zero-filled by TMA = the conv padding) ONCE per 32-channel
 //   chunk; every filter tap (dy,dx) then reads the same image through a UMMA descriptor whose start
 //   address is shifted by (dy*10+dx) rows and whose 8-row-group pitch (SBO) is 10 rows.  The swizzle
 //   XOR is a function of the absolute smem address, so shifted starts stay consistent with what TMA
@@ -17,20 +19,26 @@
 //   round-to-nearest tf32 conversion; demodulation, noise, bias and leaky-ReLU are the epilogue
 //   (src/model.py:261-263, 316, src/op/fused_act.py:110-127).
 // * Persistent CTAs (one per SM) walk the (sample, tile, n-tile) list with a stride of gridDim.x.
-//   Roles: warp 0 = TMA producer (runs ahead across tiles), warp 1 = MMA issuer (warp-uniform control
+//   Roles: warp 0 = TMA producer (runs ahead across work items), warp 1 = MMA issuer (warp-uniform control
 //   flow, one elected lane, issue loop unrolled), warps 2-5 = A transform (a third epilogue set in the
-//   unmodulated kernels), warps 6-9 / 10-13 / 14-17 = epilogue sets that alternate tiles (TMEM ->
-//   registers -> global).  The accumulator has 2-4 TMEM stages, so the epilogue of tile i overlaps the
-//   MMAs of tiles i+1...; an epilogue set waits on mbarrier parities, which is only unambiguous while
-//   nsets <= nacc (and nsets <= XS for the saved-input ring) - see tc_launch.
-// * mbarrier rings: A (3-8 stages); B either streamed (2-4 stages) or, when the whole [taps, K, BN]
+//   unmodulated kernels), warps 6-9 / 10-13 = epilogue sets that alternate (virtual) tiles (TMEM ->
+//   registers -> global); the modulated layout pads to 512 threads (register allocation granularity).
+//   The accumulator has 1-4 TMEM stages, so the epilogue of item i overlaps the MMAs of items i+1...;
+//   an epilogue set waits on mbarrier parities, which is only unambiguous while it steps at most nacc work
+//   items (and at most XS ring stages) at a time - see tc_launch.
+// * mbarrier rings: A (2-8 stages); B either streamed (3-12 stages) or, when the whole [taps, K, BN]
 //   weight slice fits in shared memory (the C <= 64 layers), loaded once and kept resident for the
-//   CTA's lifetime; XS = saved forward input tiles for the data-gradient epilogues (N <= 64).
-// * Epilogues: BN <= 128 read the accumulator with tcgen05.ld.16x256b (thread = 4 pixels x 8 channels,
-//   tools/tmem_layout_probe.cu), BN = 256 with 32x32b (thread = 1 pixel x 32 channels).  EPI_ACT: demod,
+//   CTA's lifetime; XS = per-item ring of what the epilogue needs: saved forward input tiles of the
+//   data-gradient epilogues (N <= 64), per-pixel noise / skip-gradient tiles and the per-channel
+//   demodulation / bias / modulation vectors of the slice (PXS kernels).
+// * Epilogues: tcgen05.ld.16x256b read-out for every slice width (thread = 4 pixels x 8 channels,
+//   tools/tmem_layout_probe.cu; the 32x32b variant of round 1 is kept behind LFP_TC_E2=0).  EPI_ACT: demod,
 //   noise, bias, lrelu (optionally the ToRGB dot product); EPI_STORE: raw, or the four sub-pixel phases
 //   of the transposed conv from four accumulators; EPI_DGRAD(_ACT): x s, style-gradient pixel sums and,
-//   fused, the backward through noise / bias / lrelu / ToRGB of the layer below.
+//   fused, the backward through noise / bias / lrelu / ToRGB of the layer below; EPI_RELU / EPI_DGRAD_RELU
+//   for the VGG16 backbone of the perceptual loss.
+// * Measured floors (profiles/r02_umma_rate.md, r02_conv_l2_traffic.md): an M = 128, K = 8 tf32 MMA costs 52.4
+//   cycles for every N <= 64 (N / 2 above); streamed weights run into the ~6300 B/clk L2 -> SM throughput cap.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -41,7 +49,7 @@
 namespace lfp {
 namespace tc {
 
-constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
+constexpr int TILE_W = 8, TILE_H = 16, HALO_W = TILE_W + 2;   // the haloed window is HALO_W x (TILE_H * nhalf + 2) pixels
 // one haloed activation stage: 10 x 18 = 180 rows of 128 bytes (23040 B, stride 23552) for a 16-row tile, 10 x 34 = 340 rows
 // (43520 B, stride 44032) for a tall one - Args::a_rows / a_stage
 constexpr int MAX_SA = 8, MAX_SB = 12;
