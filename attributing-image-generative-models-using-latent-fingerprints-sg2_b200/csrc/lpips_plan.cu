@@ -93,97 +93,133 @@ __global__ void __launch_bounds__(256) normalize_nhwc_kernel(const float* __rest
 //     element of the window in row-major order (what torch's max_pool2d backward does)
 //   G = (d f + routed) * (f > 0): gradient w.r.t. the pre-ReLU output of the tap's convolution
 // partial[(b * nwarps + window) ] = the window's loss contribution (summed in a fixed order afterwards).
-template <bool UP>
+// LPW lanes share a window (16 for C = 64: two windows per warp, 32 otherwise) and NJ = C / (4 LPW) float4 per lane and pixel.
+// The window's features stay in registers across the three passes (norms; loss and sum_c g_c f_c; gradient), so f is read
+// once; the first version re-read it per pass with half of the lanes idle at C = 64 and ran at 1.15 TB/s on the 1024 px tap
+// (10.8 ms of the 89 ms LPIPS step at 1024 px, B = 20).  Lane li holds channels 4 (li + LPW jj) ..+3: the per-lane fmaf chains
+// and the xor trees add the same numbers in the same order as before (the idle upper half-warp contributed exact zeros).
+template <bool UP, int LPW, int NJ>
 __global__ void __launch_bounds__(256) tap_backward_kernel(const float* __restrict__ f, const float* __restrict__ t, int64_t t_bstride,
                                                            const float* __restrict__ lin, const float* __restrict__ up,
                                                            float* __restrict__ G, float* __restrict__ partial, int H, int W, int C,
                                                            float inv_hw, int64_t nwin_per) {
-  const int lane = threadIdx.x & 31;
-  const int64_t win = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  constexpr int WPW = 32 / LPW;   // windows per warp
+  const int lane = threadIdx.x & 31, li = lane % LPW;
+  const int64_t win = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * WPW + lane / LPW;
   const int b = blockIdx.y;
-  if (win >= nwin_per) return;
+  const bool live = win < nwin_per;            // (a dead half-warp still takes part in the shuffles)
   const int W2 = W / 2;
-  const int wy = (int)(win / W2), wx = (int)(win - (int64_t)wy * W2);
-  const int C4 = C / 4;
-  float loss = 0.f;
-  // pass 1: the four pixels' squared norms and sum_c g_c f_c need the whole channel vector: two sweeps over C
-  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t wc = live ? win : 0;
+  const int wy = (int)(wc / W2), wx = (int)(wc - (int64_t)wy * W2);
   const float4* fp[4];
   const float4* tp[4];
   float4* gp[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int64_t pix = (int64_t)(2 * wy + (k >> 1)) * W + 2 * wx + (k & 1);
-    fp[k] = reinterpret_cast<const float4*>(f + ((int64_t)b * H * W + pix) * C);
-    tp[k] = reinterpret_cast<const float4*>(t + (int64_t)b * t_bstride + pix * C);
-    gp[k] = reinterpret_cast<float4*>(G + ((int64_t)b * H * W + pix) * C);
+    fp[k] = reinterpret_cast<const float4*>(f + ((int64_t)b * H * W + pix) * C) + li;
+    tp[k] = reinterpret_cast<const float4*>(t + (int64_t)b * t_bstride + pix * C) + li;
+    gp[k] = reinterpret_cast<float4*>(G + ((int64_t)b * H * W + pix) * C) + li;
   }
-  for (int j = lane; j < C4; j += 32)
+  // pass 1: the four pixels' squared norms
+  float4 v[4][NJ];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { const float4 v = fp[k][j]; ss[k] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss[k])))); }
+  for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k][jj] = live ? fp[k][jj * LPW] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float4 q = v[k][jj]; ss[k] = fmaf(q.x, q.x, fmaf(q.y, q.y, fmaf(q.z, q.z, fmaf(q.w, q.w, ss[k])))); }
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], off);
+    for (int off = LPW / 2; off > 0; off >>= 1) ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], off);
   float nrm[4], inv[4], dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int k = 0; k < 4; ++k) { nrm[k] = sqrtf(ss[k]); inv[k] = 1.f / (nrm[k] + 1e-10f); }
-  const float4* lp = reinterpret_cast<const float4*>(lin);
-  for (int j = lane; j < C4; j += 32) {
-    const float4 l4 = __ldg(lp + j);
+  // pass 2: loss and sum_c lin_c (n_c - t_c) f_c
+  const float4* lp = reinterpret_cast<const float4*>(lin) + li;
+  float loss = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < NJ; ++jj) {
+    const float4 l4 = __ldg(lp + jj * LPW);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4 v = fp[k][j], tt = tp[k][j];
-      const float dx = v.x * inv[k] - tt.x, dy = v.y * inv[k] - tt.y, dz = v.z * inv[k] - tt.z, dw = v.w * inv[k] - tt.w;
+      const float4 q = v[k][jj];
+      const float4 tt = live ? tp[k][jj * LPW] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float dx = q.x * inv[k] - tt.x, dy = q.y * inv[k] - tt.y, dz = q.z * inv[k] - tt.z, dw = q.w * inv[k] - tt.w;
       loss = fmaf(l4.x * dx, dx, fmaf(l4.y * dy, dy, fmaf(l4.z * dz, dz, fmaf(l4.w * dw, dw, loss))));
-      dot[k] = fmaf(l4.x * dx, v.x, fmaf(l4.y * dy, v.y, fmaf(l4.z * dz, v.z, fmaf(l4.w * dw, v.w, dot[k]))));
+      dot[k] = fmaf(l4.x * dx, q.x, fmaf(l4.y * dy, q.y, fmaf(l4.z * dz, q.z, fmaf(l4.w * dw, q.w, dot[k]))));
     }
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
+  for (int off = LPW / 2; off > 0; off >>= 1) {
     loss += __shfl_xor_sync(0xffffffffu, loss, off);
 #pragma unroll
     for (int k = 0; k < 4; ++k) dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], off);
   }
+  if (!live) return;
   // d f_c = 2/HW * ( lin_c (n_c - t_c) inv - f_c * dot * inv^2 / nrm )      (second term 0 where the pixel is all zero)
   float c2[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) c2[k] = nrm[k] > 0.f ? dot[k] * inv[k] * inv[k] / nrm[k] : 0.f;
   const float s2 = 2.f * inv_hw;
-  const float4* upp = UP ? reinterpret_cast<const float4*>(up + (((int64_t)b * (H / 2) + wy) * W2 + wx) * C) : nullptr;
-  for (int j = lane; j < C4; j += 32) {
-    const float4 l4 = __ldg(lp + j);
-    float4 v[4];
+  const float4* upp = UP ? reinterpret_cast<const float4*>(up + (((int64_t)b * (H / 2) + wy) * W2 + wx) * C) + li : nullptr;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = fp[k][j];
+  for (int jj = 0; jj < NJ; ++jj) {
+    const float4 l4 = __ldg(lp + jj * LPW);
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
     int ax = 0, ay = 0, az = 0, aw = 0;   // index of the first maximum of the window, per channel
     if (UP) {
-      u = upp[j];
+      u = upp[jj * LPW];
 #define LFP_ARGMAX(comp, a)                                                                 \
   {                                                                                         \
-    float m = v[0].comp; a = 0;                                                             \
-    if (v[1].comp > m) { m = v[1].comp; a = 1; }                                            \
-    if (v[2].comp > m) { m = v[2].comp; a = 2; }                                            \
-    if (v[3].comp > m) { m = v[3].comp; a = 3; }                                            \
+    float m = v[0][jj].comp; a = 0;                                                         \
+    if (v[1][jj].comp > m) { m = v[1][jj].comp; a = 1; }                                    \
+    if (v[2][jj].comp > m) { m = v[2][jj].comp; a = 2; }                                    \
+    if (v[3][jj].comp > m) { m = v[3][jj].comp; a = 3; }                                    \
   }
       LFP_ARGMAX(x, ax) LFP_ARGMAX(y, ay) LFP_ARGMAX(z, az) LFP_ARGMAX(w, aw)
 #undef LFP_ARGMAX
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4 tt = tp[k][j];
+      const float4 q = v[k][jj];
+      const float4 tt = tp[k][jj * LPW];
       float4 g;
-      g.x = s2 * (l4.x * (v[k].x * inv[k] - tt.x) * inv[k] - v[k].x * c2[k]);
-      g.y = s2 * (l4.y * (v[k].y * inv[k] - tt.y) * inv[k] - v[k].y * c2[k]);
-      g.z = s2 * (l4.z * (v[k].z * inv[k] - tt.z) * inv[k] - v[k].z * c2[k]);
-      g.w = s2 * (l4.w * (v[k].w * inv[k] - tt.w) * inv[k] - v[k].w * c2[k]);
+      g.x = s2 * (l4.x * (q.x * inv[k] - tt.x) * inv[k] - q.x * c2[k]);
+      g.y = s2 * (l4.y * (q.y * inv[k] - tt.y) * inv[k] - q.y * c2[k]);
+      g.z = s2 * (l4.z * (q.z * inv[k] - tt.z) * inv[k] - q.z * c2[k]);
+      g.w = s2 * (l4.w * (q.w * inv[k] - tt.w) * inv[k] - q.w * c2[k]);
       if (UP) { if (ax == k) g.x += u.x; if (ay == k) g.y += u.y; if (az == k) g.z += u.z; if (aw == k) g.w += u.w; }
-      g.x = v[k].x > 0.f ? g.x : 0.f; g.y = v[k].y > 0.f ? g.y : 0.f; g.z = v[k].z > 0.f ? g.z : 0.f; g.w = v[k].w > 0.f ? g.w : 0.f;
-      gp[k][j] = g;
+      g.x = q.x > 0.f ? g.x : 0.f; g.y = q.y > 0.f ? g.y : 0.f; g.z = q.z > 0.f ? g.z : 0.f; g.w = q.w > 0.f ? g.w : 0.f;
+      gp[k][jj * LPW] = g;
     }
   }
-  if (lane == 0) partial[(int64_t)b * nwin_per + win] = loss * inv_hw;
+  if (li == 0) partial[(int64_t)b * nwin_per + win] = loss * inv_hw;
+}
+
+template <bool UP>
+static int launch_tap_backward(const float* f, const float* t, int64_t tstride, const float* lin, const float* up, float* G, float* partial,
+                               int H, int W, int C, int batch, int64_t nwin, cudaStream_t s) {
+  const float inv_hw = 1.f / (float)((int64_t)H * W);
+#define LFP_TAP(LPW, NJ)                                                                                          \
+  {                                                                                                               \
+    dim3 grid((unsigned)ceil_div(nwin, (int64_t)8 * (32 / LPW)), (unsigned)batch);                                 \
+    tap_backward_kernel<UP, LPW, NJ><<<grid, 256, 0, s>>>(f, t, tstride, lin, up, G, partial, H, W, C, inv_hw, nwin); \
+  }
+  switch (C) {
+    case 64: LFP_TAP(16, 1) break;
+    case 128: LFP_TAP(32, 1) break;
+    case 256: LFP_TAP(32, 2) break;
+    case 512: LFP_TAP(32, 4) break;
+    default: set_error("lpips: unsupported tap width %d", C); return LFP_EUNSUPPORTED;
+  }
+#undef LFP_TAP
+  LFP_LAUNCH_CHECK();
+  return 0;
 }
 
 // loss[b] (+)= sum over windows of partial[b, :] in a fixed order: 256 interleaved accumulators, then a tree
@@ -415,10 +451,8 @@ extern "C" int lfp_lpips_loss_grad(lfp_lpips* h, int batch, const float* est, fl
     const int64_t nwin = (int64_t)(R / 2) * (Wd / 2);
     const int64_t tstride = h->target_batch == 1 ? 0 : (int64_t)R * Wd * C;
     float* G = gbuf[cur];
-    dim3 grid((unsigned)ceil_div(nwin, 8), (unsigned)batch);
-    if (up) tap_backward_kernel<true><<<grid, 256, 0, s>>>(ws + L.act[c_tap], h->tfeat[k], tstride, h->lin[k], up, G, ws + L.partial, R, Wd, C, 1.f / (float)((int64_t)R * Wd), nwin);
-    else tap_backward_kernel<false><<<grid, 256, 0, s>>>(ws + L.act[c_tap], h->tfeat[k], tstride, h->lin[k], nullptr, G, ws + L.partial, R, Wd, C, 1.f / (float)((int64_t)R * Wd), nwin);
-    LFP_LAUNCH_CHECK();
+    if (up) LFP_TRY(launch_tap_backward<true>(ws + L.act[c_tap], h->tfeat[k], tstride, h->lin[k], up, G, ws + L.partial, R, Wd, C, batch, nwin, s));
+    else LFP_TRY(launch_tap_backward<false>(ws + L.act[c_tap], h->tfeat[k], tstride, h->lin[k], nullptr, G, ws + L.partial, R, Wd, C, batch, nwin, s));
     lpips_loss_reduce_kernel<<<(unsigned)batch, 256, 0, s>>>(ws + L.partial, nwin, loss, k == 4 ? 0 : 1);
     LFP_LAUNCH_CHECK();
     if (d_est == nullptr) { up = nullptr; continue; }   // value only: no gradient chain (the taps' G buffers are scratch)
