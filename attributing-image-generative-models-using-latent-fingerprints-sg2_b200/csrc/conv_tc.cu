@@ -1277,12 +1277,13 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   static const size_t smem_cap = getenv("LFP_TC_SMEM_CAP") ? (size_t)atol(getenv("LFP_TC_SMEM_CAP")) : (size_t)tc::SMEM_OPTIN;
   const size_t optin = smem_cap < (size_t)tc::SMEM_OPTIN && smem_cap >= 98304 ? smem_cap : (size_t)tc::SMEM_OPTIN;
   const int nsets0 = a.nsets;
-  // LFP_TC_PREFER_RES=1: make the whole weight slice resident first, giving up saved-input ring stages (down to none: the
-  // epilogue then reads the saved input from global memory) for it.  Measured on the N <= 64 data-gradient layers at
-  // 512 / 1024 px: no gain - 64 -> 64 at 512 px takes 1.43 ms either way (with the ring the weights stream, 147 KB per
-  // tile; without it ncu shows 43 % of all stall samples on the epilogue's global loads of the saved input), and the
-  // stride-2 32 -> 64 layer loses 6 % with a two-stage ring.  So the round-1 order (ring first) stays the default.
-  static const bool prefer_res = getenv("LFP_TC_PREFER_RES") && atoi(getenv("LFP_TC_PREFER_RES")) != 0;
+  // Resident weights first: when the whole weight slice fits once the saved-input ring is given up (the 64 -> 64 data
+  // gradients: 147 KB of weights against a 34 KB-per-stage ring), keep the weights and let the epilogue read the saved input
+  // from global memory.  With the round-1 epilogue this was a wash (1.43 ms either way at 512 px: the streamed weights cost
+  // 147 KB of L2 traffic per tile, the global loads 43 % of the epilogue's stall samples); with the rebuilt epilogue
+  // addressing it wins: 64 -> 64 at 512 px 1356 -> 1127 us, the LPIPS step at 1024 px 80.6 -> 79.3 ms (same box).
+  // LFP_TC_PREFER_RES=0 restores ring-first.
+  static const bool prefer_res = getenv("LFP_TC_PREFER_RES") == nullptr || atoi(getenv("LFP_TC_PREFER_RES")) != 0;
   bool planned = false;
   if (prefer_res && a.n_ntiles == 1 && a.nhalf == 1)
     for (int xs = xs_max; xs >= 0 && !planned; --xs) {
