@@ -13,6 +13,7 @@
 // shape the tcgen05 kernel supports run on it when precision = LFP_PREC_TF32.  Parameters are frozen constants (as in the
 // plan): no weight gradients.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -91,6 +92,78 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_scale_kernel(const float* __
   }
 }
 
+// Vector forms of the two layout kernels for the common case (hw and C multiples of 4, 16-byte aligned bases): a thread
+// moves a 4 channel x 4 pixel block with four 128-bit loads, transposes it in registers and stores four 128-bit words; a warp
+// covers CQ channel quads x 32 / CQ pixel quads, so the NHWC side is written / read as whole 16 CQ-byte runs per pixel (the
+// full 128-byte line for 32 channels) and the NCHW side as 64-byte (CQ = 8) or 128-byte (CQ = 4) runs per channel row.  No
+// shared memory, no barrier, 64 bytes in flight per thread.  Same arithmetic as the scalar kernels (one multiply), so the
+// results are bit-identical; the scalar kernels remain for odd extents and channel counts.
+template <int CQ>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_vec_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                               const float* __restrict__ scale, int C, int Cp, int64_t hw) {
+  constexpr int PG = 32 / CQ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cq = lane % CQ, pg = lane / CQ;
+  const int b = blockIdx.y;
+  const int64_t pix = ((int64_t)blockIdx.x * 8 + warp) * (4 * PG) + 4 * pg;
+  if (pix >= hw) return;
+  for (int c4 = 4 * cq; c4 < Cp; c4 += 4 * CQ) {
+    float4 v[4];
+    if (c4 < C) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = ldg_stream(reinterpret_cast<const float4*>(in + ((int64_t)b * C + c4 + j) * hw + pix));
+      if (scale) {
+        const float4 sc = *reinterpret_cast<const float4*>(scale + (int64_t)b * Cp + c4);
+        v[0].x *= sc.x; v[0].y *= sc.x; v[0].z *= sc.x; v[0].w *= sc.x;
+        v[1].x *= sc.y; v[1].y *= sc.y; v[1].z *= sc.y; v[1].w *= sc.y;
+        v[2].x *= sc.z; v[2].y *= sc.z; v[2].z *= sc.z; v[2].w *= sc.z;
+        v[3].x *= sc.w; v[3].y *= sc.w; v[3].z *= sc.w; v[3].w *= sc.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float* o = out + ((int64_t)b * hw + pix) * Cp + c4;
+    stg_stream(reinterpret_cast<float4*>(o), make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+    stg_stream(reinterpret_cast<float4*>(o + Cp), make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
+    stg_stream(reinterpret_cast<float4*>(o + 2 * (int64_t)Cp), make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
+    stg_stream(reinterpret_cast<float4*>(o + 3 * (int64_t)Cp), make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
+  }
+}
+
+template <int CQ>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_vec_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                               const float* __restrict__ scale, int C, int Cp, int64_t hw) {
+  constexpr int PG = 32 / CQ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cq = lane % CQ, pg = lane / CQ;
+  const int b = blockIdx.y;
+  const int64_t pix = ((int64_t)blockIdx.x * 8 + warp) * (4 * PG) + 4 * pg;
+  if (pix >= hw) return;
+  for (int c4 = 4 * cq; c4 < C; c4 += 4 * CQ) {   // padded channels are dropped (C is a multiple of 4 here)
+    const float* i0 = in + ((int64_t)b * hw + pix) * Cp + c4;
+    const float4 p0 = ldg_stream(reinterpret_cast<const float4*>(i0));
+    const float4 p1 = ldg_stream(reinterpret_cast<const float4*>(i0 + Cp));
+    const float4 p2 = ldg_stream(reinterpret_cast<const float4*>(i0 + 2 * (int64_t)Cp));
+    const float4 p3 = ldg_stream(reinterpret_cast<const float4*>(i0 + 3 * (int64_t)Cp));
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (scale) sc = *reinterpret_cast<const float4*>(scale + (int64_t)b * Cp + c4);
+    float4 r0 = make_float4(p0.x, p1.x, p2.x, p3.x), r1 = make_float4(p0.y, p1.y, p2.y, p3.y);
+    float4 r2 = make_float4(p0.z, p1.z, p2.z, p3.z), r3 = make_float4(p0.w, p1.w, p2.w, p3.w);
+    if (scale) {
+      r0.x *= sc.x; r0.y *= sc.x; r0.z *= sc.x; r0.w *= sc.x;
+      r1.x *= sc.y; r1.y *= sc.y; r1.z *= sc.y; r1.w *= sc.y;
+      r2.x *= sc.z; r2.y *= sc.z; r2.z *= sc.z; r2.w *= sc.z;
+      r3.x *= sc.w; r3.y *= sc.w; r3.z *= sc.w; r3.w *= sc.w;
+    }
+    float* o = out + ((int64_t)b * C + c4) * hw + pix;
+    stg_stream(reinterpret_cast<float4*>(o), r0);
+    stg_stream(reinterpret_cast<float4*>(o + hw), r1);
+    stg_stream(reinterpret_cast<float4*>(o + 2 * hw), r2);
+    stg_stream(reinterpret_cast<float4*>(o + 3 * hw), r3);
+  }
+}
+
 // partial[(b * Q + q) * C + c] = sum over the pixels of segment q of a[b, pix, c] * bb[b, pix, c]   (NHWC, fixed order)
 __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ a, const float* __restrict__ bb,
                                                           float* __restrict__ partial, int C, int64_t hw, int seglen, int Q) {
@@ -113,6 +186,38 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restric
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x & 31];
     partial[((int64_t)b * Q + q) * C + c] = t;
+  }
+}
+
+// 128-bit form of dot_partial_kernel: 256 threads = 4 segments x 8 pixel lanes x 8 channel quads.  Every channel keeps the
+// scalar kernel's summation order (pixel lane `sub` runs p0 + sub, p0 + sub + 8, ... with one fmaf chain; the eight lanes are
+// added in index order), so the partial sums are bit-identical.
+__global__ void __launch_bounds__(256) dot_partial_vec_kernel(const float* __restrict__ a, const float* __restrict__ bb,
+                                                              float* __restrict__ partial, int C, int64_t hw, int seglen, int Q) {
+  const int cq = threadIdx.x & 7, sub = (threadIdx.x >> 3) & 7, qs = threadIdx.x >> 6;
+  const int c4 = (blockIdx.x * 8 + cq) * 4;
+  const int q = blockIdx.y * 4 + qs, b = blockIdx.z;
+  __shared__ float4 sm[4][8][8];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool live = c4 < C && q < Q;
+  if (live) {
+    const int64_t p0 = (int64_t)q * seglen, p1 = p0 + seglen < hw ? p0 + seglen : hw;
+#pragma unroll 4
+    for (int64_t p = p0 + sub; p < p1; p += 8) {
+      const int64_t i = ((int64_t)b * hw + p) * C + c4;
+      const float4 va = ldg_stream(reinterpret_cast<const float4*>(a + i));
+      const float4 vb = ldg_stream(reinterpret_cast<const float4*>(bb + i));
+      acc.x = fmaf(va.x, vb.x, acc.x); acc.y = fmaf(va.y, vb.y, acc.y);
+      acc.z = fmaf(va.z, vb.z, acc.z); acc.w = fmaf(va.w, vb.w, acc.w);
+    }
+  }
+  sm[qs][sub][cq] = acc;
+  __syncthreads();
+  if (sub == 0 && live) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float4 v = sm[qs][k][cq]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    *reinterpret_cast<float4*>(partial + ((int64_t)b * Q + q) * C + c4) = t;
   }
 }
 
@@ -178,21 +283,49 @@ McLayout mc_layout(const lfp_modconv* h, int B, int H, int W) {
   return L;
 }
 
+// the vector layout kernels need whole 4 x 4 blocks and 128-bit accesses on both sides
+bool layout_vec_ok(const void* a, const void* b, const void* scale, int C, int Cp, int64_t hw) {
+  return C % 4 == 0 && Cp % 16 == 0 && hw % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)scale) & 15) == 0 &&
+         getenv("LFP_MC_SCALAR_LAYOUT") == nullptr;
+}
 int launch_layout_in(const float* in, float* out, const float* scale, int B, int C, int Cp, int64_t hw, cudaStream_t s) {
+  if (layout_vec_ok(in, out, scale, C, Cp, hw)) {
+    if (Cp % 32 == 0) {
+      nchw_to_nhwc_vec_kernel<8><<<dim3((unsigned)ceil_div(hw, 8 * 16), (unsigned)B), 256, 0, s>>>(in, out, scale, C, Cp, hw);
+    } else {
+      nchw_to_nhwc_vec_kernel<4><<<dim3((unsigned)ceil_div(hw, 8 * 32), (unsigned)B), 256, 0, s>>>(in, out, scale, C, Cp, hw);
+    }
+    LFP_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)ceil_div(hw, 32), (unsigned)ceil_div(Cp, 32), (unsigned)B);
   nchw_to_nhwc_pad_kernel<<<grid, 256, 0, s>>>(in, out, scale, C, Cp, hw);
   LFP_LAUNCH_CHECK();
   return 0;
 }
 int launch_layout_out(const float* in, float* out, const float* scale, int B, int C, int Cp, int64_t hw, cudaStream_t s) {
+  if (layout_vec_ok(in, out, scale, C, Cp, hw)) {
+    if (Cp % 32 == 0) {
+      nhwc_to_nchw_vec_kernel<8><<<dim3((unsigned)ceil_div(hw, 8 * 16), (unsigned)B), 256, 0, s>>>(in, out, scale, C, Cp, hw);
+    } else {
+      nhwc_to_nchw_vec_kernel<4><<<dim3((unsigned)ceil_div(hw, 8 * 32), (unsigned)B), 256, 0, s>>>(in, out, scale, C, Cp, hw);
+    }
+    LFP_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)ceil_div(hw, 32), (unsigned)ceil_div(Cp, 32), (unsigned)B);
   nhwc_to_nchw_scale_kernel<<<grid, 256, 0, s>>>(in, out, scale, C, Cp, hw);
   LFP_LAUNCH_CHECK();
   return 0;
 }
 int launch_dot(const float* a, const float* b, float* partial, float* out, int B, int C, int64_t hw, int seglen, int Q, cudaStream_t s) {
-  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)Q, (unsigned)B);
-  dot_partial_kernel<<<grid, 256, 0, s>>>(a, b, partial, C, hw, seglen, Q);
+  if (C % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)partial) & 15) == 0 && getenv("LFP_MC_SCALAR_LAYOUT") == nullptr) {
+    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(Q, 4), (unsigned)B);
+    dot_partial_vec_kernel<<<grid, 256, 0, s>>>(a, b, partial, C, hw, seglen, Q);
+  } else {
+    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)Q, (unsigned)B);
+    dot_partial_kernel<<<grid, 256, 0, s>>>(a, b, partial, C, hw, seglen, Q);
+  }
   LFP_LAUNCH_CHECK();
   return launch_partial_reduce(partial, out, B, Q, C, C, s);
 }

@@ -2,7 +2,7 @@
 hot-path shapes, reported as algorithmic GB/s against the measured HBM peak, and model.ModulatedConv2d (native stand-alone
 layer, lfp_modconv_*) forward and forward+backward over 4-1024 px and batch 1-256, reported as TFLOP/s (2 Cin Cout 9 Hout^2
 plain, 2 Cin Cout 9 Hin^2 up; backward = data gradient, the same again) and as a fraction of max(tensor, HBM) bound.
-CUDA-event timed, L2 flushed between iterations.
+CUDA-event timed with the host running ahead of the device (see timeit), L2 flushed between iterations.
     python tools/op_microbench.py [--json out.json]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,6 +20,9 @@ dev = "cuda"
 
 
 def timeit(fn, iters=20, warm=3):
+    """Median device time of fn().  The GPU is kept busy (L2 flush + a ~1 ms spin kernel) while the host enqueues fn(), so
+    the two events bracket the kernels of fn() only; without the run-ahead every row under ~60 us measured the Python /
+    ctypes enqueue time instead of the kernel (round-2 tables before this change)."""
     torch.cuda.synchronize()
     for _ in range(warm):
         fn()
@@ -27,6 +30,7 @@ def timeit(fn, iters=20, warm=3):
     ts = []
     for _ in range(iters):
         flush.zero_()                      # evict L2 between iterations
+        torch.cuda._sleep(2_000_000)       # ~1 ms of device spin: the host runs ahead of the GPU
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -34,9 +38,22 @@ def timeit(fn, iters=20, warm=3):
     return ts[len(ts) // 2] * 1e-3
 
 
+def host_us(fn, iters=20):
+    """Host time of one call (enqueue only, no synchronisation inside the loop)."""
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fn()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    return (t1 - t0) / iters * 1e6
+
+
 rows = []
 k = torch.tensor([1., 3., 3., 1.], device=dev)
 k2 = (k[:, None] * k[None, :]) / 64
+k2x4 = k2 * 4          # the gain-4 kernel of Blur / Upsample, built once (not a launch inside the timed call)
 for (n, c, h) in [(1, 32, 1024), (8, 32, 1024), (8, 64, 512), (16, 512, 64), (64, 512, 16)]:
     x = torch.randn(n, c, h, h, device=dev)
     b = torch.randn(c, device=dev)
@@ -51,16 +68,16 @@ for (n, c, h) in [(1, 32, 1024), (8, 32, 1024), (8, 64, 512), (16, 512, 64), (64
     del xg, y, gy
     # Blur after the up-conv: [N,C,2H+1,2H+1] -> [N,C,2H,2H]  (src/model.py:75-91)
     xo = torch.randn(n, c, h + 1, h + 1, device=dev)
-    t = timeit(lambda: upfirdn2d(xo, k2 * 4, pad=(1, 1)))
+    t = timeit(lambda: upfirdn2d(xo, k2x4, pad=(1, 1)))
     rows.append(("upfirdn2d blur pad(1,1)", (n, c, h + 1, h + 1), 4 * (xo.numel() + numel), t))
-    t = timeit(lambda: upfirdn2d(x, k2 * 4, pad=(2, 2)))
+    t = timeit(lambda: upfirdn2d(x, k2x4, pad=(2, 2)))
     rows.append(("upfirdn2d blur-bwd pad(2,2)", (n, c, h, h), 4 * (xo.numel() + numel), t))
     del xo
     if h <= 512 or n == 1:
         t = timeit(lambda: upfirdn2d(x, k2, down=2, pad=(1, 1)))
         rows.append(("upfirdn2d down2 pad(1,1)", (n, c, h, h), 4 * (numel + numel // 4), t))
         xs = x[:, :, : h // 2, : h // 2].contiguous()
-        t = timeit(lambda: upfirdn2d(xs, k2 * 4, up=2, pad=(2, 1)))
+        t = timeit(lambda: upfirdn2d(xs, k2x4, up=2, pad=(2, 1)))
         rows.append(("upfirdn2d up2 pad(2,1)", (n, c, h // 2, h // 2), 4 * (numel + numel // 4), t))
         del xs
     del x
@@ -110,5 +127,14 @@ for name, shape, nbytes, t in rows:
     gbs = nbytes / t / 1e9
     print(f"{name:30s} {str(shape):24s} {t*1e3:8.3f} {gbs:8.0f} {gbs/PEAK:7.2f}")
     out.append({"op": name, "shape": list(shape), "ms": t * 1e3, "gbs": gbs, "frac_of_measured_hbm": gbs / PEAK})
+# host cost of one call of the public ops (what bounds a Python loop over small tensors)
+xs_ = torch.randn(1, 512, 16, 16, device=dev)
+bs_ = torch.randn(512, device=dev)
+m_ = ModulatedConv2d(512, 512, 3, 512).to(dev)
+m_.precision = capi.PREC_TF32
+st_ = torch.randn(1, 512, device=dev)
+host = {"upfirdn2d": host_us(lambda: upfirdn2d(xs_, k2x4, pad=(2, 2))), "fused_leaky_relu": host_us(lambda: fused_leaky_relu(xs_, bs_)),
+        "ModulatedConv2d.forward": host_us(lambda: m_(xs_, st_))}
+print("host enqueue time per call (us): " + ", ".join(f"{k} {v:.1f}" for k, v in host.items()))
 if len(sys.argv) > 2 and sys.argv[1] == "--json":
-    json.dump({"hbm_peak_gbs": PEAK, "tf32_peak_tflops": TC_PEAK, "rows": out, "modconv_rows": conv_out}, open(sys.argv[2], "w"), indent=1)
+    json.dump({"hbm_peak_gbs": PEAK, "tf32_peak_tflops": TC_PEAK, "rows": out, "modconv_rows": conv_out, "host_enqueue_us": host}, open(sys.argv[2], "w"), indent=1)
