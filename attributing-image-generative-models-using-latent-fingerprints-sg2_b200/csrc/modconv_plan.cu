@@ -473,6 +473,28 @@ extern "C" int lfp_modconv_forward(lfp_modconv* h, int batch, int in_h, int in_w
   } else {
     // stride-2 transposed conv as four sub-pixel phases into [B, 2H+1, 2W+1, Np] (src/model.py:269-279), then the Blur (:280-282)
     float* T = ws + L.T;
+    // up to 128 output channels (or an 8 px input): all four phases in one launch, as the synthesis plan does - the input tile
+    // is loaded and modulated once and every tap accumulates into its phase's TMEM accumulator (LFP_FUSE_PHASES=0: four launches)
+    static const bool fuse_off = getenv("LFP_FUSE_PHASES") != nullptr && atoi(getenv("LFP_FUSE_PHASES")) == 0;
+    const bool fuse_phases = use_tc && !fuse_off && H == W && (Np <= 128 || H <= 8);   // square: the configuration the plan runs
+    if (fuse_phases) {
+      TcConv q{};
+      q.in = x; q.in_planes = 1; q.in_h = H; q.in_w = W; q.in_bcast = false; q.mod = sm; q.wmap = h->map_fwd;
+      q.out = T; q.out_planes = 4; q.out_plane = 0; q.out_h = H + 1; q.out_w = W + 1; q.out_stride = 2;   // interleaved [2H+1, 2W+1]
+      q.batch = B; q.gh = H + 1; q.gw = W + 1; q.K = Kp; q.N = Np;
+      q.taps.ngroups = 1; q.taps.group_plane[0] = 0; q.taps.group_tap0[0] = 0; q.taps.nphase = 4;
+      int t = 0;
+      for (int a = 0; a < 2; ++a)
+        for (int bb = 0; bb < 2; ++bb)
+          for (int ky = a == 0 ? 0 : 1; ky < 3; ky += 2)
+            for (int kx = bb == 0 ? 0 : 1; kx < 3; kx += 2) {
+              q.taps.dy[t] = (signed char)(ky == 2 ? -1 : 0); q.taps.dx[t] = (signed char)(kx == 2 ? -1 : 0);
+              q.taps.widx[t] = (signed char)(ky * 3 + kx); q.taps.acc[t] = (signed char)(a * 2 + bb); ++t;
+            }
+      q.taps.group_tap0[1] = t;
+      q.epi = EPI_STORE;
+      LFP_TRY(launch_conv_tc(q, s));
+    } else
     for (int a = 0; a < 2; ++a)
       for (int bb = 0; bb < 2; ++bb) {
         ConvGeom g{};
