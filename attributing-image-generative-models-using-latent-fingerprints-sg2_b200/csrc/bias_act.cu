@@ -7,6 +7,8 @@
 // element loop (one plane = one (n, c) pair of step_b contiguous elements), 64-bit offsets, and
 // a grid sized in multiples of the SM count.  A scalar kernel handles ragged cases (rank-2
 // inputs where step_b == 1, misaligned pointers, step_b % vec != 0).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace lfp {
@@ -129,6 +131,58 @@ __global__ void __launch_bounds__(256) bias_act_plane_kernel(
   }
 }
 
+// ---- flat vector kernel: small planes (a plane is shorter than one CTA pass) ------------------
+// The plane kernel gives every plane its own CTA row; at 16 x 16 (64 vectors) three quarters of each CTA idle and the launch is
+// 32768 one-kilobyte CTAs (0.2 of the HBM rate at [64, 512, 16, 16]).  Here the tensor is one run of 16-byte vectors and the
+// bias index is recovered per vector (plane = i / vec_per_plane, one 32-bit division per 16 bytes where the reference divides
+// per element, src/op/fused_bias_act_kernel.cu:33-37).  Same per-element arithmetic as the other two kernels.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256) bias_act_flat_kernel(
+    const T* __restrict__ x, const T* __restrict__ bias, const T* __restrict__ ref,
+    T* __restrict__ out, int64_t total_vec, int64_t vec_per_plane, int64_t size_b, int code, float alpha_f,
+    float scale_f) {
+  using A = Arith<T>;
+  constexpr int N = Vec16<T>::N;
+  typename A::C alpha = A::ld((T)alpha_f), scale = A::ld((T)scale_f);
+  const bool use_bias = bias != nullptr, use_ref = ref != nullptr;
+  const bool small = total_vec < (1ll << 31);   // 32-bit divisions
+  const uint4* xp = reinterpret_cast<const uint4*>(x);
+  const uint4* rp = reinterpret_cast<const uint4*>(ref);
+  uint4* op = reinterpret_cast<uint4*>(out);
+  for (int64_t base = (int64_t)blockIdx.x * (256 * UNROLL); base < total_vec; base += (int64_t)gridDim.x * (256 * UNROLL)) {
+    uint4 xv[UNROLL], rv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < total_vec) {
+        xv[u] = __ldcs(xp + i);
+        if (use_ref) rv[u] = __ldcs(rp + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t i = base + u * 256 + threadIdx.x;
+      if (i < total_vec) {
+        typename A::C b = 0;
+        if (use_bias) {
+          const int64_t plane = small ? (int64_t)((uint32_t)i / (uint32_t)vec_per_plane) : i / vec_per_plane;
+          const int64_t c = small ? (int64_t)((uint32_t)plane % (uint32_t)size_b) : plane % size_b;
+          b = A::ld(bias[c]);
+        }
+        Vec16<T> a, r, o;
+        *reinterpret_cast<uint4*>(&a) = xv[u];
+        if (use_ref) *reinterpret_cast<uint4*>(&r) = rv[u];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          typename A::C rr = use_ref ? A::ld(r.v[k]) : (typename A::C)0;
+          o.v[k] = A::st(bias_act_one<T>(A::ld(a.v[k]), b, rr, code, alpha, scale, use_bias));
+        }
+        __stcs(op + i, *reinterpret_cast<uint4*>(&o));
+      }
+    }
+  }
+}
+
 template <typename T>
 static int bias_act_launch(const void* x_, const void* bias_, const void* ref_, void* out_,
                            int64_t size_x, int64_t step_b, int64_t size_b, int code, float alpha,
@@ -139,9 +193,19 @@ static int bias_act_launch(const void* x_, const void* bias_, const void* ref_, 
   T* out = (T*)out_;
   constexpr int N = Vec16<T>::N;
   auto aligned = [](const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
-  const bool planar = step_b >= 64 * N && step_b % N == 0 && size_x % step_b == 0 && aligned(x) &&
-                      aligned(ref) && aligned(out);
-  if (planar) {
+  constexpr int UNROLL_F = 4;
+  const bool vec_ok = step_b >= N && step_b % N == 0 && size_x % step_b == 0 && aligned(x) && aligned(ref) && aligned(out);
+  static const bool no_flat = getenv("LFP_BIAS_ACT_NO_FLAT") != nullptr;   // A/B switch: the first version's kernel choice
+  const bool flat = vec_ok && !no_flat && step_b / N < 256 * UNROLL_F && (size_b < (1ll << 31));
+  const bool planar = vec_ok && !flat && step_b >= 64 * N;
+  if (flat) {
+    const int64_t total_vec = size_x / N;
+    int64_t blocks = ceil_div(total_vec, 256 * UNROLL_F);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    bias_act_flat_kernel<T, UNROLL_F><<<(unsigned)blocks, 256, 0, stream>>>(x, bias, ref, out, total_vec, step_b / N,
+                                                                          bias ? size_b : 1, code, alpha, scale);
+  } else if (planar) {
     const int64_t planes = size_x / step_b;
     const int64_t vec_per_plane = step_b / N;
     constexpr int UNROLL = 4;

@@ -12,6 +12,8 @@
 //   * up = down = 1 (Blur and its adjoint): a shared-memory row ring filled by 1-D bulk copies (cp.async.bulk + mbarrier),
 //     consumed by warps that keep the partially summed output rows in registers - upfirdn2d_ring11_kernel;
 //   * up = 2 / down = 2: warp-streaming kernels without shared memory (a lane owns an output column, neighbours by shuffle);
+//   * many small planes (<= 34 x 34, e.g. the 4 ... 32 px layers at a large batch): runs of planes staged zero-haloed in
+//     shared memory, vertical register strips - upfirdn2d_planes_kernel;
 // everything else (minor > 1, big kernels, odd up/down, fp16/fp64) takes the direct kernel.
 // All indexing is 64-bit (the reference overflows at 2^31 elements).
 #include "common.cuh"
@@ -608,6 +610,219 @@ __global__ void __launch_bounds__(128) upfirdn2d_stream12_kernel(const float* __
   }
 }
 
+// ---- small planes: minor == 1, fp32, kernel <= 4x4, many planes of at most 34 x 34 samples -----------------------------
+// The ring / streaming kernels give a plane (pair) its own CTAs; on 8 x 8 ... 33 x 33 maps most lanes of a strip are idle and
+// the fixed per-CTA cost (barrier set-up, halo rows) dominates: 0.10-0.17 of the HBM rate at [64, 512, 16, 16]
+// (profiles/r02_op_microbench.txt).  Here a CTA stages a run of PL consecutive planes - one contiguous piece of the input - in
+// shared memory in a zero-haloed layout: row pitch in_w + 3 (the three zeros after a row are its right halo and the left halo
+// of the next row), three zero rows above and `bot` zero rows below every plane.  With the halo in place no tap needs a range
+// test: a thread produces a vertical strip of SP_R outputs from unpredicated shared-memory reads at immediate offsets, lanes
+// follow consecutive output columns (conflict-free reads, coalesced stores), work items are decoded with multiply-high
+// divisions.  A first version with range predicates and run-time divisions executed ~90 instructions per output and was
+// slower than the kernels it replaced on 64 px planes; this one is used up to 34 x 34.  Taps are summed in ascending (ty, tx)
+// order like every other kernel of this file; taps outside the kernel, on the zero halo or on stuffed zeros contribute + 0.
+constexpr int SP_R = 4;                 // output rows per thread strip
+constexpr int SP_HALO = 3;              // zero columns after every staged row, zero rows above every staged plane
+constexpr int SP_STAGE_FLOATS = 10240;  // staged (haloed) floats per CTA: 40 KB, several CTAs per SM overlap staging and arithmetic
+constexpr int SP_MAX_PLANE = 1200;      // samples of the larger of the input / output plane (34 x 34)
+
+struct SpDiv { uint64_t M; int s; };    // n / d = (n * M) >> (32 + s) for 0 <= n < 2^31 (M = ceil(2^(32+s) / d), s = ceil(log2 d))
+static inline SpDiv sp_make_div(int d) {
+  SpDiv f; f.s = 0;
+  while ((1ll << f.s) < d) ++f.s;
+  f.M = (uint64_t)((((unsigned __int128)1 << (32 + f.s)) + (unsigned)d - 1) / (unsigned)d);
+  return f;
+}
+__device__ __forceinline__ int sp_div(int n, const SpDiv& f) { return (int)(((uint64_t)(uint32_t)n * f.M) >> (32 + f.s)); }
+
+struct SpGeom {
+  int PL;       // planes per CTA
+  int Wp, PP;   // staged row pitch (in_w + 3) and plane pitch ((3 + in_h + bot) * Wp) in floats
+  int per_plane;  // work items per plane: ceil(out_h / SP_R) * out_w
+  SpDiv d_in_hw, d_in_w, d_per_plane, d_out_w;
+};
+
+// up = 1 (down = 1 or 2): rows j = 0 .. DOWN (R - 1) + 3 below the strip's first tap row feed output r with tap row ty = j - DOWN r
+template <int DOWN>
+__device__ __forceinline__ void sp_strip_down(const float* __restrict__ tap00, int Wp, const float (&k)[4][4], float (&acc)[SP_R]) {
+  constexpr int ROWS = DOWN * (SP_R - 1) + 4;
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    float v[4];
+#pragma unroll
+    for (int tx = 0; tx < 4; ++tx) v[tx] = tap00[j * Wp + tx];
+#pragma unroll
+    for (int r = 0; r < SP_R; ++r) {
+      const int ty = j - DOWN * r;   // compile-time after unrolling
+      if (ty >= 0 && ty < 4) {
+#pragma unroll
+        for (int tx = 0; tx < 4; ++tx) acc[r] = fmaf(v[tx], k[ty][tx], acc[r]);
+      }
+    }
+  }
+}
+
+// up = 2: output (oy, ox) meets samples only at the taps with (oy + ty - pad_y0) and (ox + tx - pad_x0) even: two tap rows
+// ty0, ty0 + 2 and two tap columns tx0, tx0 + 2.  PY = pad_y0 & 1 (the strip starts at a multiple of 4, so ty0 = (r + PY) & 1).
+template <int PY>
+__device__ __forceinline__ void sp_strip_up2(const float* __restrict__ plane, int Wp, const float (&k)[4][4], int oy0, int ox, int pad_x0,
+                                             int pad_y0, float (&acc)[SP_R]) {
+  const int tx0 = (ox + pad_x0) & 1;
+  const int ix0 = (ox + tx0 - pad_x0) >> 1;   // even numerator: exact, also below zero
+  float wa[4], wb[4];
+#pragma unroll
+  for (int ty = 0; ty < 4; ++ty) { wa[ty] = tx0 ? k[ty][1] : k[ty][0]; wb[ty] = tx0 ? k[ty][3] : k[ty][2]; }
+#pragma unroll
+  for (int r = 0; r < SP_R; ++r) {
+    const int ty0 = (r + PY) & 1;             // compile-time
+    const int iy0 = (oy0 + r + ty0 - pad_y0) >> 1;
+    const float* q = plane + iy0 * Wp + ix0;
+    float a = fmaf(q[0], wa[ty0], 0.f);
+    a = fmaf(q[1], wb[ty0], a);
+    a = fmaf(q[Wp], wa[ty0 + 2], a);
+    acc[r] = fmaf(q[Wp + 1], wb[ty0 + 2], a);
+  }
+}
+
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(256) upfirdn2d_planes_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                               float* __restrict__ out, UpfirdnParams p, SpGeom g) {
+  extern __shared__ __align__(16) float sp_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t p0 = (int64_t)blockIdx.x * g.PL;
+  const int npl = (int)(p.major - p0 < g.PL ? p.major - p0 : g.PL);
+  // 1. zero the staged run (halo included).  The run starts 4 floats into the buffer: the top-left taps of the first plane
+  // reach up to 3 floats before its first halo row.
+  float* const run = sp_smem + 4;
+  {
+    float4* z = reinterpret_cast<float4*>(sp_smem);
+    const int nz = ((npl * g.PP + 3) >> 2) + 1;
+    for (int i = threadIdx.x; i < nz; i += 256) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float k[4][4];
+  load_flipped_taps(kernel, p, k);
+  __syncthreads();
+  // 2. the planes of a run are one contiguous piece of global memory: 128-bit loads, eight in flight per thread (a first
+  // version copied row by row, one 68-byte request per warp and round trip, and spent its time waiting: 49 us for 67 MB), then
+  // every element is scattered to its place in the haloed layout (element e of the run -> plane, row, column by multiply-high)
+  {
+    const int in_hw = p.in_h * p.in_w;
+    const int n = npl * in_hw;
+    const float* src = in + p0 * in_hw;
+    auto place = [&](int e, float v) {
+      const int pl = sp_div(e, g.d_in_hw);
+      const int rem = e - pl * in_hw;
+      const int r = sp_div(rem, g.d_in_w);
+      run[pl * g.PP + (r + SP_HALO) * g.Wp + (rem - r * p.in_w)] = v;
+    };
+    const int mis = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    const int head = n < ((4 - mis) & 3) ? n : ((4 - mis) & 3);   // scalar elements before the first aligned vector
+    const int nvec = (n - head) >> 2;
+    if ((int)threadIdx.x < head) place(threadIdx.x, __ldg(src + threadIdx.x));
+    for (int e = head + 4 * nvec + threadIdx.x; e < n; e += 256) place(e, __ldg(src + e));
+    const float4* s4 = reinterpret_cast<const float4*>(src + head);
+    constexpr int U = 8;
+    for (int base = 0; base < nvec; base += 256 * U) {
+      float4 buf[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * 256 + threadIdx.x;
+        if (i < nvec) buf[u] = ldg_stream(s4 + i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = base + u * 256 + threadIdx.x;
+        if (i < nvec) {
+          // first element by division, the other three by stepping (row / plane wraps)
+          const int e = head + 4 * i;
+          const int pl = sp_div(e, g.d_in_hw);
+          const int rem = e - pl * in_hw;
+          int r = sp_div(rem, g.d_in_w);
+          int c = rem - r * p.in_w;
+          float* d = run + pl * g.PP + (r + SP_HALO) * g.Wp + c;
+          const float v4[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *d = v4[q];
+            ++d; ++c;
+            if (c == p.in_w) {
+              c = 0; d += SP_HALO; ++r;
+              if (r == p.in_h) { r = 0; d += g.PP - p.in_h * g.Wp; }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // 3. strips
+  const int out_hw = p.out_h * p.out_w;
+  const int items = npl * g.per_plane;
+  for (int it = threadIdx.x; it < items; it += 256) {
+    const int pli = sp_div(it, g.d_per_plane);
+    const int rem = it - pli * g.per_plane;
+    const int sy = sp_div(rem, g.d_out_w), ox = rem - sy * p.out_w;
+    const int oy0 = sy * SP_R;
+    const float* plane = run + pli * g.PP + SP_HALO * g.Wp;   // sample (0, 0) of the staged plane
+    float acc[SP_R];
+#pragma unroll
+    for (int r = 0; r < SP_R; ++r) acc[r] = 0.f;
+    if (UP == 2) {
+      if (p.pad_y0 & 1) sp_strip_up2<1>(plane, g.Wp, k, oy0, ox, p.pad_x0, p.pad_y0, acc);
+      else sp_strip_up2<0>(plane, g.Wp, k, oy0, ox, p.pad_x0, p.pad_y0, acc);
+    } else {
+      sp_strip_down<DOWN>(plane + (DOWN * oy0 - p.pad_y0) * g.Wp + (DOWN * ox - p.pad_x0), g.Wp, k, acc);
+    }
+    float* o = out + (p0 + pli) * out_hw + (int64_t)oy0 * p.out_w + ox;
+#pragma unroll
+    for (int r = 0; r < SP_R; ++r)
+      if (oy0 + r < p.out_h) o[r * p.out_w] = acc[r];
+  }
+}
+
+// The zero-haloed layout serves pads of 0 .. 3 whose taps stay within three samples of the plane; anything else (crops, wide
+// pads) stays with the other kernels.  Returns false when the configuration does not qualify.
+static bool upfirdn_planes_geom(int up, int down, const UpfirdnParams& p, SpGeom& g) {
+  if (p.pad_x0 < 0 || p.pad_x0 > SP_HALO || p.pad_y0 < 0 || p.pad_y0 > SP_HALO) return false;
+  const int nstrip = (p.out_h + SP_R - 1) / SP_R;
+  int max_ix, max_iy;   // last staged column / row any tap of any strip (whole strips, also past out_h) reads
+  if (up == 2) {
+    max_ix = (p.out_w - 1 + 3 - p.pad_x0) >> 1;
+    max_iy = ((nstrip * SP_R - 1 + 3 - p.pad_y0) >> 1) + 1;   // + 1: the second tap row is read unconditionally
+    max_ix += 1;
+  } else {
+    max_ix = down * (p.out_w - 1) + 3 - p.pad_x0;
+    max_iy = down * (nstrip * SP_R - 1) + 3 - p.pad_y0;
+  }
+  if (max_ix > p.in_w - 1 + SP_HALO) return false;
+  int bot = max_iy - (p.in_h - 1);
+  if (bot < SP_HALO) bot = SP_HALO;
+  if (bot > 16) return false;
+  g.Wp = p.in_w + SP_HALO;
+  g.PP = (SP_HALO + p.in_h + bot) * g.Wp;
+  if (g.PP > SP_STAGE_FLOATS) return false;
+  static const int stage = getenv("LFP_SP_STAGE") ? atoi(getenv("LFP_SP_STAGE")) : SP_STAGE_FLOATS;   // tuning switch (floats, <= 10240)
+  int64_t PL = (stage < SP_STAGE_FLOATS ? stage : SP_STAGE_FLOATS) / g.PP;
+  const int64_t spread = ceil_div(p.major, (int64_t)num_sms() * 4);   // enough CTAs for every SM before the runs get long
+  if (PL > spread) PL = spread;
+  if (PL < 1) PL = 1;
+  g.PL = (int)PL;
+  g.per_plane = nstrip * p.out_w;
+  g.d_in_hw = sp_make_div(p.in_h * p.in_w); g.d_in_w = sp_make_div(p.in_w); g.d_per_plane = sp_make_div(g.per_plane); g.d_out_w = sp_make_div(p.out_w);
+  return true;
+}
+
+static int upfirdn_planes_launch(int up, int down, const float* in, const float* kernel, float* out, const UpfirdnParams& p,
+                                 const SpGeom& g, cudaStream_t s) {
+  const int64_t blocks = ceil_div(p.major, g.PL);
+  const size_t smem = ((size_t)g.PL * g.PP + 12) * sizeof(float);
+  if (up == 2) upfirdn2d_planes_kernel<2, 1><<<(unsigned)blocks, 256, smem, s>>>(in, kernel, out, p, g);
+  else if (down == 2) upfirdn2d_planes_kernel<1, 2><<<(unsigned)blocks, 256, smem, s>>>(in, kernel, out, p, g);
+  else upfirdn2d_planes_kernel<1, 1><<<(unsigned)blocks, 256, smem, s>>>(in, kernel, out, p, g);
+  LFP_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T>
 static int upfirdn_direct_launch(const void* in, const void* kernel, void* out, const UpfirdnParams& p,
                                  cudaStream_t s) {
@@ -694,6 +909,13 @@ int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dty
   // 16-byte multiples
   static const bool no_ring = getenv("LFP_FIR_NO_RING") && atoi(getenv("LFP_FIR_NO_RING")) != 0;
   const bool fast = allow_tiled && dtype == LFP_F32 && minor == 1 && small_fir && p.out_h < (1 << 30) / 2;
+  static const bool no_planes = getenv("LFP_FIR_NO_PLANES") && atoi(getenv("LFP_FIR_NO_PLANES")) != 0;   // A/B switch
+  if (fast && !no_planes && ((up_x == 1 && down_x == 1) || (up_x == 2 && down_x == 1) || (up_x == 1 && down_x == 2)) &&
+      (int64_t)in_h * in_w <= SP_MAX_PLANE && (int64_t)p.out_h * p.out_w <= SP_MAX_PLANE && major >= 32 && major < (1ll << 31)) {
+    SpGeom g;
+    if (upfirdn_planes_geom(up_x, down_x, p, g))
+      return upfirdn_planes_launch(up_x, down_x, (const float*)input, (const float*)kernel, (float*)out, p, g, s);
+  }
   if (fast && !no_ring && up_x == 1 && down_x == 1 && p.out_w >= 16 && p.out_h >= 8 && (reinterpret_cast<uintptr_t>(input) & 15) == 0 &&
       ((major * in_h * (int64_t)in_w) & 3) == 0 && (int64_t)p.out_h * p.out_w < (1ll << 31) && (int64_t)in_h * in_w < (1ll << 31))
     return upfirdn_ring_launch((const float*)input, (const float*)kernel, (float*)out, p, s);

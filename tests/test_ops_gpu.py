@@ -44,6 +44,28 @@ HOT = [  # the configurations the synthesis path hits, at sizes 
     ("ring_crop", (1, 4, 96, 200), 1, 1, (-1, 4)),
     ("ring_narrow", (4, 8, 17, 17), 1, 1, (1, 1)),     # 2-warp segments
     ("ring_mid", (2, 4, 65, 100), 1, 1, (2, 2)),       # 4-warp segments, one short band
+    # the small-plane kernel (>= 32 planes of at most 34 x 34 samples, pads 0..3; runs of planes staged zero-haloed in shared
+    # memory): every up / down mode, odd plane sizes, every pad, a last run shorter than the others; the crops and the larger
+    # planes of this block fall through to the ring / streaming kernels
+    ("planes_blur17", (8, 8, 17, 17), 1, 1, (1, 1)),
+    ("planes_bwd16", (8, 8, 16, 16), 1, 1, (2, 2)),
+    ("planes_up8", (4, 16, 8, 8), 2, 1, (2, 1)),
+    ("planes_down16", (4, 16, 16, 16), 1, 2, (1, 1)),
+    ("planes_blur33", (2, 16, 33, 33), 1, 1, (1, 1)),
+    ("planes_down32", (33, 1, 32, 32), 1, 2, (1, 1)),
+    ("planes_up16", (33, 1, 16, 16), 2, 1, (2, 1)),
+    ("planes_up_odd", (3, 11, 7, 5), 2, 1, (2, 1)),
+    ("planes_down_odd", (3, 11, 11, 9), 1, 2, (1, 1)),
+    ("planes_up_pad3", (33, 1, 7, 9), 2, 1, (3, 3)),
+    ("planes_down_pad0", (33, 1, 7, 9), 1, 2, (0, 0)),
+    ("planes_pad3", (33, 1, 7, 9), 1, 1, (3, 3)),
+    ("planes_up_pad4", (33, 1, 5, 6), 2, 1, (1, 2, 3, 0)),
+    ("planes_many", (700, 1, 5, 3), 2, 1, (0, 3, 1, 2)),
+    ("planes_one_px", (33, 1, 1, 1), 2, 1, (2, 1)),
+    ("fallback_blur65", (2, 20, 65, 65), 1, 1, (1, 1)),
+    ("fallback_up33", (2, 16, 33, 33), 2, 1, (2, 1)),
+    ("fallback_crop", (5, 9, 9, 13), 1, 1, (-1, 4)),
+    ("fallback_pad4", (37, 1, 10, 12), 1, 2, (0, 2, 3, -1)),
 ]
 
 

@@ -41,6 +41,8 @@ def timeit(fn, iters=20, warm=3):
 def host_us(fn, iters=20):
     """Host time of one call (enqueue only, no synchronisation inside the loop)."""
     import time
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(iters):
@@ -92,7 +94,7 @@ conv_rows = []
 LAYERS = [(512, 512, 4, False), (512, 512, 8, True), (512, 512, 16, False), (512, 512, 32, True), (512, 512, 64, False),
           (512, 256, 128, True), (256, 256, 128, False), (256, 128, 256, True), (128, 128, 256, False), (128, 64, 512, True),
           (64, 64, 512, False), (64, 32, 1024, True), (32, 32, 1024, False)]
-for (cin, cout, res, up) in LAYERS:
+for (cin, cout, res, up) in ([] if os.environ.get("OPMB_SKIP_MODCONV") else LAYERS):   # OPMB_SKIP_MODCONV=1: FIR / bias-act rows only
     m = ModulatedConv2d(cin, cout, 3, 512, upsample=up).to(dev)
     m.precision = capi.PREC_TF32
     hin = res // 2 if up else res
