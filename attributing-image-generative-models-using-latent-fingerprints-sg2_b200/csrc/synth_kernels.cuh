@@ -188,6 +188,8 @@ int launch_nhwc_to_nchw(const float* in, float* out, int batch, int C, int hw, c
 int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dtype, int64_t major,
                        int in_h, int in_w, int64_t minor, int kh, int kw, int up_x, int up_y,
                        int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                       cudaStream_t s, bool allow_tiled);
+                       cudaStream_t s, bool allow_tiled, bool allow_planes = true);
+// allow_planes = false keeps the kernel choice independent of the plane count (the synthesis plan's skip-gradient FIRs: a
+// trajectory's bits must not depend on what shares its batch)
 
 }  // namespace lfp

@@ -781,7 +781,7 @@ extern "C" int lfp_synth_backward(lfp_synth* h, int batch, const float* d_image,
     // fused epilogue below needs it at this layer's input resolution
     if (c.up) {
       float* nd = dskips[dcur];
-      LFP_TRY(upfirdn2d_dispatch(dskip, h->fir + 48, nd, LFP_F32, (int64_t)B * 3, c.res_out, c.res_out, 1, 4, 4, 1, 1, 2, 2, 1, 1, 1, 1, s, true));
+      LFP_TRY(upfirdn2d_dispatch(dskip, h->fir + 48, nd, LFP_F32, (int64_t)B * 3, c.res_out, c.res_out, 1, 4, 4, 1, 1, 2, 2, 1, 1, 1, 1, s, true, false));
       dskip = nd;
       dcur ^= 1;
     }

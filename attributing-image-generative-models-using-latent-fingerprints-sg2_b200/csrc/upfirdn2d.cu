@@ -896,7 +896,7 @@ static int upfirdn_ring_launch(const float* in, const float* kernel, float* out,
 int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dtype, int64_t major,
                        int in_h, int in_w, int64_t minor, int kh, int kw, int up_x, int up_y,
                        int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
-                       cudaStream_t s, bool allow_tiled) {
+                       cudaStream_t s, bool allow_tiled, bool allow_planes) {
   UpfirdnParams p;
   p.major = major; p.minor = minor; p.in_h = in_h; p.in_w = in_w; p.kh = kh; p.kw = kw;
   p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y;
@@ -910,7 +910,7 @@ int upfirdn2d_dispatch(const void* input, const void* kernel, void* out, int dty
   static const bool no_ring = getenv("LFP_FIR_NO_RING") && atoi(getenv("LFP_FIR_NO_RING")) != 0;
   const bool fast = allow_tiled && dtype == LFP_F32 && minor == 1 && small_fir && p.out_h < (1 << 30) / 2;
   static const bool no_planes = getenv("LFP_FIR_NO_PLANES") && atoi(getenv("LFP_FIR_NO_PLANES")) != 0;   // A/B switch
-  if (fast && !no_planes && ((up_x == 1 && down_x == 1) || (up_x == 2 && down_x == 1) || (up_x == 1 && down_x == 2)) &&
+  if (fast && allow_planes && !no_planes && ((up_x == 1 && down_x == 1) || (up_x == 2 && down_x == 1) || (up_x == 1 && down_x == 2)) &&
       (int64_t)in_h * in_w <= SP_MAX_PLANE && (int64_t)p.out_h * p.out_w <= SP_MAX_PLANE && major >= 32 && major < (1ll << 31)) {
     SpGeom g;
     if (upfirdn_planes_geom(up_x, down_x, p, g))
@@ -955,7 +955,7 @@ extern "C" int lfp_upfirdn2d(const void* input, const void* kernel, void* out, i
   LFP_CHECK_ARG(major >= 0 && minor >= 0, "upfirdn2d: negative extent");
   if (major * minor * in_h * in_w != 0) LFP_CHECK_ARG(input && kernel && out, "upfirdn2d: null pointer");
   return upfirdn2d_dispatch(input, kernel, out, dtype, major, in_h, in_w, minor, kh, kw, up_x, up_y,
-                            down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, (cudaStream_t)stream, true);
+                            down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, (cudaStream_t)stream, true, true);
 }
 
 extern "C" int lfp_upfirdn2d_host(const void* input, const void* kernel, void* out, int dtype,
