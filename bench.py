@@ -375,7 +375,8 @@ def run_ours(args):
     e2e = {"value": world * B * e2e_steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": state_bytes,
            "d2h_bytes_per_step": state_bytes + B * 4, "steps": e2e_steps,
            "note": "AttributionEngine.step_host: alpha, key logits and Adam moments H2D from pinned memory, full step "
-                   "(embed, synthesis fwd, MSE, synthesis bwd, Adam), state + loss D2H, synchronous, every step"}
+                   f"(embed, synthesis fwd, {loss_kind.upper()} loss fwd + bwd, synthesis bwd, Adam), state + loss D2H, synchronous, "
+                   "every step"}
 
     # ---- roofline pass: per-launch CUDA events, outside every timed region ----
     L = capi.lib()
