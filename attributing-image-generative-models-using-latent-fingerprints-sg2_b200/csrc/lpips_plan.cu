@@ -28,21 +28,27 @@ static const int kVggLevel[13] = {0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};       
 static const int kVggFeat[13] = {0, 2, 5, 7, 10, 12, 14, 17, 19, 21, 24, 26, 28};   // torchvision features index
 static const int kTapConv[5] = {1, 3, 6, 9, 12};                                 // relu1_2, relu2_2, relu3_3, relu4_3, relu5_3
 
-// NCHW [B, 3, hw] image -> NHWC [B, hw, 32]: (x - shift) / scale in channels 0..2 (networks_basic.py:93-100), zeros above
-__global__ void __launch_bounds__(256) lpips_prep_kernel(const float* __restrict__ img, float* __restrict__ out, int64_t hw, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;   // over B * hw * 8 float4
-  if (i >= n) return;
-  const int q = (int)(i & 7);
-  const int64_t bp = i >> 3;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (q == 0) {
-    const int64_t b = bp / hw, p = bp - b * hw;
-    const float* s = img + b * 3 * hw + p;
-    v.x = (s[0] - (-.030f)) / .458f;
-    v.y = (s[hw] - (-.088f)) / .448f;
-    v.z = (s[2 * hw] - (-.188f)) / .450f;
+// NCHW [B, 3, hw] image -> NHWC [B, hw, 32]: (x - shift) / scale in channels 0..2 (networks_basic.py:93-100), zeros above.
+// One warp per 32 consecutive pixels (hw is a multiple of 256, so a group never straddles two samples): three coalesced loads,
+// then eight 512-byte stores whose first-channel values come from the owning lane by shuffle.  The first version gave every
+// 16-byte piece its own thread with the loads on every eighth lane: 1.18 ms for 2.7 GB written at 1024 px, B = 20.
+__global__ void __launch_bounds__(256) lpips_prep_kernel(const float* __restrict__ img, float* __restrict__ out, int64_t hw, int64_t npix) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;   // over B * hw
+  if (p0 >= npix) return;
+  const int64_t b = p0 / hw, p = p0 - b * hw + lane;
+  const float* s = img + b * 3 * hw + p;
+  const float x = (s[0] - (-.030f)) / .458f;
+  const float y = (s[hw] - (-.088f)) / .448f;
+  const float z = (s[2 * hw] - (-.188f)) / .450f;
+  float4* o = reinterpret_cast<float4*>(out) + p0 * 8 + lane;
+  const int q = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int src = 4 * j + (lane >> 3);
+    const float vx = __shfl_sync(0xffffffffu, x, src), vy = __shfl_sync(0xffffffffu, y, src), vz = __shfl_sync(0xffffffffu, z, src);
+    o[j * 32] = q == 0 ? make_float4(vx, vy, vz, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  reinterpret_cast<float4*>(out)[i] = v;
 }
 // gradient back through the scaling layer: d_img[b, c, p] = D[b, p, c] / scale_c
 __global__ void __launch_bounds__(256) lpips_unprep_kernel(const float* __restrict__ D, float* __restrict__ d_img, int64_t hw, int64_t n) {
@@ -102,11 +108,15 @@ template <bool UP, int LPW, int NJ>
 __global__ void __launch_bounds__(256) tap_backward_kernel(const float* __restrict__ f, const float* __restrict__ t, int64_t t_bstride,
                                                            const float* __restrict__ lin, const float* __restrict__ up,
                                                            float* __restrict__ G, float* __restrict__ partial, int H, int W, int C,
-                                                           float inv_hw, int64_t nwin_per) {
+                                                           float inv_hw, int64_t nwin_per, int batch) {
   constexpr int WPW = 32 / LPW;   // windows per warp
   const int lane = threadIdx.x & 31, li = lane % LPW;
-  const int64_t win = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * WPW + lane / LPW;
-  const int b = blockIdx.y;
+  // The sample is the fastest-varying part of the block index: the CTAs that work on the same windows of the batch's samples
+  // run together, so a target shared by the batch (t_bstride = 0, the attribution loop) comes from HBM once and from L2 for the
+  // other samples.  With the sample as grid.y every sample re-read the whole cached tap from HBM (268 MB per sample at the
+  // 1024 px tap: 5.4 GB of the 17.5 GB that launch moved at B = 20, ncu launch list of profiles/r02_lpips_launches.md).
+  const int b = (int)(blockIdx.x % (unsigned)batch);
+  const int64_t win = ((int64_t)(blockIdx.x / (unsigned)batch) * 8 + (threadIdx.x >> 5)) * WPW + lane / LPW;
   const bool live = win < nwin_per;            // (a dead half-warp still takes part in the shuffles)
   const int W2 = W / 2;
   const int64_t wc = live ? win : 0;
@@ -207,8 +217,9 @@ static int launch_tap_backward(const float* f, const float* t, int64_t tstride, 
   const float inv_hw = 1.f / (float)((int64_t)H * W);
 #define LFP_TAP(LPW, NJ)                                                                                          \
   {                                                                                                               \
-    dim3 grid((unsigned)ceil_div(nwin, (int64_t)8 * (32 / LPW)), (unsigned)batch);                                 \
-    tap_backward_kernel<UP, LPW, NJ><<<grid, 256, 0, s>>>(f, t, tstride, lin, up, G, partial, H, W, C, inv_hw, nwin); \
+    const int64_t nblk = ceil_div(nwin, (int64_t)8 * (32 / LPW)) * batch;                                          \
+    LFP_CHECK_ARG(nblk < (1ll << 31), "lpips: too many windows");                                                 \
+    tap_backward_kernel<UP, LPW, NJ><<<(unsigned)nblk, 256, 0, s>>>(f, t, tstride, lin, up, G, partial, H, W, C, inv_hw, nwin, batch); \
   }
   switch (C) {
     case 64: LFP_TAP(16, 1) break;
@@ -316,8 +327,8 @@ int vgg_conv(const lfp_lpips* h, int c, const float* in, float* out, int B, int 
 // VGG16 forward: fills L.act[0..12] from the NCHW image
 int vgg_forward(const lfp_lpips* h, int B, const float* img, float* ws, const LpLayout& L, int precision, cudaStream_t s) {
   const int64_t hw = (int64_t)h->H * h->W;
-  const int64_t n0 = (int64_t)B * hw * 8;
-  lpips_prep_kernel<<<(unsigned)ceil_div(n0, 256), 256, 0, s>>>(img, ws + L.x0, hw, n0);
+  const int64_t npix = (int64_t)B * hw;   // a CTA converts 256 pixels
+  lpips_prep_kernel<<<(unsigned)ceil_div(npix, 256), 256, 0, s>>>(img, ws + L.x0, hw, npix);
   LFP_LAUNCH_CHECK();
   const float* x = ws + L.x0;
   for (int c = 0; c < 13; ++c) {
