@@ -284,9 +284,12 @@ McLayout mc_layout(const lfp_modconv* h, int B, int H, int W) {
 }
 
 // the vector layout kernels need whole 4 x 4 blocks and 128-bit accesses on both sides
+bool scalar_layout_forced() {   // A/B switch, read once
+  static const bool v = getenv("LFP_MC_SCALAR_LAYOUT") != nullptr;
+  return v;
+}
 bool layout_vec_ok(const void* a, const void* b, const void* scale, int C, int Cp, int64_t hw) {
-  return C % 4 == 0 && Cp % 16 == 0 && hw % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)scale) & 15) == 0 &&
-         getenv("LFP_MC_SCALAR_LAYOUT") == nullptr;
+  return C % 4 == 0 && Cp % 16 == 0 && hw % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)scale) & 15) == 0 && !scalar_layout_forced();
 }
 int launch_layout_in(const float* in, float* out, const float* scale, int B, int C, int Cp, int64_t hw, cudaStream_t s) {
   if (layout_vec_ok(in, out, scale, C, Cp, hw)) {
@@ -319,7 +322,7 @@ int launch_layout_out(const float* in, float* out, const float* scale, int B, in
   return 0;
 }
 int launch_dot(const float* a, const float* b, float* partial, float* out, int B, int C, int64_t hw, int seglen, int Q, cudaStream_t s) {
-  if (C % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)partial) & 15) == 0 && getenv("LFP_MC_SCALAR_LAYOUT") == nullptr) {
+  if (C % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)partial) & 15) == 0 && !scalar_layout_forced()) {
     dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(Q, 4), (unsigned)B);
     dot_partial_vec_kernel<<<grid, 256, 0, s>>>(a, b, partial, C, hw, seglen, Q);
   } else {
