@@ -124,6 +124,8 @@ for name, B, flops, nbytes, t_f, t_fb in conv_rows:
     conv_out.append({"op": name, "batch": B, "fwd_ms": t_f * 1e3, "fwd_tflops": flops / t_f / 1e12, "fwd_frac_of_bound": bound / t_f,
                      "fwd_bwd_ms": t_fb * 1e3, "fwd_bwd_tflops": 2 * flops / t_fb / 1e12})
 out = []
+print("# FIR / bias-act rows: algorithmic bytes / device time against the measured HBM copy rate; tensors under ~60 MB (the 16 px rows)\n"
+      "# leave their output in the 126 MB L2, so their fraction measures launch ramp and on-chip work, not DRAM")
 print(f"{'op':30s} {'shape':24s} {'ms':>8s} {'GB/s':>8s} {'of HBM':>7s}")
 for name, shape, nbytes, t in rows:
     gbs = nbytes / t / 1e9
